@@ -1,0 +1,172 @@
+/*
+ * sa_engine.h -- C-ABI of the B200 spectral engine (libsa_engine.so).
+ *
+ * Drop-in boundary for the ONE hot path of GassiusODude/spectral_analyzer: the three Spring
+ * @Service bodies and one static JDSP call that today run on the JVM
+ * (S/ = src/main/java/net/kcundercover/spectral_analyzer/ in the reference):
+ *
+ *   SpectralService.computeMagnitudes(MappedByteBuffer,int,int,String)            S/services/SpectralService.java:33
+ *   frame loop of MainController.updateDisplay                                    S/controllers/MainController.java:980-999
+ *   renderSpectrogram / getColorForMagnitude                                      S/controllers/MainController.java:1261-1291, :926-957
+ *   ExtractDownConvertService.extractAndDownConvert(..)                           S/services/ExtractDownConvertService.java:34,54
+ *   AsyncExtractDownConvertService.extractAndDownConvertAsync(..)                 S/services/AsyncExtractDownConvertService.java:48
+ *   PowerSpectralDensity.calculatePsdWelch(double[][],double,int) [JDSP] call     S/controllers/AnalysisDialogController.java:308-312
+ *
+ * The reference has no FFI today; these are the symbols a Java 21 Panama (java.lang.foreign)
+ * binding would look up (INTEGRATION.md shows that binding).  Plain pointers and sizes only,
+ * no callbacks, no global state; every call returns an int32 status (0 = ok) and
+ * sa_last_error() returns a thread-local message.  All entry points are re-entrant: calls
+ * on one engine serialise on an internal lock, different engines run concurrently.
+ * There is NO CPU fallback: without a CUDA device sa_engine_create fails with SA_ERR_NO_DEVICE.
+ */
+#ifndef SA_ENGINE_H
+#define SA_ENGINE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SA_API __attribute__((visibility("default")))
+
+typedef struct sa_engine sa_engine;
+
+/* status codes */
+enum {
+    SA_OK = 0,
+    SA_ERR_INVALID_ARG = 1,   /* null pointer, nfft not a power of two (commons-math throws), bad enum */
+    SA_ERR_UNSUPPORTED = 2,   /* valid request this build has no kernel for */
+    SA_ERR_OUT_OF_RANGE = 3,  /* read past the end of the buffer (IndexOutOfBoundsException in Java) */
+    SA_ERR_CUDA = 4,
+    SA_ERR_NO_DEVICE = 5,
+    SA_ERR_OOM = 6,
+    SA_ERR_SMALL_OUTPUT = 7
+};
+
+/* SigMF core:datatype families (S/sigmf/Global.java:67-79) */
+enum { SA_CF32 = 0, SA_CI16 = 1, SA_CU8 = 2, SA_CI8 = 3, SA_CF64 = 4 };
+/* windows, periodic (DFT-even) definitions; the reference spectrogram is SA_WIN_RECT */
+enum { SA_WIN_RECT = 0, SA_WIN_HANN = 1, SA_WIN_HAMMING = 2, SA_WIN_BLACKMAN = 3, SA_WIN_BLACKMAN_HARRIS = 4 };
+/* dB scaling: MAG_1E10 is the reference, 20*log10(|X| + 1e-10) (SpectralService.java:80-81) */
+enum { SA_DB_MAG_1E10 = 0, SA_DB_POWER = 1 /* 10*log10(|X|^2 + 1e-20) */ };
+/* output element kinds */
+enum { SA_OUT_F32_DB = 0, SA_OUT_F64_DB = 1, SA_OUT_RGBA8 = 2 };
+/* arithmetic: F32 kernels (default) or the FP64 path (mandatory for cf64 input) */
+enum { SA_PREC_AUTO = 0, SA_PREC_F32 = 1, SA_PREC_F64 = 2 };
+/* colormaps of getColorForMagnitude (MainController.java:939-956) */
+enum { SA_CMAP_GRAYSCALE = 0, SA_CMAP_HEATMAP = 1 };
+
+/* Batched spectrogram request: replaces the per-frame loop MainController.java:982-999.
+ * Frame t covers samples [start_sample + t*hop, +nfft) of the buffer; a frame that would
+ * read past the end of the buffer becomes a row of eof_fill_db (-150.0 in the reference,
+ * :994-998).  Row layout: out[t][(k + nfft/2) % nfft] (fft-shifted, SpectralService.java:78).
+ * Reference parity mode = {window RECT, hop nfft, db_mode MAG_1E10}. */
+typedef struct sa_spectrogram_params {
+    uint32_t struct_size;   /* sizeof(sa_spectrogram_params), for forward compatibility */
+    int32_t  dtype;         /* SA_CF32.. */
+    int32_t  big_endian;    /* 0: "_le" datatypes; 1 otherwise (S/sigmf/SigMfHelper.java:87-91) */
+    int32_t  window;        /* SA_WIN_* */
+    uint32_t nfft;          /* power of two, 64..65536 (main-scene.fxml:129) */
+    int32_t  db_mode;       /* SA_DB_* */
+    int32_t  out_kind;      /* SA_OUT_* */
+    int32_t  precision;     /* SA_PREC_* */
+    uint64_t start_sample;  /* currentSampleOffset (MainController.java:984) */
+    uint64_t hop;           /* samples between frame starts; the reference uses nfft */
+    uint64_t n_frames;      /* canvasW in the reference */
+    double   eof_fill_db;   /* -150.0 (MainController.java:996-997) */
+    /* only for SA_OUT_RGBA8: renderSpectrogram's dB/Hz conversion and colour ramp */
+    int32_t  colormap;      /* SA_CMAP_* */
+    int32_t  reserved0;
+    double   sample_rate;   /* fs: conversion = 10*log10(fs/nfft) + 20*log10(nfft) (:1273-1274) */
+    double   min_db;        /* -160 default (main-scene.fxml:143) */
+    double   max_db;        /* -30 default  (main-scene.fxml:150) */
+} sa_spectrogram_params;
+
+/* One annotation of the batched downconvert(+PSD) call; replaces one iteration of
+ * AnnotationController.java:321-360 / one MainController.handleAnalyzeSelection (:684-751). */
+typedef struct sa_annotation {
+    uint64_t start_sample;  /* targetStart */
+    uint64_t count;         /* targetWidth, samples to extract */
+    double   freq_off;      /* cycles/sample = (annotation centre - capture fc)/fs (:703,:744) */
+    int32_t  down;          /* floor(fs/bw), >= 1 (:721-728) */
+    int32_t  fast;          /* 0 conventional (LPF then decimate), 1 polyphase moving average */
+} sa_annotation;
+
+/* ---- lifecycle ---- */
+SA_API int32_t     sa_engine_create(int32_t device_ordinal, sa_engine** out_engine);
+SA_API void        sa_engine_destroy(sa_engine* engine);
+SA_API const char* sa_last_error(void);                 /* thread-local, never NULL */
+SA_API const char* sa_version(void);
+/* number of CUDA kernels this engine has launched so far (bench.py's gpu_launches) */
+SA_API uint64_t    sa_kernel_launches(const sa_engine* engine);
+
+/* ---- helpers mirroring S/sigmf/Global.java:67-79 and S/sigmf/SigMfHelper.java:87-91 ---- */
+SA_API int32_t sa_bytes_per_iq(int32_t dtype);          /* 8,4,2,2,16 ; 0 if unknown */
+/* "ci16_le" -> (SA_CI16, 0); prefix match like String.startsWith, order LE iff ends "_le" */
+SA_API int32_t sa_parse_datatype(const char* sigmf_datatype, int32_t* dtype, int32_t* big_endian);
+SA_API void    sa_spectrogram_params_init(sa_spectrogram_params* p);   /* reference defaults */
+
+/* ---- host memory: the mmapped .sigmf-data MemorySegment (SigMfHelper.java:78-84) ---- */
+/* Page-locks [ptr, ptr+bytes) so H2D copies run asynchronously at full PCIe rate.  Optional:
+ * unregistered memory works through pageable copies.  read_only != 0 for PROT_READ mappings. */
+SA_API int32_t sa_register_host(sa_engine* engine, const void* ptr, uint64_t bytes, int32_t read_only);
+SA_API int32_t sa_unregister_host(sa_engine* engine, const void* ptr);
+
+/* ---- spectrogram ---- */
+/* iq / out are HOST pointers; iq points at sample 0 of the capture (position 0 of the mapped
+ * buffer, i.e. already past core:header_bytes, SigMfHelper.java:84) and need only be aligned to
+ * its element size.  out holds n_frames*nfft elements of out_kind (4, 8 or 4 bytes each). */
+SA_API int32_t sa_spectrogram(sa_engine* engine, const void* iq, uint64_t iq_bytes,
+                              const sa_spectrogram_params* params, void* out, uint64_t out_bytes);
+/* Same with DEVICE pointers; asynchronous on `cuda_stream` (a cudaStream_t, NULL = the legacy
+ * default stream).  d_iq must be aligned to one IQ pair (sa_bytes_per_iq). */
+SA_API int32_t sa_spectrogram_device(sa_engine* engine, const void* d_iq, uint64_t iq_bytes,
+                                     const sa_spectrogram_params* params, void* d_out,
+                                     uint64_t out_bytes, void* cuda_stream);
+/* SpectralService.computeMagnitudes (SpectralService.java:33-85), kept for API compatibility:
+ * one frame at byte offset start_byte, rect window, 20*log10(|X|+1e-10), fft-shifted, FP64 out. */
+SA_API int32_t sa_compute_magnitudes(sa_engine* engine, const void* buffer, uint64_t capacity_bytes,
+                                     uint64_t start_byte, uint32_t nfft, int32_t dtype,
+                                     int32_t big_endian, double* out_magnitudes);
+
+/* ---- downconvert (ExtractDownConvertService.java:54-117) ---- */
+/* out_re/out_im: host arrays of at least count/down doubles (row 0 / row 1 of the Java
+ * double[2][M]); *out_len receives M = count/down. */
+SA_API int32_t sa_downconvert(sa_engine* engine, const void* iq, uint64_t iq_bytes, int32_t dtype,
+                              int32_t big_endian, uint64_t start_sample, uint64_t count,
+                              double freq_off, int32_t down, int32_t fast,
+                              double* out_re, double* out_im, uint64_t* out_len);
+SA_API int32_t sa_lowpass_taps(int32_t down, double* taps /* 8*down+1 */);
+
+/* ---- Welch PSD (JDSP calculatePsdWelch call site, AnalysisDialogController.java:303-313) ---- */
+/* re/im: host FP64 arrays of n samples (rows of double[2][n]).  hop = 0 selects nfft/4
+ * (75 % overlap).  out_freq / out_db hold nfft doubles: frequency axis centred on 0 and the
+ * level in dB/Hz, fft-shifted. */
+SA_API int32_t sa_psd_welch(sa_engine* engine, const double* re, const double* im, uint64_t n,
+                            double fs, uint32_t nfft, uint64_t hop, int32_t window,
+                            double* out_freq, double* out_db);
+
+/* ---- batched annotation analysis: downconvert + Welch PSD for many annotations, one call ----
+ * iq: HOST pointer to the capture; for annotation a: decimated IQ goes to
+ * out_iq + iq_offsets[a] (re block of M_a doubles followed by im block, M_a = count/down) when
+ * out_iq != NULL; the PSD (psd_nfft doubles, dB/Hz, fft-shifted; fs' = sample_rate/down) goes to
+ * out_psd_db + a*psd_nfft when out_psd_db != NULL.  Annotations with M_a < psd_nfft get a PSD
+ * row of NaN (the Java caller falls back to a single short window, :304-307). */
+SA_API int32_t sa_downconvert_psd_batch(sa_engine* engine, const void* iq, uint64_t iq_bytes,
+                                        int32_t dtype, int32_t big_endian, double sample_rate,
+                                        const sa_annotation* anns, uint32_t n_ann,
+                                        uint32_t psd_nfft, uint64_t psd_hop, int32_t psd_window,
+                                        double* out_iq, const uint64_t* iq_offsets,
+                                        double* out_psd_db);
+/* device-resident variant used for roofline timing: d_iq device capture, outputs device. */
+SA_API int32_t sa_downconvert_psd_batch_device(sa_engine* engine, const void* d_iq, uint64_t iq_bytes,
+                                               int32_t dtype, int32_t big_endian, double sample_rate,
+                                               const sa_annotation* anns, uint32_t n_ann,
+                                               uint32_t psd_nfft, uint64_t psd_hop, int32_t psd_window,
+                                               double* d_out_iq, const uint64_t* iq_offsets,
+                                               double* d_out_psd_db, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SA_ENGINE_H */

@@ -1,0 +1,498 @@
+// engine.cu -- C-ABI implementation (include/sa_engine.h): argument checking, plan/table cache,
+// kernel selection, and the host<->device chunk pipeline.  No CPU fallback anywhere: every
+// compute entry point launches CUDA kernels or fails.
+#include "engine_internal.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+namespace sa {
+
+// ---------------- error reporting ----------------
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    return set_error(e == cudaErrorMemoryAllocation ? SA_ERR_OOM : SA_ERR_CUDA, "%s: %s", what,
+                     cudaGetErrorString(e));
+}
+
+// ---------------- kernel registry ----------------
+static std::vector<SpecKernelInfo>& spec_registry() {
+    static std::vector<SpecKernelInfo> r;
+    return r;
+}
+void register_spec_kernel(const SpecKernelInfo& k) { spec_registry().push_back(k); }
+
+const SpecKernelInfo* find_spec_kernel(int prec, int n, int dk, int win) {
+    for (const auto& k : spec_registry())
+        if (k.prec == prec && k.n == n && k.dk == dk && k.win == win) return &k;
+    return nullptr;
+}
+
+// ---------------- tables ----------------
+void host_window(int window_id, int n, std::vector<double>& w) {
+    w.resize(n);
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int i = 0; i < n; i++) {
+        const double x = two_pi * (double)i / (double)n;
+        switch (window_id) {
+            case SA_WIN_HANN:     w[i] = 0.5 - 0.5 * std::cos(x); break;
+            case SA_WIN_HAMMING:  w[i] = 0.54 - 0.46 * std::cos(x); break;
+            case SA_WIN_BLACKMAN: w[i] = 0.42 - 0.5 * std::cos(x) + 0.08 * std::cos(2 * x); break;
+            case SA_WIN_BLACKMAN_HARRIS:
+                w[i] = 0.35875 - 0.48829 * std::cos(x) + 0.14128 * std::cos(2 * x) - 0.01168 * std::cos(3 * x);
+                break;
+            default: w[i] = 1.0;
+        }
+    }
+}
+
+// Stockham twiddles in the [pass][s][m][t] order fft_pass reads them (fft_core.cuh)
+static void host_twiddles(int n, int p, int np, const int* radix, std::vector<double>& re, std::vector<double>& im) {
+    const int tpf = n / p;
+    re.assign((size_t)(np - 1) * n, 1.0);
+    im.assign((size_t)(np - 1) * n, 0.0);
+    const double two_pi = 6.283185307179586476925286766559;
+    int ns = radix[0];
+    for (int pass = 1; pass < np; pass++) {
+        const int r = radix[pass], s_cnt = p / r;
+        for (int s = 0; s < s_cnt; s++)
+            for (int m = 0; m < r; m++)
+                for (int t = 0; t < tpf; t++) {
+                    const int j = t + tpf * s;
+                    const long long e = (long long)(j % ns) * m * (n / (ns * r));
+                    const double ang = -two_pi * (double)(e % n) / (double)n;
+                    const size_t idx = (size_t)(pass - 1) * n + (size_t)(s * r + m) * tpf + t;
+                    re[idx] = std::cos(ang);
+                    im[idx] = std::sin(ang);
+                }
+        ns *= r;
+    }
+}
+
+template <typename T>
+static int upload_pairs(const std::vector<double>& re, const std::vector<double>& im, void** d_out) {
+    std::vector<T> h(re.size() * 2);
+    for (size_t i = 0; i < re.size(); i++) { h[2 * i] = (T)re[i]; h[2 * i + 1] = (T)im[i]; }
+    cudaError_t e = cudaMalloc(d_out, h.size() * sizeof(T));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(twiddle)");
+    e = cudaMemcpy(*d_out, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(twiddle)");
+    return SA_OK;
+}
+
+int Engine::twiddle_table(const SpecKernelInfo& k, const void** d_tab) {
+    const uint64_t key = ((uint64_t)k.prec << 32) | (uint32_t)k.n;
+    auto it = twiddles.find(key);
+    if (it != twiddles.end()) { *d_tab = it->second; return SA_OK; }
+    std::vector<double> re, im;
+    host_twiddles(k.n, k.p, k.np, k.radix, re, im);
+    void* d = nullptr;
+    int rc = (k.prec == SA_PREC_F64) ? upload_pairs<double>(re, im, &d) : upload_pairs<float>(re, im, &d);
+    if (rc) return rc;
+    twiddles[key] = d;
+    *d_tab = d;
+    return SA_OK;
+}
+
+int Engine::window_table(int window_id, int n, int prec, const void** d_tab) {
+    const uint64_t key = ((uint64_t)prec << 48) | ((uint64_t)window_id << 32) | (uint32_t)n;
+    auto it = windows.find(key);
+    if (it != windows.end()) { *d_tab = it->second; return SA_OK; }
+    std::vector<double> w;
+    host_window(window_id, n, w);
+    void* d = nullptr;
+    cudaError_t e;
+    if (prec == SA_PREC_F64) {
+        e = cudaMalloc(&d, n * sizeof(double));
+        if (e == cudaSuccess) e = cudaMemcpy(d, w.data(), n * sizeof(double), cudaMemcpyHostToDevice);
+    } else {
+        std::vector<float> wf(w.begin(), w.end());
+        e = cudaMalloc(&d, n * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemcpy(d, wf.data(), n * sizeof(float), cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "window table");
+    windows[key] = d;
+    *d_tab = d;
+    return SA_OK;
+}
+
+int Engine::kernel_grid(const void* fn, int cta, size_t smem, int* blocks_per_sm) {
+    auto it = occupancy.find(fn);
+    if (it != occupancy.end()) { *blocks_per_sm = it->second; return SA_OK; }
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(smem)");
+    int nb = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, cta, smem);
+    if (e != cudaSuccess) return cuda_fail(e, "occupancy query");
+    if (nb < 1) return set_error(SA_ERR_CUDA, "kernel does not fit on an SM (smem %zu)", smem);
+    occupancy[fn] = nb;
+    *blocks_per_sm = nb;
+    return SA_OK;
+}
+
+int dtype_kind(int dtype) {
+    switch (dtype) {
+        case SA_CF32: return DK_CF32;
+        case SA_CI16: return DK_CI16;
+        case SA_CU8:
+        case SA_CI8:  return DK_C8;
+        case SA_CF64: return DK_CF64;
+        default:      return -1;
+    }
+}
+
+void fill_load_params(LoadParams& lp, const void* base, int dtype, int big_endian) {
+    lp.base = base;
+    lp.swap = big_endian ? 1 : 0;
+    lp.c8_flip = (dtype == SA_CI8) ? 0x8080u : 0u;
+    lp.c8_off = (dtype == SA_CI8) ? 1.0f : 127.5f / 128.0f;
+}
+
+static bool is_pow2(uint64_t x) { return x && !(x & (x - 1)); }
+
+static size_t out_elem_bytes(int out_kind) { return out_kind == SA_OUT_F64_DB ? 8 : 4; }
+
+// Validates a request and resolves precision; returns SA_OK or an error.
+static int check_spec_params(const sa_spectrogram_params* p, int* prec_out) {
+    if (!p) return set_error(SA_ERR_INVALID_ARG, "params is NULL");
+    if (p->struct_size != sizeof(sa_spectrogram_params))
+        return set_error(SA_ERR_INVALID_ARG, "params.struct_size %u != %zu", p->struct_size, sizeof(sa_spectrogram_params));
+    if (sa_bytes_per_iq(p->dtype) == 0) return set_error(SA_ERR_INVALID_ARG, "unknown dtype %d", p->dtype);
+    if (!is_pow2(p->nfft))   // commons-math3 throws MathIllegalArgumentException (SpectralService.java:29)
+        return set_error(SA_ERR_INVALID_ARG, "nfft %u is not a power of two", p->nfft);
+    if (p->nfft < 64 || p->nfft > 65536)
+        return set_error(SA_ERR_UNSUPPORTED, "nfft %u outside 64..65536 (main-scene.fxml:129)", p->nfft);
+    if (p->hop == 0) return set_error(SA_ERR_INVALID_ARG, "hop is 0");
+    if (p->window < SA_WIN_RECT || p->window > SA_WIN_BLACKMAN_HARRIS) return set_error(SA_ERR_INVALID_ARG, "unknown window %d", p->window);
+    if (p->db_mode != SA_DB_MAG_1E10 && p->db_mode != SA_DB_POWER) return set_error(SA_ERR_INVALID_ARG, "unknown db_mode %d", p->db_mode);
+    if (p->out_kind < SA_OUT_F32_DB || p->out_kind > SA_OUT_RGBA8) return set_error(SA_ERR_INVALID_ARG, "unknown out_kind %d", p->out_kind);
+    if (p->out_kind == SA_OUT_RGBA8) {
+        if (!(p->sample_rate > 0.0)) return set_error(SA_ERR_INVALID_ARG, "RGBA8 output needs sample_rate > 0");
+        if (!(p->max_db > p->min_db)) return set_error(SA_ERR_INVALID_ARG, "RGBA8 output needs max_db > min_db");
+        if (p->colormap != SA_CMAP_GRAYSCALE && p->colormap != SA_CMAP_HEATMAP) return set_error(SA_ERR_INVALID_ARG, "unknown colormap %d", p->colormap);
+    }
+    int prec = p->precision;
+    if (prec == SA_PREC_AUTO) prec = (p->dtype == SA_CF64) ? SA_PREC_F64 : SA_PREC_F32;
+    if (prec != SA_PREC_F32 && prec != SA_PREC_F64) return set_error(SA_ERR_INVALID_ARG, "unknown precision %d", p->precision);
+    if (p->dtype == SA_CF64 && prec == SA_PREC_F32)
+        return set_error(SA_ERR_UNSUPPORTED, "cf64 input runs on the FP64 path only");
+    *prec_out = prec;
+    return SA_OK;
+}
+
+// Launches the fused spectrogram kernel on device-resident samples.
+int Engine::launch_spectrogram(const void* d_iq, uint64_t n_samples, const sa_spectrogram_params& p, int prec,
+                               void* d_out, cudaStream_t stream) {
+    if (p.n_frames == 0) return SA_OK;
+    const int dk = dtype_kind(p.dtype);
+    const int win = (prec == SA_PREC_F64) ? 1 : (p.window != SA_WIN_RECT ? 1 : 0);
+    const SpecKernelInfo* k = find_spec_kernel(prec, (int)p.nfft, dk, win);
+    if (!k) return set_error(SA_ERR_UNSUPPORTED, "no kernel for nfft %u precision %s dtype %d", p.nfft,
+                             prec == SA_PREC_F64 ? "f64" : "f32", p.dtype);
+    SpecArgs a;
+    memset(&a, 0, sizeof(a));
+    fill_load_params(a.lp, d_iq, p.dtype, p.big_endian);
+    a.n_samples = (long long)n_samples;
+    a.start_sample = (long long)p.start_sample;
+    a.hop = (long long)p.hop;
+    a.n_frames = (long long)p.n_frames;
+    int rc = twiddle_table(*k, &a.twiddle);
+    if (rc) return rc;
+    if (win) { rc = window_table(p.window, (int)p.nfft, prec, &a.window); if (rc) return rc; }
+    a.out = d_out;
+    a.out_kind = p.out_kind;
+    a.db_mode = p.db_mode;
+    a.eof_fill = p.eof_fill_db;
+    if (p.out_kind == SA_OUT_RGBA8) {
+        a.conv = (float)(10.0 * std::log10(p.sample_rate / (double)p.nfft) + 20.0 * std::log10((double)p.nfft));
+        a.min_db = (float)p.min_db;
+        a.inv_range = (float)(1.0 / (p.max_db - p.min_db));
+        a.cmap = p.colormap;
+    }
+    int bps = 0;
+    rc = kernel_grid(k->fn, k->cta, k->smem, &bps);
+    if (rc) return rc;
+    const long long n_blocks = ((long long)p.n_frames + k->fpc - 1) / k->fpc;
+    const long long max_grid = (long long)bps * num_sms;
+    const unsigned grid = (unsigned)std::min<long long>(n_blocks, max_grid);
+    void* args[] = { &a };
+    cudaError_t e = cudaLaunchKernel(k->fn, dim3(grid), dim3(k->cta), args, k->smem, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "launch spectrogram_kernel");
+    launches++;
+    return SA_OK;
+}
+
+int Engine::ensure_slot(Slot& s, size_t in_bytes, size_t out_bytes) {
+    cudaError_t e;
+    if (!s.stream) {
+        e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
+    }
+    if (s.in_cap < in_bytes) {
+        if (s.d_in) cudaFree(s.d_in);
+        s.d_in = nullptr; s.in_cap = 0;
+        e = cudaMalloc(&s.d_in, in_bytes);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(chunk in)");
+        s.in_cap = in_bytes;
+    }
+    if (s.out_cap < out_bytes) {
+        if (s.d_out) cudaFree(s.d_out);
+        s.d_out = nullptr; s.out_cap = 0;
+        e = cudaMalloc(&s.d_out, out_bytes);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(chunk out)");
+        s.out_cap = out_bytes;
+    }
+    return SA_OK;
+}
+
+// Host-buffer spectrogram: frames are cut into chunks; chunk c runs H2D -> kernel -> D2H on
+// slot c % kSlots' stream, so copies of one chunk overlap the kernel of another.
+int Engine::spectrogram_host(const void* iq, uint64_t iq_bytes, const sa_spectrogram_params& p, int prec, void* out) {
+    const uint64_t bps = (uint64_t)sa_bytes_per_iq(p.dtype);
+    const uint64_t n_samples = iq_bytes / bps;
+    const uint64_t obytes = out_elem_bytes(p.out_kind);
+    const uint64_t row_bytes = (uint64_t)p.nfft * obytes;
+    // frames per chunk: bound the larger of the two buffers by chunk_bytes
+    const uint64_t per_frame = std::max<uint64_t>(p.hop * bps, row_bytes);
+    uint64_t fpc = std::max<uint64_t>(1, chunk_bytes / per_frame);
+    fpc = std::min<uint64_t>(fpc, p.n_frames);
+    const uint64_t in_cap = ((fpc - 1) * p.hop + p.nfft) * bps;
+    const uint64_t out_cap = fpc * row_bytes;
+    int rc = SA_OK;
+    uint64_t c = 0;
+    for (uint64_t f0 = 0; f0 < p.n_frames && rc == SA_OK; f0 += fpc, c++) {
+        Slot& s = slots[c % kSlots];
+        rc = ensure_slot(s, in_cap, out_cap);
+        if (rc) break;
+        cudaError_t e = cudaStreamSynchronize(s.stream);     // slot buffers free again
+        if (e != cudaSuccess) { rc = cuda_fail(e, "slot sync"); break; }
+        const uint64_t nf = std::min<uint64_t>(fpc, p.n_frames - f0);
+        const uint64_t s_begin = p.start_sample + f0 * p.hop;
+        uint64_t s_end = s_begin + (nf - 1) * p.hop + p.nfft;
+        if (s_end > n_samples) s_end = n_samples;             // frames past EOF become fill rows
+        const uint64_t ns = s_end > s_begin ? s_end - s_begin : 0;
+        if (ns) {
+            e = cudaMemcpyAsync(s.d_in, (const char*)iq + s_begin * bps, ns * bps, cudaMemcpyHostToDevice, s.stream);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "H2D"); break; }
+        }
+        sa_spectrogram_params q = p;
+        q.start_sample = 0;
+        q.n_frames = nf;
+        rc = launch_spectrogram(s.d_in, ns, q, prec, s.d_out, s.stream);
+        if (rc) break;
+        e = cudaMemcpyAsync((char*)out + f0 * row_bytes, s.d_out, nf * row_bytes, cudaMemcpyDeviceToHost, s.stream);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "D2H"); break; }
+    }
+    for (int i = 0; i < kSlots; i++)
+        if (slots[i].stream) {
+            cudaError_t e = cudaStreamSynchronize(slots[i].stream);
+            if (e != cudaSuccess && rc == SA_OK) rc = cuda_fail(e, "pipeline drain");
+        }
+    return rc;
+}
+
+Engine::~Engine() {
+    cudaSetDevice(device);
+    for (auto& kv : twiddles) cudaFree(kv.second);
+    for (auto& kv : windows) cudaFree(kv.second);
+    for (auto& kv : misc_tables) cudaFree(kv.second);
+    for (int i = 0; i < kSlots; i++) {
+        if (slots[i].d_in) cudaFree(slots[i].d_in);
+        if (slots[i].d_out) cudaFree(slots[i].d_out);
+        if (slots[i].stream) cudaStreamDestroy(slots[i].stream);
+    }
+    for (auto& r : registered) cudaHostUnregister(const_cast<void*>(r));
+    if (scratch) cudaFree(scratch);
+}
+
+int Engine::ensure_scratch(size_t bytes) {
+    if (scratch_cap >= bytes) return SA_OK;
+    if (scratch) cudaFree(scratch);
+    scratch = nullptr; scratch_cap = 0;
+    cudaError_t e = cudaMalloc(&scratch, bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(scratch)");
+    scratch_cap = bytes;
+    return SA_OK;
+}
+
+}  // namespace sa
+
+using namespace sa;
+
+struct sa_engine : public sa::Engine {};
+
+#define ENGINE_ENTER(engine)                                                         \
+    if (!(engine)) return set_error(SA_ERR_INVALID_ARG, "engine is NULL");            \
+    std::lock_guard<std::mutex> lock_((engine)->mu);                                  \
+    { cudaError_t e_ = cudaSetDevice((engine)->device);                               \
+      if (e_ != cudaSuccess) return cuda_fail(e_, "cudaSetDevice"); }
+
+extern "C" {
+
+const char* sa_last_error(void) { return g_err; }
+const char* sa_version(void) { return "spectral_analyzer_b200 0.1.0 (sm_100a)"; }
+
+int32_t sa_bytes_per_iq(int32_t dtype) {     // S/sigmf/Global.java:67-79
+    switch (dtype) {
+        case SA_CF32: return 8;
+        case SA_CI16: return 4;
+        case SA_CU8:  return 2;
+        case SA_CI8:  return 2;
+        case SA_CF64: return 16;
+        default:      return 0;
+    }
+}
+
+int32_t sa_parse_datatype(const char* s, int32_t* dtype, int32_t* big_endian) {
+    if (!s || !dtype || !big_endian) return set_error(SA_ERR_INVALID_ARG, "NULL argument");
+    // String.startsWith tests of SpectralService.java:35-38 / ExtractDownConvertService.java:79-94
+    int d = -1;
+    if (!strncmp(s, "ci16", 4)) d = SA_CI16;
+    else if (!strncmp(s, "cf32", 4)) d = SA_CF32;
+    else if (!strncmp(s, "cu8", 3)) d = SA_CU8;
+    else if (!strncmp(s, "ci8", 3)) d = SA_CI8;
+    else if (!strncmp(s, "cf64", 4)) d = SA_CF64;
+    if (d < 0) return set_error(SA_ERR_UNSUPPORTED, "datatype '%s' has no decode branch", s);
+    const size_t n = strlen(s);
+    *big_endian = (n >= 3 && !strcmp(s + n - 3, "_le")) ? 0 : 1;     // SigMfHelper.java:87-91
+    *dtype = d;
+    return SA_OK;
+}
+
+void sa_spectrogram_params_init(sa_spectrogram_params* p) {
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->struct_size = sizeof(*p);
+    p->dtype = SA_CF32;
+    p->window = SA_WIN_RECT;
+    p->nfft = 1024;                 // main-scene.fxml:129-132 default 2^10
+    p->db_mode = SA_DB_MAG_1E10;
+    p->out_kind = SA_OUT_F32_DB;
+    p->precision = SA_PREC_AUTO;
+    p->hop = 1024;
+    p->eof_fill_db = -150.0;        // MainController.java:996-997
+    p->colormap = SA_CMAP_GRAYSCALE;
+    p->sample_rate = 1.0;
+    p->min_db = -160.0;             // main-scene.fxml:143
+    p->max_db = -30.0;              // main-scene.fxml:150
+}
+
+int32_t sa_engine_create(int32_t device, sa_engine** out) {
+    if (!out) return set_error(SA_ERR_INVALID_ARG, "out_engine is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return set_error(SA_ERR_NO_DEVICE, "no CUDA device (%s); this engine has no CPU fallback",
+                         e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= count) return set_error(SA_ERR_INVALID_ARG, "device %d out of range (count %d)", device, count);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
+    if (prop.major != 10)
+        return set_error(SA_ERR_NO_DEVICE, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
+    sa_engine* eng = new sa_engine();
+    eng->device = device;
+    eng->num_sms = prop.multiProcessorCount;
+    const char* cm = getenv("SA_CHUNK_MB");
+    if (cm && atoi(cm) > 0) eng->chunk_bytes = (uint64_t)atoi(cm) << 20;
+    *out = eng;
+    return SA_OK;
+}
+
+void sa_engine_destroy(sa_engine* engine) {
+    if (!engine) return;
+    { std::lock_guard<std::mutex> lock_(engine->mu); cudaSetDevice(engine->device); cudaDeviceSynchronize(); }
+    delete engine;
+}
+
+uint64_t sa_kernel_launches(const sa_engine* engine) { return engine ? engine->launches : 0; }
+
+int32_t sa_register_host(sa_engine* engine, const void* ptr, uint64_t bytes, int32_t read_only) {
+    ENGINE_ENTER(engine);
+    if (!ptr || !bytes) return set_error(SA_ERR_INVALID_ARG, "empty range");
+    unsigned flags = cudaHostRegisterPortable;
+    if (read_only) flags |= cudaHostRegisterReadOnly;
+    cudaError_t e = cudaHostRegister(const_cast<void*>(ptr), bytes, flags);
+    if (e != cudaSuccess && read_only) {      // some platforms refuse the read-only flag
+        cudaGetLastError();
+        e = cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterPortable);
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); return cuda_fail(e, "cudaHostRegister"); }
+    engine->registered.push_back(ptr);
+    return SA_OK;
+}
+
+int32_t sa_unregister_host(sa_engine* engine, const void* ptr) {
+    ENGINE_ENTER(engine);
+    auto it = std::find(engine->registered.begin(), engine->registered.end(), ptr);
+    if (it == engine->registered.end()) return set_error(SA_ERR_INVALID_ARG, "range was not registered");
+    engine->registered.erase(it);
+    cudaError_t e = cudaHostUnregister(const_cast<void*>(ptr));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaHostUnregister");
+    return SA_OK;
+}
+
+int32_t sa_spectrogram_device(sa_engine* engine, const void* d_iq, uint64_t iq_bytes,
+                              const sa_spectrogram_params* params, void* d_out, uint64_t out_bytes,
+                              void* cuda_stream) {
+    ENGINE_ENTER(engine);
+    int prec = 0;
+    int rc = check_spec_params(params, &prec);
+    if (rc) return rc;
+    if (!d_out || (!d_iq && iq_bytes)) return set_error(SA_ERR_INVALID_ARG, "NULL buffer");
+    const uint64_t bps = (uint64_t)sa_bytes_per_iq(params->dtype);
+    if ((uintptr_t)d_iq % bps) return set_error(SA_ERR_INVALID_ARG, "d_iq must be aligned to %llu bytes", (unsigned long long)bps);
+    const uint64_t need = params->n_frames * (uint64_t)params->nfft * out_elem_bytes(params->out_kind);
+    if (out_bytes < need) return set_error(SA_ERR_SMALL_OUTPUT, "out_bytes %llu < %llu", (unsigned long long)out_bytes, (unsigned long long)need);
+    return engine->launch_spectrogram(d_iq, iq_bytes / bps, *params, prec, d_out, (cudaStream_t)cuda_stream);
+}
+
+int32_t sa_spectrogram(sa_engine* engine, const void* iq, uint64_t iq_bytes, const sa_spectrogram_params* params,
+                       void* out, uint64_t out_bytes) {
+    ENGINE_ENTER(engine);
+    int prec = 0;
+    int rc = check_spec_params(params, &prec);
+    if (rc) return rc;
+    if (!out || (!iq && iq_bytes)) return set_error(SA_ERR_INVALID_ARG, "NULL buffer");
+    const uint64_t need = params->n_frames * (uint64_t)params->nfft * out_elem_bytes(params->out_kind);
+    if (out_bytes < need) return set_error(SA_ERR_SMALL_OUTPUT, "out_bytes %llu < %llu", (unsigned long long)out_bytes, (unsigned long long)need);
+    if (params->n_frames == 0) return SA_OK;
+    return engine->spectrogram_host(iq, iq_bytes, *params, prec, out);
+}
+
+int32_t sa_compute_magnitudes(sa_engine* engine, const void* buffer, uint64_t capacity_bytes, uint64_t start_byte,
+                              uint32_t nfft, int32_t dtype, int32_t big_endian, double* out) {
+    ENGINE_ENTER(engine);
+    sa_spectrogram_params p;
+    sa_spectrogram_params_init(&p);
+    p.dtype = dtype; p.big_endian = big_endian; p.nfft = nfft; p.hop = nfft; p.n_frames = 1;
+    p.out_kind = SA_OUT_F64_DB;
+    int prec = 0;
+    int rc = check_spec_params(&p, &prec);
+    if (rc) return rc;
+    if (!buffer || !out) return set_error(SA_ERR_INVALID_ARG, "NULL buffer");
+    const uint64_t bps = (uint64_t)sa_bytes_per_iq(dtype);
+    // buffer.getShort/getFloat past the limit throws IndexOutOfBoundsException in Java
+    if (start_byte > capacity_bytes || (uint64_t)nfft * bps > capacity_bytes - start_byte)
+        return set_error(SA_ERR_OUT_OF_RANGE, "frame [%llu, +%llu) exceeds capacity %llu", (unsigned long long)start_byte,
+                         (unsigned long long)(nfft * bps), (unsigned long long)capacity_bytes);
+    return engine->spectrogram_host((const char*)buffer + start_byte, (uint64_t)nfft * bps, p, prec, out);
+}
+
+}  // extern "C"

@@ -1,0 +1,53 @@
+// engine_internal.h -- host-side state behind the opaque sa_engine handle.
+#pragma once
+#include <cuda_runtime.h>
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "../../include/sa_engine.h"
+#include "spectrogram_kernel.cuh"
+
+namespace sa {
+
+int set_error(int code, const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+const SpecKernelInfo* find_spec_kernel(int prec, int n, int dk, int win);
+void host_window(int window_id, int n, std::vector<double>& w);
+int dtype_kind(int dtype);
+void fill_load_params(LoadParams& lp, const void* base, int dtype, int big_endian);
+
+constexpr int kSlots = 3;
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    void* d_in = nullptr;  size_t in_cap = 0;
+    void* d_out = nullptr; size_t out_cap = 0;
+};
+
+struct Engine {
+    int device = 0;
+    int num_sms = 0;
+    std::mutex mu;
+    uint64_t launches = 0;
+    uint64_t chunk_bytes = 64ull << 20;              // per-slot staging size of the host pipeline
+    std::map<uint64_t, void*> twiddles;              // (prec, nfft) -> device table
+    std::map<uint64_t, void*> windows;               // (prec, window, nfft) -> device table
+    std::map<uint64_t, void*> misc_tables;           // FIR taps etc.
+    std::map<const void*, int> occupancy;            // kernel -> resident CTAs per SM
+    std::vector<const void*> registered;             // cudaHostRegister'ed ranges
+    Slot slots[kSlots];
+    void* scratch = nullptr; size_t scratch_cap = 0; // device workspace (Welch partials, ...)
+
+    ~Engine();
+    int twiddle_table(const SpecKernelInfo& k, const void** d_tab);
+    int window_table(int window_id, int n, int prec, const void** d_tab);
+    int kernel_grid(const void* fn, int cta, size_t smem, int* blocks_per_sm);
+    int ensure_slot(Slot& s, size_t in_bytes, size_t out_bytes);
+    int ensure_scratch(size_t bytes);
+    int launch_spectrogram(const void* d_iq, uint64_t n_samples, const sa_spectrogram_params& p, int prec,
+                           void* d_out, cudaStream_t stream);
+    int spectrogram_host(const void* iq, uint64_t iq_bytes, const sa_spectrogram_params& p, int prec, void* out);
+};
+
+}  // namespace sa

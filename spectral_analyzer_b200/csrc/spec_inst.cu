@@ -1,0 +1,33 @@
+// spec_inst.cu -- explicit instantiations of spectrogram_kernel, one object file per
+// (precision, nfft) so the build parallelises: compiled with -DSA_INST_PREC=1|2 -DSA_INST_N=<nfft>.
+#include "spectrogram_kernel.cuh"
+
+#ifndef SA_INST_PREC
+#error "compile with -DSA_INST_PREC=1|2 -DSA_INST_N=<nfft>"
+#endif
+
+namespace sa {
+namespace {
+struct Registrar {
+    Registrar() {
+#if SA_INST_PREC == 1
+        // FP32 arithmetic: cf32 / ci16 / cu8+ci8 inputs, with and without a window multiply
+        register_spec_kernel(make_spec_info<float, SA_INST_N, DK_CF32, false>(1));
+        register_spec_kernel(make_spec_info<float, SA_INST_N, DK_CF32, true>(1));
+        register_spec_kernel(make_spec_info<float, SA_INST_N, DK_CI16, false>(1));
+        register_spec_kernel(make_spec_info<float, SA_INST_N, DK_CI16, true>(1));
+        register_spec_kernel(make_spec_info<float, SA_INST_N, DK_C8, false>(1));
+        register_spec_kernel(make_spec_info<float, SA_INST_N, DK_C8, true>(1));
+#else
+        // FP64 arithmetic (cf64 input, or any input when the caller asks for SA_PREC_F64);
+        // always windowed -- a rectangular window is a table of ones
+        register_spec_kernel(make_spec_info<double, SA_INST_N, DK_CF32, true>(2));
+        register_spec_kernel(make_spec_info<double, SA_INST_N, DK_CI16, true>(2));
+        register_spec_kernel(make_spec_info<double, SA_INST_N, DK_C8, true>(2));
+        register_spec_kernel(make_spec_info<double, SA_INST_N, DK_CF64, true>(2));
+#endif
+    }
+};
+static Registrar registrar_instance;
+}  // namespace
+}  // namespace sa

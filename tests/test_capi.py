@@ -1,0 +1,68 @@
+"""CPU checks of the drop-in boundary: the shared library loads, exports every symbol that
+include/sa_engine.h declares, the helper entry points follow the reference's rules, and the
+product refuses to run without a GPU (no CPU fallback).  No compute calls here."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from spectral_analyzer_b200 import _capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "sa_engine.h")).read()
+    return sorted(set(re.findall(r"SA_API\s+[\w\s\*]+?\b(sa_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _capi.lib()
+    names = declared_symbols()
+    assert len(names) >= 17
+    for n in names:
+        assert hasattr(L, n), "libsa_engine.so does not export " + n
+
+
+def test_bytes_per_iq_matches_global_java():
+    L = _capi.lib()      # S/sigmf/Global.java:67-79
+    assert [L.sa_bytes_per_iq(i) for i in range(6)] == [8, 4, 2, 2, 16, 0]
+
+
+@pytest.mark.parametrize("s,exp", [("cf32_le", (0, 0)), ("cf32_be", (0, 1)), ("ci16_le", (1, 0)), ("ci16_be", (1, 1)),
+                                   ("cu8", (2, 1)), ("ci8", (3, 1)), ("cf64_le", (4, 0)), ("ci16", (1, 1))])
+def test_parse_datatype(s, exp):
+    assert _capi.parse_datatype(s) == exp
+
+
+def test_parse_datatype_unknown_is_error():
+    with pytest.raises(_capi.EngineError) as ei:
+        _capi.parse_datatype("ri16_le")          # mono WAV: no decode branch in the reference
+    assert ei.value.code == 2
+
+
+def test_params_defaults_are_the_reference_mode():
+    p = _capi.default_params()
+    assert p.struct_size == C.sizeof(_capi.SpectrogramParams)
+    assert (p.window, p.nfft, p.hop, p.db_mode, p.eof_fill_db) == (0, 1024, 1024, 0, -150.0)
+    assert (p.min_db, p.max_db) == (-160.0, -30.0)
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    h = C.c_void_p()
+    rc = _capi.lib().sa_engine_create(0, C.byref(h))
+    assert rc == 5 and not h.value
+    assert b"no CPU fallback" in _capi.lib().sa_last_error()
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "spectral_analyzer_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.lower(), f + " mentions the oracle"

@@ -1,0 +1,161 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI, against the CPU oracle."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle as co
+from spectral_analyzer_b200 import synth, SpectralService, EngineError
+from util import check_db_parity
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+ALL_DT = ["cf32_le", "cf32_be", "ci16_le", "ci16_be", "cu8", "ci8"]
+
+
+def test_impulse_and_dc_kat(engine):
+    n = 1024
+    x = np.zeros(n, complex); x[0] = 1.0
+    out = engine.spectrogram(synth.encode(x, "cf32_le"), "cf32_le", n, 1)
+    assert np.abs(out - 20 * np.log10(1 + 1e-10)).max() < 1e-5
+    out = engine.spectrogram(synth.encode(np.full(n, 0.25), "cf32_le"), "cf32_le", n, 1)[0]
+    assert abs(out[n // 2] - 20 * np.log10(0.25 * n)) < 1e-4
+    assert (np.delete(out, n // 2) < -100).all()
+
+
+@pytest.mark.parametrize("dt", ALL_DT)
+def test_integer_decode_bit_exact(engine, dt):
+    """A length-64 frame holding ONE non-zero sample at n=0 has |X[k]| = |x[0]| in every bin, so the
+    decoded value is read back exactly: 20*log10(|v| + 1e-10) must match the FP64 oracle to FP32
+    rounding of the dB value -- and, decoded through the FP64 path, to 1e-12."""
+    kind = dt.split("_")[0]
+    vals = {"ci16": [-32768, -1, 1, 32767, 12345], "cu8": [0, 127, 128, 255, 37], "ci8": [-128, -1, 1, 127, 37],
+            "cf32": [1.0, -0.5, 3.0e-5, 12345.678, -1e-3]}[kind]
+    for v in vals:
+        iq = np.zeros(128, synth.NP_DTYPE[kind])
+        if kind == "cu8":
+            iq[:] = 0            # cu8 zero level is -127.5/128, so every sample is non-zero: use oracle directly
+        iq[0] = v
+        raw = iq.astype(("<" if dt.endswith("_le") else ">") + synth.NP_DTYPE[kind]).view(np.uint8)
+        ref = co.compute_magnitudes(raw, 0, 64, dt)
+        got64 = engine.spectrogram(raw, dt, 64, 1, precision="f64", out_kind="f64")[0]
+        assert np.abs(got64 - ref).max() < 1e-9, (dt, v)
+        got32 = engine.spectrogram(raw, dt, 64, 1)[0]
+        lin = np.abs(10 ** (got32 / 20.0) - 10 ** (ref / 20.0))
+        assert lin.max() <= 2e-6 * 10 ** (ref.max() / 20.0), (dt, v)
+
+
+@pytest.mark.parametrize("nfft", [64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384])
+def test_reference_parity_mode_all_sizes(engine, nfft):
+    """rect window, hop = nfft, 20*log10(|X|+1e-10): the reference's own framing."""
+    frames = 9
+    raw = synth.recording(nfft * frames - 17, "cf32_le", seed=nfft)
+    ref = co.spectrogram(raw, "cf32_le", 0, nfft, nfft, "rect", frames)
+    got = engine.spectrogram(raw, "cf32_le", nfft, frames)
+    assert (got[-1] == -150.0).all()                      # EOF row, MainController.java:994-998
+    check_db_parity(got[:-1], ref[:-1])
+
+
+@pytest.mark.parametrize("dt", ALL_DT)
+@pytest.mark.parametrize("nfft,win,hop", [(1024, "hann", 512), (4096, "blackman_harris", 4096), (2048, "rect", 2048),
+                                          (256, "hamming", 64), (512, "blackman", 300)])
+def test_dtypes_windows_hops(engine, dt, nfft, win, hop):
+    frames = 13
+    raw = synth.recording((frames - 1) * hop + nfft + 5, dt, seed=3)
+    ref = co.spectrogram(raw, dt, 5, nfft, hop, win, frames)
+    got = engine.spectrogram(raw, dt, nfft, frames, hop=hop, window=win, start_sample=5)
+    check_db_parity(got, ref)
+
+
+@pytest.mark.parametrize("dt", ["cf64_le", "cf64_be", "cf32_le", "ci16_le", "cu8"])
+@pytest.mark.parametrize("nfft", [64, 512, 1024, 8192])
+def test_fp64_path_tight(engine, dt, nfft):
+    frames = 5
+    raw = synth.recording(nfft * frames, dt, seed=5)
+    for win, hop in (("rect", nfft), ("hann", nfft // 2)):
+        ref = co.spectrogram(raw, dt, 0, nfft, hop, win, frames)
+        got = engine.spectrogram(raw, dt, nfft, frames, hop=hop, window=win, precision="f64", out_kind="f64")
+        check_db_parity(got, ref, strong_tol=1e-9, floor_tol=1e-6)
+
+
+def test_power_db_mode(engine):
+    raw = synth.recording(1024 * 8, "cf32_le", seed=7)
+    ref = co.spectrogram(raw, "cf32_le", 0, 1024, 512, "hann", 15, db_mode=co.DB_POWER)
+    got = engine.spectrogram(raw, "cf32_le", 1024, 15, hop=512, window="hann", db_mode=1)
+    check_db_parity(got, ref, mode_power=True)
+
+
+def test_golden_fixtures(engine):
+    for f in sorted(glob.glob(os.path.join(GOLD, "spec_parity_*.npz"))):
+        g = np.load(f)
+        dt, nfft, frames = str(g["datatype"]), int(g["nfft"]), int(g["frames"])
+        got = engine.spectrogram(g["raw"], dt, nfft, frames)
+        assert (got[-1] == -150.0).all()
+        check_db_parity(got[:-1], g["img"][:-1])
+    g = np.load(os.path.join(GOLD, "spec_c1_mini.npz"))
+    got = engine.spectrogram(g["raw"], "cf32_le", 1024, 9, hop=512, window="hann")
+    check_db_parity(got, g["img"])
+
+
+def test_compute_magnitudes_service(engine):
+    """The per-frame entry point kept for API compatibility (SpectralService.java:33)."""
+    svc = SpectralService(engine)
+    raw = synth.recording(5000, "ci16_le", seed=8)
+    out = svc.computeMagnitudes(raw, 4 * 123, 1024, "ci16_le")
+    assert out.dtype == np.float64 and out.shape == (1024,)
+    check_db_parity(out[None], co.compute_magnitudes(raw, 4 * 123, 1024, "ci16_le")[None])
+    # odd byte offsets are legal in Java (absolute get on the ByteBuffer)
+    out = svc.computeMagnitudes(raw, 3, 256, "ci16_le")
+    check_db_parity(out[None], co.compute_magnitudes(raw, 3, 256, "ci16_le")[None])
+    with pytest.raises(EngineError) as ei:
+        svc.computeMagnitudes(raw, 0, 1000, "ci16_le")       # MathIllegalArgumentException
+    assert ei.value.code == 1
+    with pytest.raises(EngineError) as ei:
+        svc.computeMagnitudes(raw, 4 * 4500, 1024, "ci16_le")  # IndexOutOfBoundsException
+    assert ei.value.code == 3
+    wf = svc.computeWaterfall(raw, 100, 6, 1024, "ci16_le")
+    ref = co.spectrogram(raw, "ci16_le", 100, 1024, 1024, "rect", 6)
+    assert (wf[4:] == -150.0).all() and wf.dtype == np.float64
+    check_db_parity(wf[:4], ref[:4])
+
+
+def test_empty_and_ragged(engine):
+    raw = synth.recording(100, "cf32_le")
+    out = engine.spectrogram(raw, "cf32_le", 256, 3)            # shorter than one frame: all EOF rows
+    assert (out == -150.0).all()
+    out = engine.spectrogram(raw, "cf32_le", 64, 0)
+    assert out.shape == (0, 64)
+    out = engine.spectrogram(np.zeros(0, np.uint8), "cf32_le", 64, 2)
+    assert (out == -150.0).all()
+
+
+def test_chunked_host_pipeline_matches_single_chunk(engine, monkeypatch):
+    """Frame indexing across chunk boundaries of the H2D/D2H pipeline is exact."""
+    import spectral_analyzer_b200 as sa
+    raw = synth.recording(1 << 18, "ci16_le", seed=12)
+    frames = ((1 << 18) - 1024) // 384 + 3
+    a = engine.spectrogram(raw, "ci16_le", 1024, frames, hop=384, window="hann")
+    monkeypatch.setenv("SA_CHUNK_MB", "1")
+    small = sa.Engine(0)
+    small_chunks = small.spectrogram(raw, "ci16_le", 1024, frames, hop=384, window="hann")
+    small.close()
+    assert np.array_equal(a, small_chunks)
+    assert (a[-1] == -150.0).all() and (a[-3] != -150.0).any()
+
+
+def test_linearity_and_time_shift_properties(engine):
+    """Size-independent properties at a larger size than the oracle is asked to handle."""
+    n, nfft = 1 << 22, 1024
+    x = synth.complex_signal(n, seed=21)
+    a = engine.spectrogram(synth.encode(x, "cf32_le"), "cf32_le", nfft, n // nfft)
+    b = engine.spectrogram(synth.encode(2.0 * x, "cf32_le"), "cf32_le", nfft, n // nfft)
+    strong = a > a.max() - 60
+    assert np.abs((b - a)[strong] - 20 * np.log10(2.0)).max() < 1e-4          # homogeneity in dB
+    # starting one frame later reproduces rows shifted by one
+    c = engine.spectrogram(synth.encode(x, "cf32_le"), "cf32_le", nfft, n // nfft - 1, start_sample=nfft)
+    assert np.array_equal(c, a[1:])
+    # Parseval on a few frames: sum |X|^2 = N * sum |x|^2
+    p = (10 ** (a[:8].astype(np.float64) / 10)).sum(axis=1)
+    e = (np.abs(x[:8 * nfft].astype(np.complex64)) ** 2).reshape(8, nfft).sum(axis=1) * nfft
+    assert np.abs(p / e - 1).max() < 1e-4
