@@ -18,7 +18,6 @@ that block.  Multi-GPU: the recording is time-sharded, every rank owns a contigu
 """
 import argparse
 import json
-import math
 import os
 import sys
 import threading
@@ -74,7 +73,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(0.002)
 
     def summary(self):
         s = sorted(self.samples)
@@ -103,7 +102,7 @@ def make_device_recording(torch, n, seed, device):
     return out
 
 
-def cpu_port_throughput(n_samples, nthreads=0):
+def cpu_port_throughput(n_samples, nthreads=0, min_seconds=0.0):
     """Times the oracle's spectrogram (C FP64 restatement of SpectralService.computeMagnitudes +
     the updateDisplay frame loop) on host cores; returns (Msamples/s, threads, seconds)."""
     import numpy as np
@@ -114,10 +113,13 @@ def cpu_port_throughput(n_samples, nthreads=0):
     frames = (n_samples - NFFT) // HOP + 1
     threads = nthreads if nthreads > 0 else (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count())
     co.spectrogram(raw[: 8 * (1 << 16)], DATATYPE, 0, NFFT, HOP, WINDOW, 64, nthreads=threads)     # warm
-    t0 = time.perf_counter()
-    co.spectrogram(raw, DATATYPE, 0, NFFT, HOP, WINDOW, frames, nthreads=threads)
-    dt = time.perf_counter() - t0
-    return frames * HOP / dt / 1e6, threads, dt
+    reps, dt = 0, 0.0
+    while reps < 1 or (dt < min_seconds and reps < 64):
+        t0 = time.perf_counter()
+        co.spectrogram(raw, DATATYPE, 0, NFFT, HOP, WINDOW, frames, nthreads=threads)
+        dt += time.perf_counter() - t0
+        reps += 1
+    return reps * frames * HOP / dt / 1e6, threads, dt
 
 
 def run_reference(args, rank):
@@ -150,8 +152,8 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2-samples", type=int, default=LOG2_SAMPLES_PER_GPU)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -269,12 +271,11 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         v1, _, dt1 = cpu_port_throughput(1 << 21, nthreads=1)
-        probe, threads, _ = cpu_port_throughput(1 << 22)
-        # bounded sample: about 10 s of wall time on all host threads, 2^22..2^26 samples
-        log2n = max(22, min(26, int(math.log2(max(probe, 1e-3) * 1e6 * 10.0))))
-        vall, threads, dtall = cpu_port_throughput(1 << log2n)
+        # bounded sample: 2^25 samples repeated until about 4 s of wall time on all host threads
+        log2n = 25
+        vall, threads, dtall = cpu_port_throughput(1 << log2n, min_seconds=4.0)
         cpu = {"value": round(vall, 3), "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "2^%d samples, same parameters, %.1f s on %d threads; 1 thread (the reference's FX-thread "
+               "sample": "2^%d samples (repeated), same parameters, %.1f s on %d threads; 1 thread (the reference's FX-thread "
                          "concurrency): %.3f Msamples/s on 2^21 samples" % (log2n, dtall, threads, v1),
                "single_thread_value": round(v1, 3)}
 

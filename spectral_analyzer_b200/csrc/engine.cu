@@ -315,16 +315,16 @@ Engine::~Engine() {
         if (slots[i].stream) cudaStreamDestroy(slots[i].stream);
     }
     for (auto& r : registered) cudaHostUnregister(const_cast<void*>(r));
-    if (scratch) cudaFree(scratch);
+    for (int i = 0; i < 2; i++) if (scratch[i]) cudaFree(scratch[i]);
 }
 
-int Engine::ensure_scratch(size_t bytes) {
-    if (scratch_cap >= bytes) return SA_OK;
-    if (scratch) cudaFree(scratch);
-    scratch = nullptr; scratch_cap = 0;
-    cudaError_t e = cudaMalloc(&scratch, bytes);
+int Engine::ensure_scratch(int which, size_t bytes) {
+    if (scratch_cap[which] >= bytes) return SA_OK;
+    if (scratch[which]) { cudaDeviceSynchronize(); cudaFree(scratch[which]); }
+    scratch[which] = nullptr; scratch_cap[which] = 0;
+    cudaError_t e = cudaMalloc(&scratch[which], bytes);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(scratch)");
-    scratch_cap = bytes;
+    scratch_cap[which] = bytes;
     return SA_OK;
 }
 

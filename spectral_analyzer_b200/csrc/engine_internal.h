@@ -37,14 +37,15 @@ struct Engine {
     std::map<const void*, int> occupancy;            // kernel -> resident CTAs per SM
     std::vector<const void*> registered;             // cudaHostRegister'ed ranges
     Slot slots[kSlots];
-    void* scratch = nullptr; size_t scratch_cap = 0; // device workspace (Welch partials, ...)
+    void* scratch[2] = {nullptr, nullptr};           // device workspaces: [0] annotation plan + taps,
+    size_t scratch_cap[2] = {0, 0};                  //                    [1] Welch plan + partial spectra
 
     ~Engine();
     int twiddle_table(const SpecKernelInfo& k, const void** d_tab);
     int window_table(int window_id, int n, int prec, const void** d_tab);
     int kernel_grid(const void* fn, int cta, size_t smem, int* blocks_per_sm);
     int ensure_slot(Slot& s, size_t in_bytes, size_t out_bytes);
-    int ensure_scratch(size_t bytes);
+    int ensure_scratch(int which, size_t bytes);
     int launch_spectrogram(const void* d_iq, uint64_t n_samples, const sa_spectrogram_params& p, int prec,
                            void* d_out, cudaStream_t stream);
     int spectrogram_host(const void* iq, uint64_t iq_bytes, const sa_spectrogram_params& p, int prec, void* out);
