@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsa_engine.so")
+# SA_ENGINE_LIB selects another build of the same library (A/B runs of kernel tuning knobs)
+LIB_PATH = os.environ.get("SA_ENGINE_LIB") or os.path.join(_HERE, "libsa_engine.so")
 
 SA_OK = 0
 ERR_NAMES = {1: "INVALID_ARG", 2: "UNSUPPORTED", 3: "OUT_OF_RANGE", 4: "CUDA", 5: "NO_DEVICE", 6: "OOM",

@@ -40,7 +40,7 @@ template <int N> WelchKernel make_welch() {
     using PL = Plan<float, N>;
     WelchKernel k;
     k.fn = (const void*)&welch_accum_kernel<N>;
-    k.n = N; k.cta = G::CTA; k.fpc = G::FPC; k.smem = G::SMEM_BYTES; k.p = G::P; k.np = PL::NP;
+    k.n = N; k.cta = G::CTA; k.fpc = G::FPC; k.smem = G::SMEM_BYTES + G::TW_BYTES; k.p = G::P; k.np = PL::NP;
     for (int i = 0; i < 4; i++) k.radix[i] = PL::radix(i);
     return k;
 }

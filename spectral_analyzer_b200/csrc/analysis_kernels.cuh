@@ -199,6 +199,12 @@ welch_accum_kernel(const WelchArgs a) {
     const int fl = threadIdx.x / TPF, t = threadIdx.x % TPF;
     float2* sm = reinterpret_cast<float2*>(smem_raw) + (size_t)fl * G::SM_ELEMS;
     const float2* tw = reinterpret_cast<const float2*>(a.twiddle);
+    if constexpr (G::TW_SMEM) {      // one-warp-per-frame plans read their twiddles from shared memory
+        float2* tsm = reinterpret_cast<float2*>(smem_raw + G::SMEM_BYTES);
+        for (int i = threadIdx.x; i < (int)(G::TW_BYTES / sizeof(float2)); i += G::CTA) tsm[i] = __ldg(&tw[i]);
+        __syncthreads();
+        tw = tsm;
+    }
     const WelchSig sg = a.sigs[blockIdx.y];
     float acc[P];
 #pragma unroll
@@ -221,7 +227,7 @@ welch_accum_kernel(const WelchArgs a) {
 #pragma unroll
             for (int q = 0; q < P; q++) v[q] = make_float2(0.f, 0.f);
         }
-        fft_frame<float, N>(v, t, sm, tw);
+        fft_frame<float, N, false>(v, t, sm, tw, nullptr);
         if (valid) {
 #pragma unroll
             for (int q = 0; q < P; q++) acc[q] += __fmaf_rn(v[q].x, v[q].x, v[q].y * v[q].y);

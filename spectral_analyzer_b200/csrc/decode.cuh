@@ -28,18 +28,26 @@ __device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 
 template <typename T, int DK> struct Loader;
 
 template <typename T> struct Loader<T, DK_CF32> {
+    using raw_t = uint2;
     template <bool SWAP>
     static __device__ __forceinline__ cpx<T> load(const LoadParams& lp, int64_t i) {
-        uint2 w = __ldg(reinterpret_cast<const uint2*>(lp.base) + i);
+        return decode<SWAP>(lp, __ldg(reinterpret_cast<const uint2*>(lp.base) + i));
+    }
+    template <bool SWAP>
+    static __device__ __forceinline__ cpx<T> decode(const LoadParams&, uint2 w) {
         if constexpr (SWAP) { w.x = bswap32(w.x); w.y = bswap32(w.y); }
         return mk2<T>((T)__uint_as_float(w.x), (T)__uint_as_float(w.y));
     }
 };
 
 template <typename T> struct Loader<T, DK_CI16> {
+    using raw_t = uint32_t;
     template <bool SWAP>
     static __device__ __forceinline__ cpx<T> load(const LoadParams& lp, int64_t i) {
-        uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(lp.base) + i);
+        return decode<SWAP>(lp, __ldg(reinterpret_cast<const uint32_t*>(lp.base) + i));
+    }
+    template <bool SWAP>
+    static __device__ __forceinline__ cpx<T> decode(const LoadParams&, uint32_t w) {
         if constexpr (SWAP) w = __byte_perm(w, 0, 0x2301);
         if constexpr (sizeof(T) == 4) {
             w ^= 0x80008000u;                                   // two's complement -> offset binary
@@ -54,9 +62,14 @@ template <typename T> struct Loader<T, DK_CI16> {
 };
 
 template <typename T> struct Loader<T, DK_C8> {
+    using raw_t = uint16_t;
     template <bool SWAP>
     static __device__ __forceinline__ cpx<T> load(const LoadParams& lp, int64_t i) {
-        uint32_t w = __ldg(reinterpret_cast<const uint16_t*>(lp.base) + i);
+        return decode<SWAP>(lp, __ldg(reinterpret_cast<const uint16_t*>(lp.base) + i));
+    }
+    template <bool SWAP>
+    static __device__ __forceinline__ cpx<T> decode(const LoadParams& lp, uint16_t w16) {
+        uint32_t w = w16;
         w ^= lp.c8_flip;
         const float a = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440)) - 8388608.0f;   // byte 0
         const float b = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7441)) - 8388608.0f;   // byte 1
@@ -66,9 +79,13 @@ template <typename T> struct Loader<T, DK_C8> {
 };
 
 template <typename T> struct Loader<T, DK_CF64> {
+    using raw_t = uint4;
     template <bool SWAP>
     static __device__ __forceinline__ cpx<T> load(const LoadParams& lp, int64_t i) {
-        uint4 w = __ldg(reinterpret_cast<const uint4*>(lp.base) + i);
+        return decode<SWAP>(lp, __ldg(reinterpret_cast<const uint4*>(lp.base) + i));
+    }
+    template <bool SWAP>
+    static __device__ __forceinline__ cpx<T> decode(const LoadParams&, uint4 w) {
         if constexpr (SWAP) {
             uint32_t a = bswap32(w.y), b = bswap32(w.x), c = bswap32(w.w), d = bswap32(w.z);
             w = make_uint4(a, b, c, d);

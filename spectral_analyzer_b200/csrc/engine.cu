@@ -35,9 +35,9 @@ static std::vector<SpecKernelInfo>& spec_registry() {
 }
 void register_spec_kernel(const SpecKernelInfo& k) { spec_registry().push_back(k); }
 
-const SpecKernelInfo* find_spec_kernel(int prec, int n, int dk, int win) {
+const SpecKernelInfo* find_spec_kernel(int prec, int n, int dk, int win, int tma) {
     for (const auto& k : spec_registry())
-        if (k.prec == prec && k.n == n && k.dk == dk && k.win == win) return &k;
+        if (k.prec == prec && k.n == n && k.dk == dk && k.win == win && k.tma == tma) return &k;
     return nullptr;
 }
 
@@ -59,7 +59,8 @@ void host_window(int window_id, int n, std::vector<double>& w) {
     }
 }
 
-// Stockham twiddles in the [pass][s][m][t] order fft_pass reads them (fft_core.cuh)
+// Stockham twiddles in the order fft_pass reads them (fft_core.cuh): per pass, per sub-butterfly s,
+// per m' < R/2, per thread t one PAIR (W for element m', W for element m' + R/2).
 static void host_twiddles(int n, int p, int np, const int* radix, std::vector<double>& re, std::vector<double>& im) {
     const int tpf = n / p;
     re.assign((size_t)(np - 1) * n, 1.0);
@@ -69,15 +70,17 @@ static void host_twiddles(int n, int p, int np, const int* radix, std::vector<do
     for (int pass = 1; pass < np; pass++) {
         const int r = radix[pass], s_cnt = p / r;
         for (int s = 0; s < s_cnt; s++)
-            for (int m = 0; m < r; m++)
-                for (int t = 0; t < tpf; t++) {
-                    const int j = t + tpf * s;
-                    const long long e = (long long)(j % ns) * m * (n / (ns * r));
-                    const double ang = -two_pi * (double)(e % n) / (double)n;
-                    const size_t idx = (size_t)(pass - 1) * n + (size_t)(s * r + m) * tpf + t;
-                    re[idx] = std::cos(ang);
-                    im[idx] = std::sin(ang);
-                }
+            for (int mp = 0; mp < r / 2; mp++)
+                for (int t = 0; t < tpf; t++)
+                    for (int h = 0; h < 2; h++) {
+                        const int m = mp + h * (r / 2);
+                        const int j = t + tpf * s;
+                        const long long e = (long long)(j % ns) * m * (n / (ns * r));
+                        const double ang = -two_pi * (double)(e % n) / (double)n;
+                        const size_t idx = (size_t)(pass - 1) * n + ((size_t)(s * (r / 2) + mp) * tpf + t) * 2 + h;
+                        re[idx] = std::cos(ang);
+                        im[idx] = std::sin(ang);
+                    }
         ns *= r;
     }
 }
@@ -199,7 +202,13 @@ int Engine::launch_spectrogram(const void* d_iq, uint64_t n_samples, const sa_sp
     if (p.n_frames == 0) return SA_OK;
     const int dk = dtype_kind(p.dtype);
     const int win = (prec == SA_PREC_F64) ? 1 : (p.window != SA_WIN_RECT ? 1 : 0);
-    const SpecKernelInfo* k = find_spec_kernel(prec, (int)p.nfft, dk, win);
+    // TMA-staged variant (needs every frame start 16-byte aligned), else the LDG kernel
+    const uint64_t iq_b = (uint64_t)sa_bytes_per_iq(p.dtype);
+    const bool aligned = ((uintptr_t)d_iq % 16 == 0) && ((p.start_sample * iq_b) % 16 == 0) && ((p.hop * iq_b) % 16 == 0);
+    // (opt-in: measured 2 % slower than the LDG + L2-prefetch kernel on B200, see DESIGN.md ablations)
+    static const bool use_tma = getenv("SA_USE_TMA") != nullptr;
+    const SpecKernelInfo* k = (aligned && use_tma) ? find_spec_kernel(prec, (int)p.nfft, dk, win, 1) : nullptr;
+    if (!k) k = find_spec_kernel(prec, (int)p.nfft, dk, win, 0);
     if (!k) return set_error(SA_ERR_UNSUPPORTED, "no kernel for nfft %u precision %s dtype %d", p.nfft,
                              prec == SA_PREC_F64 ? "f64" : "f32", p.dtype);
     SpecArgs a;

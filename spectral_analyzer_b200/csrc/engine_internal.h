@@ -6,13 +6,13 @@
 #include <vector>
 
 #include "../../include/sa_engine.h"
-#include "spectrogram_kernel.cuh"
+#include "spectrogram_tma_kernel.cuh"
 
 namespace sa {
 
 int set_error(int code, const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
-const SpecKernelInfo* find_spec_kernel(int prec, int n, int dk, int win);
+const SpecKernelInfo* find_spec_kernel(int prec, int n, int dk, int win, int tma);
 void host_window(int window_id, int n, std::vector<double>& w);
 int dtype_kind(int dtype);
 void fill_load_params(LoadParams& lp, const void* base, int dtype, int big_endian);

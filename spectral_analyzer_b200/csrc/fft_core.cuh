@@ -7,8 +7,9 @@
 // Layout of one transform of N points over TPF = N/P threads (P points per thread):
 //   at the start of every pass thread t holds elements  t + TPF*q  (q = 0..P-1) in v[q];
 //   a pass of radix R runs S = P/R independent radix-R butterflies per thread on the register
-//   sub-arrays v[s + m*S] (m = 0..R-1), preceded (for passes after the first) by the Stockham
-//   twiddle W_N^{(j mod Ns) * m * N/(Ns*R)}, j = t + TPF*s, Ns = product of earlier radices;
+//   sub-arrays v[s + m*S] (m = 0..R-1); passes after the first multiply by the Stockham twiddle
+//   W_N^{(j mod Ns) * m * N/(Ns*R)}, j = t + TPF*s, Ns = product of earlier radices, fused into
+//   the first butterfly stage (as is the window in pass 0);
 //   the pass writes element (j/Ns)*Ns*R + (j mod Ns) + m*Ns to shared memory and every thread
 //   reads back t + TPF*q.  After the last pass v[q] = X[t + TPF*q] (no final exchange), so both
 //   the global loads of pass 0 and the global stores of the epilogue are coalesced.
@@ -17,6 +18,21 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+// tuning knobs (kernel K2): resident warps per SM of the one-warp-per-frame FP32
+// kernels, and the widest plan that keeps its window rows in shared memory instead of registers
+#ifndef SA_WARPS_1WPF
+#define SA_WARPS_1WPF 16
+#endif
+#ifndef SA_CTA_1WPF
+#define SA_CTA_1WPF 128
+#endif
+#ifndef SA_WIN_SMEM_MAX_TPF
+#define SA_WIN_SMEM_MAX_TPF 128
+#endif
+#ifndef SA_TW_SMEM_MAX_TPF
+#define SA_TW_SMEM_MAX_TPF 32
+#endif
 
 namespace sa {
 
@@ -85,23 +101,138 @@ __device__ __forceinline__ void dit_stages(cpx<T> (&a)[R]) {
     if constexpr (LEN < R) dit_stages<T, R, LEN * 2>(a);
 }
 
-// In-place radix-R DFT (natural in, natural out) on v[OFF + STR*m], m = 0..R-1.
-template <typename T, int R, int STR, int OFF, int P>
-__device__ __forceinline__ void radix_fft(cpx<T> (&v)[P]) {
+// ---- packed FP32 (Blackwell FFMA2 / FADD2 / FMUL2: two FP32 lanes per issue slot) ----
+// A packed value is a 64-bit register pair (lo, hi).  With the pairing (a[i], a[i + R/2]) of the
+// bit-reversed work array, the DIT stages of span 4 .. R/2 run the SAME butterfly (same twiddle) in both
+// lanes, so each issue slot retires two butterfly operations; twiddle constants are scalar immediates
+// that FFMA2 broadcasts.  The first stage (span 2, fused multipliers) and the last stage (span R, lanes
+// interact) stay scalar and absorb the re-pairing for free.
+typedef unsigned long long pk2;
+__device__ __forceinline__ pk2 pack2(float lo, float hi) { pk2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(pk2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ pk2 bcast2(float c) { return pack2(c, c); }
+__device__ __forceinline__ pk2 fma2(pk2 a, pk2 b, pk2 c) { pk2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ pk2 add2(pk2 a, pk2 b) { pk2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ pk2 sub2(pk2 a, pk2 b) { pk2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ pk2 mul2(pk2 a, pk2 b) { pk2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+// negation written on the scalar halves so that ptxas folds it into the operand modifier of FFMA2/FADD2
+__device__ __forceinline__ pk2 neg2(pk2 a) { float lo, hi; unpack2(a, lo, hi); return pack2(-lo, -hi); }
+
+// two DIT butterflies at once: (a, b) <- (a + W b, a - W b), W = W32^q in both lanes
+__device__ __forceinline__ void bfly2(pk2& ar, pk2& ai, pk2& br, pk2& bi, const int q) {
+    if (q == 0) {
+        const pk2 xr = br, xi = bi;
+        br = sub2(ar, xr); bi = sub2(ai, xi);
+        ar = add2(ar, xr); ai = add2(ai, xi);
+    } else if (q == 8) {            // W = -i : W b = (b.im, -b.re)
+        const pk2 xr = br, xi = bi;
+        br = sub2(ar, xi); bi = add2(ai, xr);
+        ar = add2(ar, xi); ai = sub2(ai, xr);
+    } else {
+        const float wr = (float)w32_re(q), wi = (float)w32_im(q);
+        const pk2 o_r = fma2(bcast2(-wi), bi, fma2(bcast2(wr), br, ar));
+        const pk2 o_i = fma2(bcast2(wi), br, fma2(bcast2(wr), bi, ai));
+        br = fma2(bcast2(2.0f), ar, neg2(o_r));
+        bi = fma2(bcast2(2.0f), ai, neg2(o_i));
+        ar = o_r; ai = o_i;
+    }
+}
+
+// packed stages of span LEN .. H on H = R/2 packed positions
+template <int H, int LEN>
+__device__ __forceinline__ void dit_stages_packed(pk2 (&pr)[H], pk2 (&pi)[H]) {
+#pragma unroll
+    for (int b = 0; b < H; b += LEN) {
+#pragma unroll
+        for (int k = 0; k < LEN / 2; k++) bfly2(pr[b + k], pi[b + k], pr[b + k + LEN / 2], pi[b + k + LEN / 2], k * (32 / LEN));
+    }
+    if constexpr (LEN < H) dit_stages_packed<H, LEN * 2>(pr, pi);
+}
+
+// stages of span 4 .. R on the bit-reversed work array (stage of span 2 already done)
+template <typename T, int R>
+__device__ __forceinline__ void dit_tail(cpx<T> (&a)[R]) {
+    if constexpr (sizeof(T) == 4 && R >= 8) {
+        constexpr int H = R / 2;
+        pk2 pr[H], pi[H];
+#pragma unroll
+        for (int i = 0; i < H; i++) { pr[i] = pack2(a[i].x, a[i + H].x); pi[i] = pack2(a[i].y, a[i + H].y); }
+        dit_stages_packed<H, 4>(pr, pi);
+#pragma unroll
+        for (int i = 0; i < H; i++) { unpack2(pr[i], a[i].x, a[i + H].x); unpack2(pi[i], a[i].y, a[i + H].y); }
+#pragma unroll
+        for (int k = 0; k < H; k++) bfly<T>(a[k], a[k + H], k * (32 / R));     // last stage: lanes interact
+    } else {
+        if constexpr (R > 2) dit_stages<T, R, 4>(a);
+    }
+}
+
+// Multiplier fused into the first DIT stage of a radix-R butterfly:
+//   MUL_NONE  plain
+//   MUL_REAL  x[m] *= window; wr[2m], wr[2m+1] hold the factors of elements m and m + R/2 (pass 0)
+//   MUL_CPX   x[m] *= tw[m]  (m >= 1; tw[0] == 1)    (Stockham twiddle, later passes)
+enum { MUL_NONE = 0, MUL_REAL = 1, MUL_CPX = 2 };
+
+template <typename T> struct TwPair { cpx<T> lo, hi; };     // twiddles of elements m and m + R/2
+// TW_SMEM: the table was copied to shared memory (plain loads); otherwise read-only global loads
+template <bool TW_SMEM> __device__ __forceinline__ TwPair<float> ldg_tw(const TwPair<float>* p) {
+    float4 w;
+    if constexpr (TW_SMEM) w = *reinterpret_cast<const float4*>(p);
+    else w = __ldg(reinterpret_cast<const float4*>(p));
+    TwPair<float> r; r.lo = make_float2(w.x, w.y); r.hi = make_float2(w.z, w.w); return r;
+}
+template <bool TW_SMEM> __device__ __forceinline__ TwPair<double> ldg_tw(const TwPair<double>* p) {
+    TwPair<double> r;
+    if constexpr (TW_SMEM) { r.lo = reinterpret_cast<const double2*>(p)[0]; r.hi = reinterpret_cast<const double2*>(p)[1]; }
+    else { r.lo = __ldg(reinterpret_cast<const double2*>(p)); r.hi = __ldg(reinterpret_cast<const double2*>(p) + 1); }
+    return r;
+}
+
+// In-place radix-R DFT (natural in, natural out) on v[OFF + STR*m], m = 0..R-1.  The first DIT
+// stage pairs (m, m + R/2); an element-wise multiplier is folded into it:
+//   real  : (wa a + wb b, wa a - wb b)            6 ops per component pair instead of 8
+//   cpx   : t = ta a ; o0 = t + tb b ; o1 = 2t - o0   10 FMA-class ops instead of 12
+template <typename T, int R, int STR, int OFF, int P, int MUL, bool TW_SMEM>
+__device__ __forceinline__ void radix_fft(cpx<T> (&v)[P], const T* __restrict__ wr,
+                                          const TwPair<T>* __restrict__ tw, const int tw_stride) {
     static_assert(R == 2 || R == 4 || R == 8 || R == 16 || R == 32, "radix");
     cpx<T> a[R];
 #pragma unroll
-    for (int m = 0; m < R; m++) a[bitrev_c(m, R)] = v[OFF + STR * m];
-    dit_stages<T, R, 2>(a);
+    for (int m = 0; m < R / 2; m++) {
+        const cpx<T> x = v[OFF + STR * m], y = v[OFF + STR * (m + R / 2)];
+        cpx<T> o0, o1;
+        if constexpr (MUL == MUL_REAL) {
+            static_assert(MUL != MUL_REAL || (STR == 1 && OFF == 0), "the window is applied in pass 0 (one butterfly per thread)");
+            const cpx<T> wp = *reinterpret_cast<const cpx<T>*>(wr + 2 * m);
+            const T wa = wp.x, wb = wp.y;
+            const T tx = wa * x.x, ty = wa * x.y;
+            o0 = mk2<T>(fma_t(wb, y.x, tx), fma_t(wb, y.y, ty));
+            o1 = mk2<T>(fma_t(-wb, y.x, tx), fma_t(-wb, y.y, ty));
+        } else if constexpr (MUL == MUL_CPX) {
+            const TwPair<T> w = ldg_tw<TW_SMEM>(tw + (size_t)m * tw_stride);
+            cpx<T> t = x;
+            if (m != 0) t = mk2<T>(fma_t(-w.lo.y, x.y, w.lo.x * x.x), fma_t(w.lo.y, x.x, w.lo.x * x.y));
+            o0 = mk2<T>(fma_t(-w.hi.y, y.y, fma_t(w.hi.x, y.x, t.x)), fma_t(w.hi.y, y.x, fma_t(w.hi.x, y.y, t.y)));
+            o1 = mk2<T>(fma_t((T)2, t.x, -o0.x), fma_t((T)2, t.y, -o0.y));
+        } else {
+            o0 = mk2<T>(x.x + y.x, x.y + y.y);
+            o1 = mk2<T>(x.x - y.x, x.y - y.y);
+        }
+        a[bitrev_c(m, R)] = o0;
+        a[bitrev_c(m, R) + 1] = o1;
+    }
+    dit_tail<T, R>(a);
 #pragma unroll
     for (int m = 0; m < R; m++) v[OFF + STR * m] = a[m];
 }
 
-template <typename T, int R, int S, int P, int I>
+template <typename T, int R, int S, int P, int MUL, bool TW_SMEM, int I>
 struct RadixAll {
-    static __device__ __forceinline__ void run(cpx<T> (&v)[P]) {
-        radix_fft<T, R, S, I, P>(v);
-        if constexpr (I + 1 < S) RadixAll<T, R, S, P, I + 1>::run(v);
+    static __device__ __forceinline__ void run(cpx<T> (&v)[P], const T* __restrict__ wr,
+                                               const TwPair<T>* __restrict__ tw, const int tpf) {
+        // twiddle pairs of sub-butterfly I sit at tw[(I*(R/2) + m) * tpf]
+        radix_fft<T, R, S, I, P, MUL, TW_SMEM>(v, wr, tw + (size_t)I * (R / 2) * tpf, tpf);
+        if constexpr (I + 1 < S) RadixAll<T, R, S, P, MUL, TW_SMEM, I + 1>::run(v, wr, tw, tpf);
     }
 };
 
@@ -136,68 +267,83 @@ template <typename T, int N> struct Geo {
     using PL = Plan<T, N>;
     static constexpr int P = PL::P;
     static constexpr int TPF = N / P;                        // threads per frame
-    static constexpr int CTA = TPF > 128 ? TPF : 128;        // threads per CTA
+    // threads per CTA: one-warp-per-frame FP32 plans use a larger CTA so that fewer copies of the
+    // shared twiddle/window tables sit in an SM
+    static constexpr int CTA = (sizeof(T) == 4 && TPF == 32) ? SA_CTA_1WPF : (TPF > 128 ? TPF : 128);
     static constexpr int FPC = CTA / TPF;                    // frames per CTA pass
-    static constexpr int MINB = 512 / CTA;                   // CTAs per SM the register cap allows (128 regs)
+    // resident CTAs per SM the register cap is set for: one-warp-per-frame FP32 kernels run 5 warps per
+    // scheduler (96 registers), everything else 4 (128 registers)
+    static constexpr int MINB = (sizeof(T) == 4 && TPF <= 32) ? SA_WARPS_1WPF * 32 / CTA : 512 / CTA;
+    static constexpr int WROW = P + 2;                       // window row per thread: P factors + 2 pad (bank spread)
+    static constexpr bool WIN_SMEM = TPF <= SA_WIN_SMEM_MAX_TPF;             // window rows in shared memory, else in registers
+    static constexpr size_t WIN_BYTES = WIN_SMEM ? (size_t)TPF * WROW * sizeof(T) : 0;
     static constexpr int R0 = PL::radix(0);
-    static constexpr int SM_ELEMS = N + N / R0;              // padded elements per frame
+    static constexpr int PADW = sizeof(T) == 4 ? 2 : 1;      // pad elements per R0 (keeps 16-byte alignment)
+    static constexpr int SM_ELEMS = N + (N / R0) * PADW;     // padded elements per frame
     static constexpr size_t SMEM_BYTES = (size_t)FPC * SM_ELEMS * sizeof(cpx<T>);
+    // one-warp-per-frame plans keep the Stockham twiddle table in shared memory as well
+    static constexpr bool TW_SMEM = TPF <= SA_TW_SMEM_MAX_TPF;
+    static constexpr size_t TW_BYTES = TW_SMEM ? (size_t)(PL::NP - 1) * N * sizeof(cpx<T>) : 0;
+    static constexpr size_t EXTRA_WIN_OFF = SMEM_BYTES + TW_BYTES;   // window rows follow the twiddles
     static constexpr int TW_ELEMS = (PL::NP - 1) * N;        // twiddle table entries
     __host__ __device__ static constexpr int ns(int pass) { int r = 1; for (int i = 0; i < pass; i++) r *= PL::radix(i); return r; }
 };
 
-// padded shared-memory index: one element of padding per R0 elements keeps the stride-R0
-// writes of pass 0 and the unit-stride reads conflict-free
-template <int R0> __device__ __forceinline__ int pad_idx(int i) { return i + i / R0; }
+// padded shared-memory index: PADW elements (16 bytes) of padding per R0 elements keep the
+// stride-R0 128-bit writes of pass 0 and the unit-stride reads conflict-free
+template <int R0, int PADW> __device__ __forceinline__ int pad_idx(int i) { return i + (i / R0) * PADW; }
 
 template <int TPF> __device__ __forceinline__ void frame_sync() {
     if constexpr (TPF <= 32) __syncwarp(); else __syncthreads();
 }
 
-// One pass: optional Stockham twiddle, S radix-R butterflies, and (unless last) the exchange.
-template <typename T, int N, int PASS>
+// One pass: S radix-R butterflies (window or Stockham twiddle fused into their first stage) and,
+// unless it is the last pass, the exchange through shared memory.
+template <typename T, int N, int PASS, bool WIN>
 __device__ __forceinline__ void fft_pass(cpx<T> (&v)[Plan<T, N>::P], const int t, cpx<T>* __restrict__ sm,
-                                         const cpx<T>* __restrict__ tw) {
+                                         const cpx<T>* __restrict__ tw, const T* __restrict__ win) {
     using G = Geo<T, N>;
     using PL = Plan<T, N>;
     constexpr int P = G::P, TPF = G::TPF, R = PL::radix(PASS), S = P / R, NS = G::ns(PASS);
-    if constexpr (PASS > 0) {
-        const cpx<T>* twp = tw + (size_t)(PASS - 1) * N + t;
-#pragma unroll
-        for (int s = 0; s < S; s++) {
-#pragma unroll
-            for (int m = 1; m < R; m++) {
-                const cpx<T> w = __ldg(&twp[(s * R + m) * TPF]);
-                const cpx<T> x = v[s + m * S];
-                v[s + m * S] = mk2<T>(fma_t(-w.y, x.y, w.x * x.x), fma_t(w.y, x.x, w.x * x.y));
-            }
-        }
+    if constexpr (PASS == 0) {
+        RadixAll<T, R, S, P, WIN ? MUL_REAL : MUL_NONE, false, 0>::run(v, win, nullptr, TPF);
+    } else {
+        const TwPair<T>* twp = reinterpret_cast<const TwPair<T>*>(tw) + (size_t)(PASS - 1) * (N / 2) + t;
+        RadixAll<T, R, S, P, MUL_CPX, G::TW_SMEM, 0>::run(v, nullptr, twp, TPF);
     }
-    RadixAll<T, R, S, P, 0>::run(v);
     if constexpr (PASS + 1 < PL::NP) {
         frame_sync<TPF>();   // every reader of the previous exchange (or previous frame) is done
 #pragma unroll
         for (int s = 0; s < S; s++) {
             const int j = t + TPF * s;
             const int base = (j / NS) * (NS * R) + (j % NS);
+            if constexpr (NS == 1 && sizeof(T) == 4) {
+                // pass 0: R consecutive elements per butterfly -> 128-bit stores of element pairs
+                float4* dst = reinterpret_cast<float4*>(sm + pad_idx<G::R0, G::PADW>(base));
 #pragma unroll
-            for (int m = 0; m < R; m++) sm[pad_idx<G::R0>(base + m * NS)] = v[s + m * S];
+                for (int m = 0; m < R; m += 2)
+                    dst[m / 2] = make_float4(v[s + m * S].x, v[s + m * S].y, v[s + (m + 1) * S].x, v[s + (m + 1) * S].y);
+            } else {
+#pragma unroll
+                for (int m = 0; m < R; m++) sm[pad_idx<G::R0, G::PADW>(base + m * NS)] = v[s + m * S];
+            }
         }
         frame_sync<TPF>();
 #pragma unroll
-        for (int q = 0; q < P; q++) v[q] = sm[pad_idx<G::R0>(t + TPF * q)];
+        for (int q = 0; q < P; q++) v[q] = sm[pad_idx<G::R0, G::PADW>(t + TPF * q)];
     }
 }
 
-// Full transform of the registers of one frame.
-template <typename T, int N>
+// Full transform of the registers of one frame; win (T[P], thread-private) multiplies the inputs
+// when WIN is set.
+template <typename T, int N, bool WIN>
 __device__ __forceinline__ void fft_frame(cpx<T> (&v)[Plan<T, N>::P], const int t, cpx<T>* __restrict__ sm,
-                                          const cpx<T>* __restrict__ tw) {
+                                          const cpx<T>* __restrict__ tw, const T* __restrict__ win) {
     using PL = Plan<T, N>;
-    fft_pass<T, N, 0>(v, t, sm, tw);
-    if constexpr (PL::NP > 1) fft_pass<T, N, 1>(v, t, sm, tw);
-    if constexpr (PL::NP > 2) fft_pass<T, N, 2>(v, t, sm, tw);
-    if constexpr (PL::NP > 3) fft_pass<T, N, 3>(v, t, sm, tw);
+    fft_pass<T, N, 0, WIN>(v, t, sm, tw, win);
+    if constexpr (PL::NP > 1) fft_pass<T, N, 1, WIN>(v, t, sm, tw, win);
+    if constexpr (PL::NP > 2) fft_pass<T, N, 2, WIN>(v, t, sm, tw, win);
+    if constexpr (PL::NP > 3) fft_pass<T, N, 3, WIN>(v, t, sm, tw, win);
 }
 
 }  // namespace sa

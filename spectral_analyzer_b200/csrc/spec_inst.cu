@@ -1,6 +1,6 @@
 // spec_inst.cu -- explicit instantiations of spectrogram_kernel, one object file per
 // (precision, nfft) so the build parallelises: compiled with -DSA_INST_PREC=1|2 -DSA_INST_N=<nfft>.
-#include "spectrogram_kernel.cuh"
+#include "spectrogram_tma_kernel.cuh"
 
 #ifndef SA_INST_PREC
 #error "compile with -DSA_INST_PREC=1|2 -DSA_INST_N=<nfft>"
@@ -18,6 +18,15 @@ struct Registrar {
         register_spec_kernel(make_spec_info<float, SA_INST_N, DK_CI16, true>(1));
         register_spec_kernel(make_spec_info<float, SA_INST_N, DK_C8, false>(1));
         register_spec_kernel(make_spec_info<float, SA_INST_N, DK_C8, true>(1));
+#if SA_INST_N == 1024
+        // one warp per frame: TMA-staged variants, taken when the frames are 16-byte aligned
+        register_spec_kernel(make_spec_tma_info<float, SA_INST_N, DK_CF32, false>(1));
+        register_spec_kernel(make_spec_tma_info<float, SA_INST_N, DK_CF32, true>(1));
+        register_spec_kernel(make_spec_tma_info<float, SA_INST_N, DK_CI16, false>(1));
+        register_spec_kernel(make_spec_tma_info<float, SA_INST_N, DK_CI16, true>(1));
+        register_spec_kernel(make_spec_tma_info<float, SA_INST_N, DK_C8, false>(1));
+        register_spec_kernel(make_spec_tma_info<float, SA_INST_N, DK_C8, true>(1));
+#endif
 #else
         // FP64 arithmetic (cf64 input, or any input when the caller asks for SA_PREC_F64);
         // always windowed -- a rectangular window is a table of ones

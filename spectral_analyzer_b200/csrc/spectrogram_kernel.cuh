@@ -37,14 +37,43 @@ __device__ __forceinline__ float lg2_approx(float x) { float r; asm("lg2.approx.
 __device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 // SpectralService.java:80-81: 20*log10(abs + 1e-10)
-__device__ __forceinline__ float to_db(float re, float im, int mode) {
+template <int MODE> __device__ __forceinline__ float to_db(float re, float im) {
     const float p = __fmaf_rn(re, re, im * im);
-    if (mode == DBM_MAG_1E10) return 6.02059991327962f * lg2_approx(sqrt_approx(p) + 1e-10f);
+    if constexpr (MODE == DBM_MAG_1E10) return 6.02059991327962f * lg2_approx(sqrt_approx(p) + 1e-10f);
     return 3.01029995663981f * lg2_approx(p + 1e-20f);
 }
-__device__ __forceinline__ double to_db(double re, double im, int mode) {
-    if (mode == DBM_MAG_1E10) return 20.0 * log10(sqrt(re * re + im * im) + 1e-10);
+template <int MODE> __device__ __forceinline__ double to_db(double re, double im) {
+    if constexpr (MODE == DBM_MAG_1E10) return 20.0 * log10(sqrt(re * re + im * im) + 1e-10);
     return 10.0 * log10(re * re + im * im + 1e-20);
+}
+
+// dB of all P bins of a thread.  FP32 fast path for MAG_1E10: when |X| >= 2^-9 the FP32 sum
+// |X| + 1e-10 rounds back to |X| (ulp(|X|) >= 2^-32, so 1e-10 is below half an ulp), hence
+// 20 log10(|X| + 1e-10) equals 10 log10(|X|^2) and the square root is skipped; threads holding a
+// bin with |X|^2 < 2^-18 take the literal form.
+template <typename T, int P, int MODE>
+__device__ __forceinline__ void bins_to_db(const cpx<T> (&v)[P], T (&db)[P]) {
+    if constexpr (sizeof(T) == 4 && MODE == DBM_MAG_1E10) {
+        // |X|^2 and the dB scale run two bins per issue slot (FMUL2 / FFMA2)
+        float pmin = 3.0e38f;
+#pragma unroll
+        for (int q = 0; q < P; q += 2) {
+            const pk2 xr = pack2(v[q].x, v[q + 1].x), xi = pack2(v[q].y, v[q + 1].y);
+            unpack2(fma2(xr, xr, mul2(xi, xi)), db[q], db[q + 1]);
+            pmin = fminf(pmin, fminf(db[q], db[q + 1]));
+        }
+        if (pmin >= 3.814697265625e-6f) {      // 2^-18
+#pragma unroll
+            for (int q = 0; q < P; q += 2)
+                unpack2(mul2(pack2(lg2_approx(db[q]), lg2_approx(db[q + 1])), bcast2(3.01029995663981f)), db[q], db[q + 1]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < P; q++) db[q] = 6.02059991327962f * lg2_approx(sqrt_approx(db[q]) + 1e-10f);
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < P; q++) db[q] = to_db<MODE>(v[q].x, v[q].y);
+    }
 }
 
 // getColorForMagnitude (MainController.java:926-957) on float components, channels packed
@@ -55,13 +84,108 @@ __device__ __forceinline__ uint32_t colormap_rgba(float db, const SpecArgs& a) {
     float r, g, b;
     if (a.cmap == 1) {                          // Heatmap :944-953
         if (n < 0.2f)      { r = 0.f; g = 0.f; b = 0.f; }
-        else if (n < 0.5f) { const float u = (n - 0.2f) / 0.3f; r = u; g = 0.f; b = 1.0f + (0.0f - 1.0f) * u; }
-        else               { const float u = (n - 0.5f) / 0.5f; r = 1.f; g = u; b = 0.f; }
+        else if (n < 0.5f) { const float u = (n - 0.2f) * (1.0f / 0.3f); r = u; g = 0.f; b = 1.0f - u; }
+        else               { const float u = (n - 0.5f) * 2.0f; r = 1.f; g = u; b = 0.f; }
     } else { r = g = b = n; }                   // Grayscale :939-942
     const uint32_t R = (uint32_t)floorf(__fmaf_rn(r, 255.0f, 0.5f));
     const uint32_t G = (uint32_t)floorf(__fmaf_rn(g, 255.0f, 0.5f));
     const uint32_t B = (uint32_t)floorf(__fmaf_rn(b, 255.0f, 0.5f));
     return R | (G << 8) | (B << 16) | 0xFF000000u;
+}
+
+template <int DK> __host__ __device__ constexpr int bytes_per_iq_kind() {
+    return DK == DK_CF32 ? 8 : DK == DK_CI16 ? 4 : DK == DK_C8 ? 2 : 16;
+}
+
+// EOF row: frames that would read past the end of the buffer (MainController.java:994-998)
+template <typename T, int N>
+__device__ __forceinline__ void store_fill(const SpecArgs& a, const long long frame, const int t) {
+    constexpr int P = Geo<T, N>::P, TPF = Geo<T, N>::TPF;
+    const size_t row = (size_t)frame * N;
+    if (a.out_kind == OUT_F32_DB) {
+        float* o = reinterpret_cast<float*>(a.out) + row;
+#pragma unroll
+        for (int q = 0; q < P; q++) o[t + TPF * q] = (float)a.eof_fill;
+    } else if (a.out_kind == OUT_F64_DB) {
+        double* o = reinterpret_cast<double*>(a.out) + row;
+#pragma unroll
+        for (int q = 0; q < P; q++) o[t + TPF * q] = a.eof_fill;
+    } else {
+        uint32_t* o = reinterpret_cast<uint32_t*>(a.out) + row;
+        const uint32_t px = colormap_rgba((float)a.eof_fill, a);
+#pragma unroll
+        for (int q = 0; q < P; q++) o[t + TPF * q] = px;
+    }
+}
+
+// Copies the twiddle table into shared memory (plans with Geo::TW_SMEM) and returns the pointer the
+// passes read; the caller must __syncthreads() (setup_window does) or sync before first use.
+template <typename T, int N>
+__device__ __forceinline__ const cpx<T>* setup_twiddles(const SpecArgs& a, unsigned char* smem_raw) {
+    using G = Geo<T, N>;
+    const cpx<T>* tw = reinterpret_cast<const cpx<T>*>(a.twiddle);
+    if constexpr (G::TW_SMEM) {
+        cpx<T>* tsm = reinterpret_cast<cpx<T>*>(smem_raw + G::SMEM_BYTES);
+        for (int i = threadIdx.x; i < (int)(G::TW_BYTES / sizeof(cpx<T>)); i += G::CTA) tsm[i] = __ldg(&tw[i]);
+        __syncthreads();
+        return tsm;
+    } else {
+        return tw;
+    }
+}
+
+// Window factors in pair order (element m, element m + P/2), m = 0..P/2-1, as the first butterfly
+// stage consumes them: a padded row per thread in shared memory (one 8/16-byte load per butterfly),
+// or registers for the wide plans.  Returns the calling thread's row.
+template <typename T, int N>
+__device__ __forceinline__ const T* setup_window(const SpecArgs& a, unsigned char* wsm_raw,
+                                                 T (&win_reg)[Geo<T, N>::WIN_SMEM ? 1 : Geo<T, N>::P], const int t) {
+    using G = Geo<T, N>;
+    constexpr int P = G::P, TPF = G::TPF;
+    const T* w = reinterpret_cast<const T*>(a.window);
+    if constexpr (G::WIN_SMEM) {
+        T* wsm = reinterpret_cast<T*>(wsm_raw);
+        for (int i = threadIdx.x; i < TPF * P; i += G::CTA) {
+            const int tt = i % TPF, e = i / TPF;             // element e of thread tt: sample tt + TPF*e
+            const int slot = e < P / 2 ? 2 * e : 2 * (e - P / 2) + 1;
+            wsm[tt * G::WROW + slot] = __ldg(&w[i]);
+        }
+        __syncthreads();
+        return wsm + t * G::WROW;
+    } else {
+#pragma unroll
+        for (int m = 0; m < P / 2; m++) {
+            win_reg[2 * m] = __ldg(&w[t + TPF * m]);
+            win_reg[2 * m + 1] = __ldg(&w[t + TPF * (m + P / 2)]);
+        }
+        return win_reg;
+    }
+}
+
+// Epilogue of one frame: |X| -> dB (-> colour), written as the fft-shifted row
+// out[(k + N/2) % N] (SpectralService.java:76-82), k = t + TPF*q.
+template <typename T, int N>
+__device__ __forceinline__ void store_row(const SpecArgs& a, const long long frame, const int t,
+                                          const cpx<T> (&v)[Plan<T, N>::P]) {
+    constexpr int P = Geo<T, N>::P, TPF = Geo<T, N>::TPF;
+    T db[P];
+    if (a.db_mode == DBM_MAG_1E10) bins_to_db<T, P, DBM_MAG_1E10>(v, db);
+    else bins_to_db<T, P, DBM_POWER>(v, db);
+    const size_t row = (size_t)frame * N;
+    const int k0 = (t + N / 2) & (N - 1);
+    if (a.out_kind == OUT_F32_DB) {
+        float* o = reinterpret_cast<float*>(a.out) + row;
+#pragma unroll
+        for (int q = 0; q < P; q++) o[(k0 + TPF * q) & (N - 1)] = (float)db[q];
+    } else if (a.out_kind == OUT_F64_DB) {
+        double* o = reinterpret_cast<double*>(a.out) + row;
+#pragma unroll
+        for (int q = 0; q < P; q++) o[(k0 + TPF * q) & (N - 1)] = (double)db[q];
+    } else {
+        uint32_t* o = reinterpret_cast<uint32_t*>(a.out) + row;
+#pragma unroll
+        for (int q = 0; q < P; q++) o[(k0 + TPF * q) & (N - 1)] = colormap_rgba((float)db[q], a);
+    }
 }
 
 template <typename T, int N, int DK, bool WIN>
@@ -73,22 +197,38 @@ spectrogram_kernel(const SpecArgs a) {
     const int fl = threadIdx.x / TPF;            // frame slot in this CTA
     const int t  = threadIdx.x % TPF;            // thread within the frame
     cpx<T>* sm = reinterpret_cast<cpx<T>*>(smem_raw) + (size_t)fl * G::SM_ELEMS;
-    const cpx<T>* tw = reinterpret_cast<const cpx<T>*>(a.twiddle);
+    const cpx<T>* tw = setup_twiddles<T, N>(a, smem_raw);
 
-    T win[WIN ? P : 1];
-    if constexpr (WIN) {
-        const T* w = reinterpret_cast<const T*>(a.window);
-#pragma unroll
-        for (int q = 0; q < P; q++) win[q] = __ldg(&w[t + TPF * q]);
-    }
+    T win_reg[G::WIN_SMEM ? 1 : P];
+    const T* win = win_reg;
+    if constexpr (WIN) win = setup_window<T, N>(a, smem_raw + G::EXTRA_WIN_OFF, win_reg, t);
 
     const long long n_blocks = (a.n_frames + FPC - 1) / FPC;
+    // bytes of a frame that no earlier frame covers (all of it when hop >= N)
+    const int bps = bytes_per_iq_kind<DK>();
+    const int new_bytes = (int)(a.hop < N ? a.hop : N) * bps;
     for (long long fb = blockIdx.x; fb < n_blocks; fb += gridDim.x) {
         const long long frame = fb * FPC + fl;
         const long long s0 = a.start_sample + frame * a.hop;            // MainController.java:984
+        {   // pull the new samples of this slot's NEXT frame into L2 while the current one is transformed
+            const long long nf = frame + (long long)gridDim.x * FPC;
+            const long long ns_end = a.start_sample + nf * a.hop + N;
+            if (nf < a.n_frames && ns_end <= a.n_samples) {
+                const char* pf = reinterpret_cast<const char*>(a.lp.base) + ns_end * bps - new_bytes;
+                for (int off = t * 128; off < new_bytes; off += TPF * 128)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + off));
+            }
+        }
         const bool in_grid = frame < a.n_frames;
         const bool readable = in_grid && (s0 + N <= a.n_samples);       // :987
         cpx<T> v[P];
+        if constexpr (TPF == 32) {
+            // one frame per warp: validity is warp-uniform, so EOF rows skip the transform
+            if (!readable) {
+                if (in_grid) store_fill<T, N>(a, frame, t);
+                continue;
+            }
+        }
         if (readable) {
             if (a.lp.swap) {
 #pragma unroll
@@ -97,43 +237,16 @@ spectrogram_kernel(const SpecArgs a) {
 #pragma unroll
                 for (int q = 0; q < P; q++) v[q] = Loader<T, DK>::template load<false>(a.lp, s0 + t + TPF * q);
             }
-            if constexpr (WIN) {
-#pragma unroll
-                for (int q = 0; q < P; q++) { v[q].x *= win[q]; v[q].y *= win[q]; }
-            }
         } else {
 #pragma unroll
             for (int q = 0; q < P; q++) v[q] = mk2<T>((T)0, (T)0);
         }
 
-        fft_frame<T, N>(v, t, sm, tw);
+        fft_frame<T, N, WIN>(v, t, sm, tw, win);
 
         if (!in_grid) continue;
-        // out[(k + N/2) % N], SpectralService.java:76-82 ; k = t + TPF*q
-        const size_t row = (size_t)frame * N;
-        const int k0 = (t + N / 2) & (N - 1);
-        if (a.out_kind == OUT_F32_DB) {
-            float* o = reinterpret_cast<float*>(a.out) + row;
-            if (readable) {
-#pragma unroll
-                for (int q = 0; q < P; q++) o[(k0 + TPF * q) & (N - 1)] = (float)to_db(v[q].x, v[q].y, a.db_mode);
-            } else {
-#pragma unroll
-                for (int q = 0; q < P; q++) o[(k0 + TPF * q) & (N - 1)] = (float)a.eof_fill;
-            }
-        } else if (a.out_kind == OUT_F64_DB) {
-            double* o = reinterpret_cast<double*>(a.out) + row;
-#pragma unroll
-            for (int q = 0; q < P; q++)
-                o[(k0 + TPF * q) & (N - 1)] = readable ? (double)to_db(v[q].x, v[q].y, a.db_mode) : a.eof_fill;
-        } else {
-            uint32_t* o = reinterpret_cast<uint32_t*>(a.out) + row;
-#pragma unroll
-            for (int q = 0; q < P; q++) {
-                const float db = readable ? (float)to_db(v[q].x, v[q].y, a.db_mode) : (float)a.eof_fill;
-                o[(k0 + TPF * q) & (N - 1)] = colormap_rgba(db, a);
-            }
-        }
+        if (!readable) { store_fill<T, N>(a, frame, t); continue; }
+        store_row<T, N>(a, frame, t, v);
     }
 }
 
@@ -151,6 +264,7 @@ struct SpecKernelInfo {
     int p;          // points per thread
     int np;         // passes
     int radix[4];
+    int tma;        // 1: TMA-staged variant (needs 16-byte aligned frames)
 };
 
 void register_spec_kernel(const SpecKernelInfo& k);   // engine.cu
@@ -162,8 +276,8 @@ SpecKernelInfo make_spec_info(int prec) {
     SpecKernelInfo k;
     k.fn = (const void*)&spectrogram_kernel<T, N, DK, WIN>;
     k.prec = prec; k.n = N; k.dk = DK; k.win = WIN ? 1 : 0;
-    k.cta = G::CTA; k.fpc = G::FPC; k.minb = G::MINB; k.smem = G::SMEM_BYTES;
-    k.p = G::P; k.np = PL::NP;
+    k.cta = G::CTA; k.fpc = G::FPC; k.minb = G::MINB; k.smem = G::SMEM_BYTES + G::TW_BYTES + (WIN ? G::WIN_BYTES : 0);
+    k.p = G::P; k.np = PL::NP; k.tma = 0;
     for (int i = 0; i < 4; i++) k.radix[i] = PL::radix(i);
     return k;
 }
