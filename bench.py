@@ -152,12 +152,14 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2-samples", type=int, default=LOG2_SAMPLES_PER_GPU)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg")
+    ap.add_argument("--sustained-steps", type=int, default=400,
+                    help="extra back-to-back steps timed as one region to show the power-capped rate (0: skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -268,6 +270,28 @@ def main():
         same = bool(torch.equal(h_out.to(device), d_out))
         e2e["matches_device_path"] = same
 
+    # ---- sustained leg: the same step back to back for ~0.4 s; on a 1 kW part the SM clock drops under
+    # sw_power_cap, so this is the rate a long recording sees (reported beside, not instead of, `value`)
+    sustained = None
+    if args.sustained_steps > 0:
+        s2 = ClockSampler(local_rank)
+        s2.start()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.sustained_steps):
+            step()
+        e1.record()
+        barrier()
+        s2.stop_flag = True
+        s2.join()
+        ts = torch.tensor([e0.elapsed_time(e1) / args.sustained_steps], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        sustained = {"steps": args.sustained_steps, "ms_per_step": round(ts.item(), 4),
+                     "value": round(tot.item() / (ts.item() * 1e-3) / 1e6, 3), "unit": UNIT,
+                     "roofline_frac": round(alg_bytes / (ts.item() * 1e-3) / 1e9 / peak, 4), "clocks": s2.summary()}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         v1, _, dt1 = cpu_port_throughput(1 << 21, nthreads=1)
@@ -296,6 +320,8 @@ def main():
         }
         if e2e:
             line["e2e"] = e2e
+        if sustained:
+            line["sustained"] = sustained
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))

@@ -205,6 +205,7 @@ welch_accum_kernel(const WelchArgs a) {
         __syncthreads();
         tw = tsm;
     }
+    const TwSeed<float> seed = load_tw_seed<float, N>(reinterpret_cast<const float2*>(a.twiddle), t);
     const WelchSig sg = a.sigs[blockIdx.y];
     float acc[P];
 #pragma unroll
@@ -227,7 +228,7 @@ welch_accum_kernel(const WelchArgs a) {
 #pragma unroll
             for (int q = 0; q < P; q++) v[q] = make_float2(0.f, 0.f);
         }
-        fft_frame<float, N, false>(v, t, sm, tw, nullptr);
+        fft_frame<float, N, false>(v, t, sm, tw, nullptr, seed);
         if (valid) {
 #pragma unroll
             for (int q = 0; q < P; q++) acc[q] += __fmaf_rn(v[q].x, v[q].x, v[q].y * v[q].y);

@@ -205,9 +205,8 @@ int Engine::launch_spectrogram(const void* d_iq, uint64_t n_samples, const sa_sp
     // TMA-staged variant (needs every frame start 16-byte aligned), else the LDG kernel
     const uint64_t iq_b = (uint64_t)sa_bytes_per_iq(p.dtype);
     const bool aligned = ((uintptr_t)d_iq % 16 == 0) && ((p.start_sample * iq_b) % 16 == 0) && ((p.hop * iq_b) % 16 == 0);
-    // (opt-in: measured 2 % slower than the LDG + L2-prefetch kernel on B200, see DESIGN.md ablations)
-    static const bool use_tma = getenv("SA_USE_TMA") != nullptr;
-    const SpecKernelInfo* k = (aligned && use_tma) ? find_spec_kernel(prec, (int)p.nfft, dk, win, 1) : nullptr;
+    static const bool no_tma = getenv("SA_NO_TMA") != nullptr;      // A/B switch for the ablation in DESIGN.md
+    const SpecKernelInfo* k = (aligned && !no_tma) ? find_spec_kernel(prec, (int)p.nfft, dk, win, 1) : nullptr;
     if (!k) k = find_spec_kernel(prec, (int)p.nfft, dk, win, 0);
     if (!k) return set_error(SA_ERR_UNSUPPORTED, "no kernel for nfft %u precision %s dtype %d", p.nfft,
                              prec == SA_PREC_F64 ? "f64" : "f32", p.dtype);

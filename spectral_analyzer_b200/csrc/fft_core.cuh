@@ -33,6 +33,9 @@
 #ifndef SA_TW_SMEM_MAX_TPF
 #define SA_TW_SMEM_MAX_TPF 32
 #endif
+#ifndef SA_TW_RECURRENCE
+#define SA_TW_RECURRENCE 1
+#endif
 
 namespace sa {
 
@@ -171,7 +174,12 @@ __device__ __forceinline__ void dit_tail(cpx<T> (&a)[R]) {
 //   MUL_NONE  plain
 //   MUL_REAL  x[m] *= window; wr[2m], wr[2m+1] hold the factors of elements m and m + R/2 (pass 0)
 //   MUL_CPX   x[m] *= tw[m]  (m >= 1; tw[0] == 1)    (Stockham twiddle, later passes)
-enum { MUL_NONE = 0, MUL_REAL = 1, MUL_CPX = 2 };
+//   MUL_REC   like MUL_CPX, but tw[m] = om^m generated in registers: the pair (om^m, om^(m+R/2)) advances
+//             by one packed complex multiply per butterfly (plans whose pass-1 twiddle is lane * m)
+enum { MUL_NONE = 0, MUL_REAL = 1, MUL_CPX = 2, MUL_REC = 3 };
+
+// per-lane seeds of the twiddle recurrence: om = W_N^t, oh = om^(R/2)
+template <typename T> struct TwSeed { cpx<T> om, oh; };
 
 template <typename T> struct TwPair { cpx<T> lo, hi; };     // twiddles of elements m and m + R/2
 // TW_SMEM: the table was copied to shared memory (plain loads); otherwise read-only global loads
@@ -194,9 +202,12 @@ template <bool TW_SMEM> __device__ __forceinline__ TwPair<double> ldg_tw(const T
 //   cpx   : t = ta a ; o0 = t + tb b ; o1 = 2t - o0   10 FMA-class ops instead of 12
 template <typename T, int R, int STR, int OFF, int P, int MUL, bool TW_SMEM>
 __device__ __forceinline__ void radix_fft(cpx<T> (&v)[P], const T* __restrict__ wr,
-                                          const TwPair<T>* __restrict__ tw, const int tw_stride) {
+                                          const TwPair<T>* __restrict__ tw, const int tw_stride,
+                                          const TwSeed<T>& seed) {
     static_assert(R == 2 || R == 4 || R == 8 || R == 16 || R == 32, "radix");
     cpx<T> a[R];
+    pk2 rec_re = 0, rec_im = 0;                 // (om^m, om^(m+R/2)) as packed re / im (MUL_REC)
+    if constexpr (MUL == MUL_REC) { rec_re = pack2(1.0f, (float)seed.oh.x); rec_im = pack2(0.0f, (float)seed.oh.y); }
 #pragma unroll
     for (int m = 0; m < R / 2; m++) {
         const cpx<T> x = v[OFF + STR * m], y = v[OFF + STR * (m + R / 2)];
@@ -208,8 +219,21 @@ __device__ __forceinline__ void radix_fft(cpx<T> (&v)[P], const T* __restrict__ 
             const T tx = wa * x.x, ty = wa * x.y;
             o0 = mk2<T>(fma_t(wb, y.x, tx), fma_t(wb, y.y, ty));
             o1 = mk2<T>(fma_t(-wb, y.x, tx), fma_t(-wb, y.y, ty));
-        } else if constexpr (MUL == MUL_CPX) {
-            const TwPair<T> w = ldg_tw<TW_SMEM>(tw + (size_t)m * tw_stride);
+        } else if constexpr (MUL == MUL_CPX || MUL == MUL_REC) {
+            TwPair<T> w;
+            if constexpr (MUL == MUL_REC) {
+                float lr, hr, li, hi;
+                unpack2(rec_re, lr, hr); unpack2(rec_im, li, hi);
+                w.lo = mk2<T>((T)lr, (T)li); w.hi = mk2<T>((T)hr, (T)hi);
+                if (m + 1 < R / 2) {            // advance both lanes: w <- w * om
+                    const pk2 orr = bcast2((float)seed.om.x), oii = bcast2((float)seed.om.y);
+                    const pk2 nre = fma2(neg2(oii), rec_im, mul2(orr, rec_re));
+                    rec_im = fma2(oii, rec_re, mul2(orr, rec_im));
+                    rec_re = nre;
+                }
+            } else {
+                w = ldg_tw<TW_SMEM>(tw + (size_t)m * tw_stride);
+            }
             cpx<T> t = x;
             if (m != 0) t = mk2<T>(fma_t(-w.lo.y, x.y, w.lo.x * x.x), fma_t(w.lo.y, x.x, w.lo.x * x.y));
             o0 = mk2<T>(fma_t(-w.hi.y, y.y, fma_t(w.hi.x, y.x, t.x)), fma_t(w.hi.y, y.x, fma_t(w.hi.x, y.y, t.y)));
@@ -229,10 +253,11 @@ __device__ __forceinline__ void radix_fft(cpx<T> (&v)[P], const T* __restrict__ 
 template <typename T, int R, int S, int P, int MUL, bool TW_SMEM, int I>
 struct RadixAll {
     static __device__ __forceinline__ void run(cpx<T> (&v)[P], const T* __restrict__ wr,
-                                               const TwPair<T>* __restrict__ tw, const int tpf) {
+                                               const TwPair<T>* __restrict__ tw, const int tpf,
+                                               const TwSeed<T>& seed) {
         // twiddle pairs of sub-butterfly I sit at tw[(I*(R/2) + m) * tpf]
-        radix_fft<T, R, S, I, P, MUL, TW_SMEM>(v, wr, tw + (size_t)I * (R / 2) * tpf, tpf);
-        if constexpr (I + 1 < S) RadixAll<T, R, S, P, MUL, TW_SMEM, I + 1>::run(v, wr, tw, tpf);
+        radix_fft<T, R, S, I, P, MUL, TW_SMEM>(v, wr, tw + (size_t)I * (R / 2) * tpf, tpf, seed);
+        if constexpr (I + 1 < S) RadixAll<T, R, S, P, MUL, TW_SMEM, I + 1>::run(v, wr, tw, tpf, seed);
     }
 };
 
@@ -281,6 +306,9 @@ template <typename T, int N> struct Geo {
     static constexpr int PADW = sizeof(T) == 4 ? 2 : 1;      // pad elements per R0 (keeps 16-byte alignment)
     static constexpr int SM_ELEMS = N + (N / R0) * PADW;     // padded elements per frame
     static constexpr size_t SMEM_BYTES = (size_t)FPC * SM_ELEMS * sizeof(cpx<T>);
+    // two-pass plans with one butterfly per thread in pass 1 (twiddle = lane * m) can generate the
+    // twiddles by a register recurrence instead of loading them
+    static constexpr bool TW_REC = SA_TW_RECURRENCE && sizeof(T) == 4 && PL::NP == 2 && PL::radix(1) == P;
     // one-warp-per-frame plans keep the Stockham twiddle table in shared memory as well
     static constexpr bool TW_SMEM = TPF <= SA_TW_SMEM_MAX_TPF;
     static constexpr size_t TW_BYTES = TW_SMEM ? (size_t)(PL::NP - 1) * N * sizeof(cpx<T>) : 0;
@@ -299,17 +327,19 @@ template <int TPF> __device__ __forceinline__ void frame_sync() {
 
 // One pass: S radix-R butterflies (window or Stockham twiddle fused into their first stage) and,
 // unless it is the last pass, the exchange through shared memory.
-template <typename T, int N, int PASS, bool WIN>
+template <typename T, int N, int PASS, bool WIN, bool REC>
 __device__ __forceinline__ void fft_pass(cpx<T> (&v)[Plan<T, N>::P], const int t, cpx<T>* __restrict__ sm,
-                                         const cpx<T>* __restrict__ tw, const T* __restrict__ win) {
+                                         const cpx<T>* __restrict__ tw, const T* __restrict__ win,
+                                         const TwSeed<T>& seed) {
     using G = Geo<T, N>;
     using PL = Plan<T, N>;
     constexpr int P = G::P, TPF = G::TPF, R = PL::radix(PASS), S = P / R, NS = G::ns(PASS);
     if constexpr (PASS == 0) {
-        RadixAll<T, R, S, P, WIN ? MUL_REAL : MUL_NONE, false, 0>::run(v, win, nullptr, TPF);
+        RadixAll<T, R, S, P, WIN ? MUL_REAL : MUL_NONE, false, 0>::run(v, win, nullptr, TPF, seed);
     } else {
         const TwPair<T>* twp = reinterpret_cast<const TwPair<T>*>(tw) + (size_t)(PASS - 1) * (N / 2) + t;
-        RadixAll<T, R, S, P, MUL_CPX, G::TW_SMEM, 0>::run(v, nullptr, twp, TPF);
+        if constexpr (REC && G::TW_REC) RadixAll<T, R, S, P, MUL_REC, false, 0>::run(v, nullptr, nullptr, TPF, seed);
+        else RadixAll<T, R, S, P, MUL_CPX, G::TW_SMEM, 0>::run(v, nullptr, twp, TPF, seed);
     }
     if constexpr (PASS + 1 < PL::NP) {
         frame_sync<TPF>();   // every reader of the previous exchange (or previous frame) is done
@@ -334,16 +364,32 @@ __device__ __forceinline__ void fft_pass(cpx<T> (&v)[Plan<T, N>::P], const int t
     }
 }
 
+// Seeds of the twiddle recurrence (kernels instantiated with REC), read once per thread from the pair table: pair (m'=1).lo = W_N^t,
+// pair (m'=0).hi = W_N^(t*P/2).
+template <typename T, int N>
+__device__ __forceinline__ TwSeed<T> load_tw_seed(const cpx<T>* __restrict__ tw, const int t) {
+    using G = Geo<T, N>;
+    TwSeed<T> s;
+    s.om = mk2<T>((T)1, (T)0); s.oh = s.om;
+    if constexpr (G::TW_REC) {
+        const TwPair<T>* p = reinterpret_cast<const TwPair<T>*>(tw);
+        s.om = ldg_tw<false>(p + 1 * G::TPF + t).lo;
+        s.oh = ldg_tw<false>(p + 0 * G::TPF + t).hi;
+    }
+    return s;
+}
+
 // Full transform of the registers of one frame; win (T[P], thread-private) multiplies the inputs
 // when WIN is set.
-template <typename T, int N, bool WIN>
+template <typename T, int N, bool WIN, bool REC = false>
 __device__ __forceinline__ void fft_frame(cpx<T> (&v)[Plan<T, N>::P], const int t, cpx<T>* __restrict__ sm,
-                                          const cpx<T>* __restrict__ tw, const T* __restrict__ win) {
+                                          const cpx<T>* __restrict__ tw, const T* __restrict__ win,
+                                          const TwSeed<T>& seed) {
     using PL = Plan<T, N>;
-    fft_pass<T, N, 0, WIN>(v, t, sm, tw, win);
-    if constexpr (PL::NP > 1) fft_pass<T, N, 1, WIN>(v, t, sm, tw, win);
-    if constexpr (PL::NP > 2) fft_pass<T, N, 2, WIN>(v, t, sm, tw, win);
-    if constexpr (PL::NP > 3) fft_pass<T, N, 3, WIN>(v, t, sm, tw, win);
+    fft_pass<T, N, 0, WIN, REC>(v, t, sm, tw, win, seed);
+    if constexpr (PL::NP > 1) fft_pass<T, N, 1, WIN, REC>(v, t, sm, tw, win, seed);
+    if constexpr (PL::NP > 2) fft_pass<T, N, 2, WIN, REC>(v, t, sm, tw, win, seed);
+    if constexpr (PL::NP > 3) fft_pass<T, N, 3, WIN, REC>(v, t, sm, tw, win, seed);
 }
 
 }  // namespace sa

@@ -198,6 +198,7 @@ spectrogram_kernel(const SpecArgs a) {
     const int t  = threadIdx.x % TPF;            // thread within the frame
     cpx<T>* sm = reinterpret_cast<cpx<T>*>(smem_raw) + (size_t)fl * G::SM_ELEMS;
     const cpx<T>* tw = setup_twiddles<T, N>(a, smem_raw);
+    const TwSeed<T> seed = load_tw_seed<T, N>(reinterpret_cast<const cpx<T>*>(a.twiddle), t);
 
     T win_reg[G::WIN_SMEM ? 1 : P];
     const T* win = win_reg;
@@ -242,7 +243,7 @@ spectrogram_kernel(const SpecArgs a) {
             for (int q = 0; q < P; q++) v[q] = mk2<T>((T)0, (T)0);
         }
 
-        fft_frame<T, N, WIN>(v, t, sm, tw, win);
+        fft_frame<T, N, WIN>(v, t, sm, tw, win, seed);
 
         if (!in_grid) continue;
         if (!readable) { store_fill<T, N>(a, frame, t); continue; }

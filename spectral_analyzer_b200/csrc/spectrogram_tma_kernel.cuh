@@ -52,15 +52,17 @@ spectrogram_tma_kernel(const SpecArgs a) {
     const int fl = threadIdx.x / TPF, t = threadIdx.x % TPF;
     cpx<T>* sm = reinterpret_cast<cpx<T>*>(smem_raw) + (size_t)fl * G::SM_ELEMS;
     const raw_t* raw = reinterpret_cast<const raw_t*>(sm);
-    const cpx<T>* tw = setup_twiddles<T, N>(a, smem_raw);
+    static_assert(G::TW_REC, "the TMA-staged kernel generates its pass-1 twiddles by recurrence");
+    const cpx<T>* tw = reinterpret_cast<const cpx<T>*>(a.twiddle);
+    const TwSeed<T> seed = load_tw_seed<T, N>(reinterpret_cast<const cpx<T>*>(a.twiddle), t);
     // one mbarrier per warp, after the exchange buffers, the twiddles and the window rows
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + G::EXTRA_WIN_OFF + (WIN ? G::WIN_BYTES : 0));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + G::SMEM_BYTES + (WIN ? G::WIN_BYTES : 0));
     const uint32_t bar = smem_u32(&bars[fl]);
     const uint32_t dst = smem_u32(sm);
 
     T win_reg[G::WIN_SMEM ? 1 : P];
     const T* win = win_reg;
-    if constexpr (WIN) win = setup_window<T, N>(a, smem_raw + G::EXTRA_WIN_OFF, win_reg, t);
+    if constexpr (WIN) win = setup_window<T, N>(a, smem_raw + G::SMEM_BYTES, win_reg, t);
 
     if (t == 0) mbar_init(bar, 1);
     __syncwarp();
@@ -101,13 +103,13 @@ spectrogram_tma_kernel(const SpecArgs a) {
             for (int q = 0; q < P; q++) v[q] = LD::template decode<false>(a.lp, raw[t + TPF * q]);
         }
         // pass 0 ends with: sync, exchange write (overwrites the raw frame), sync, exchange read
-        fft_pass<T, N, 0, WIN>(v, t, sm, tw, win);
+        fft_pass<T, N, 0, WIN, true>(v, t, sm, tw, win, seed);
         __syncwarp();                                 // every lane has read its exchange values back
         if (next_readable && t == 0) {
             fence_proxy_async();                      // generic-proxy accesses ordered before the async write
             issue(next);
         }
-        fft_pass<T, N, 1, WIN>(v, t, sm, tw, win);
+        fft_pass<T, N, 1, WIN, true>(v, t, sm, tw, win, seed);
         store_row<T, N>(a, frame, t, v);
     }
 }
@@ -116,7 +118,7 @@ template <typename T, int N, int DK, bool WIN>
 SpecKernelInfo make_spec_tma_info(int prec) {
     SpecKernelInfo k = make_spec_info<T, N, DK, WIN>(prec);
     k.fn = (const void*)&spectrogram_tma_kernel<T, N, DK, WIN>;
-    k.smem += Geo<T, N>::FPC * sizeof(uint64_t);
+    k.smem = Geo<T, N>::SMEM_BYTES + (WIN ? Geo<T, N>::WIN_BYTES : 0) + Geo<T, N>::FPC * sizeof(uint64_t);
     k.tma = 1;
     return k;
 }

@@ -159,3 +159,30 @@ def test_linearity_and_time_shift_properties(engine):
     p = (10 ** (a[:8].astype(np.float64) / 10)).sum(axis=1)
     e = (np.abs(x[:8 * nfft].astype(np.complex64)) ** 2).reshape(8, nfft).sum(axis=1) * nfft
     assert np.abs(p / e - 1).max() < 1e-4
+
+
+def test_both_1024_kernels_against_oracle(engine):
+    """The 1024-point FP32 plan has two kernels: TMA-staged frames (16-byte aligned frame starts) and
+    the LDG kernel (any alignment, or SA_NO_TMA=1).  Both are checked against the oracle; the LDG
+    kernel on aligned input runs in a subprocess because the switch is read once per process."""
+    import subprocess
+    import sys
+    raw = synth.recording(1024 * 40, "cf32_le", seed=31)
+    ref = co.spectrogram(raw, "cf32_le", 0, 1024, 512, "hann", 70)
+    got = engine.spectrogram(raw, "cf32_le", 1024, 70, hop=512, window="hann")          # TMA kernel
+    check_db_parity(got, ref)
+    ref_odd = co.spectrogram(raw, "cf32_le", 3, 1024, 512, "hann", 70)
+    got_odd = engine.spectrogram(raw, "cf32_le", 1024, 70, hop=512, window="hann", start_sample=3)   # LDG kernel
+    check_db_parity(got_odd, ref_odd)
+    code = ("import numpy as np, sys; sys.path.insert(0, %r); import spectral_analyzer_b200 as sa;"
+            "from spectral_analyzer_b200 import synth; e = sa.Engine(0);"
+            "raw = synth.recording(1024 * 40, 'cf32_le', seed=31);"
+            "np.save(sys.argv[1], e.spectrogram(raw, 'cf32_le', 1024, 70, hop=512, window='hann'))"
+            % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    out = os.path.join(os.environ.get("TMPDIR", "/tmp"), "sa_no_tma.npy")
+    env = dict(os.environ, SA_NO_TMA="1")
+    subprocess.run([sys.executable, "-c", code, out], check=True, env=env)
+    got_ldg = np.load(out)
+    check_db_parity(got_ldg, ref)
+    strong = ref > ref.max(axis=1, keepdims=True) - 40
+    assert np.abs(got_ldg - got)[strong].max() < 1e-4   # two twiddle sources, same answer to FP32 rounding
