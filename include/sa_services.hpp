@@ -1,0 +1,115 @@
+// sa_services.hpp -- C++ host-side mirror of the reference's DSP service interface on top of the C-ABI
+// (include/sa_engine.h).  Header-only.  The reference is compiled JVM code; its toolchain is absent from
+// the build image, so this is the compiled-language host layer: same class and method names, argument
+// meaning and error behaviour as the Java services it stands in for
+//   SpectralService.computeMagnitudes                 S/services/SpectralService.java:33
+//   ExtractDownConvertService.extractAndDownConvert   S/services/ExtractDownConvertService.java:34,54
+//   PowerSpectralDensity.calculatePsdWelch [JDSP]     S/controllers/AnalysisDialogController.java:308-312
+// (S/ = src/main/java/net/kcundercover/spectral_analyzer/).  Java exceptions map to C++ ones:
+//   MathIllegalArgumentException -> std::invalid_argument, IndexOutOfBoundsException -> std::out_of_range.
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "sa_engine.h"
+
+namespace spectral_analyzer {
+
+// The MappedByteBuffer of S/sigmf/SigMfHelper.java:78-84: a read-only view of the .sigmf-data bytes,
+// position 0 already past core:header_bytes.
+struct MappedByteBuffer {
+    const void* data = nullptr;
+    uint64_t capacity = 0;
+};
+
+inline void sa_check(int32_t rc) {
+    if (rc == SA_OK) return;
+    const std::string msg = sa_last_error();
+    if (rc == SA_ERR_INVALID_ARG) throw std::invalid_argument(msg);
+    if (rc == SA_ERR_OUT_OF_RANGE) throw std::out_of_range(msg);
+    throw std::runtime_error("sa_engine error " + std::to_string(rc) + ": " + msg);
+}
+
+class Engine {
+public:
+    explicit Engine(int device = 0) { sa_check(sa_engine_create(device, &h_)); }
+    ~Engine() { sa_engine_destroy(h_); }
+    Engine(const Engine&) = delete;
+    Engine& operator=(const Engine&) = delete;
+    sa_engine* handle() const { return h_; }
+    void registerHost(const MappedByteBuffer& b) { sa_check(sa_register_host(h_, b.data, b.capacity, 1)); }
+    void unregisterHost(const MappedByteBuffer& b) { sa_check(sa_unregister_host(h_, b.data)); }
+private:
+    sa_engine* h_ = nullptr;
+};
+
+struct Datatype {
+    int32_t dtype = 0, big_endian = 0;
+    explicit Datatype(const std::string& sigmf) { sa_check(sa_parse_datatype(sigmf.c_str(), &dtype, &big_endian)); }
+};
+
+class SpectralService {
+public:
+    explicit SpectralService(Engine& e) : e_(e) {}
+    // double[] computeMagnitudes(MappedByteBuffer buffer, int startByte, int nfft, String datatype)
+    std::vector<double> computeMagnitudes(const MappedByteBuffer& buffer, int startByte, int nfft,
+                                          const std::string& datatype) const {
+        const Datatype dt(datatype);
+        std::vector<double> out((size_t)nfft);
+        sa_check(sa_compute_magnitudes(e_.handle(), buffer.data, buffer.capacity, (uint64_t)startByte, (uint32_t)nfft,
+                                       dt.dtype, dt.big_endian, out.data()));
+        return out;
+    }
+    // The frame loop of MainController.updateDisplay (:980-999) as one call: waterfall[canvasW][fftSize].
+    std::vector<double> computeWaterfall(const MappedByteBuffer& buffer, int64_t currentSampleOffset, int canvasW,
+                                         int fftSize, const std::string& datatype) const {
+        const Datatype dt(datatype);
+        sa_spectrogram_params p;
+        sa_spectrogram_params_init(&p);
+        p.dtype = dt.dtype; p.big_endian = dt.big_endian; p.nfft = (uint32_t)fftSize; p.hop = (uint64_t)fftSize;
+        p.start_sample = (uint64_t)currentSampleOffset; p.n_frames = (uint64_t)canvasW; p.out_kind = SA_OUT_F64_DB;
+        std::vector<double> out((size_t)canvasW * fftSize);
+        sa_check(sa_spectrogram(e_.handle(), buffer.data, buffer.capacity, &p, out.data(), out.size() * sizeof(double)));
+        return out;
+    }
+private:
+    Engine& e_;
+};
+
+class ExtractDownConvertService {
+public:
+    explicit ExtractDownConvertService(Engine& e) : e_(e) {}
+    // double[2][M] extractAndDownConvert(buffer, long startSample, int count, String datatype,
+    //                                    double freqOff, int down, boolean fast = false)
+    std::vector<std::vector<double>> extractAndDownConvert(const MappedByteBuffer& buffer, int64_t startSample, int count,
+                                                           const std::string& datatype, double freqOff, int down,
+                                                           bool fast = false) const {
+        const Datatype dt(datatype);
+        if (down < 1) throw std::invalid_argument("down < 1");
+        const size_t m = (size_t)count / (size_t)down;
+        std::vector<std::vector<double>> out(2, std::vector<double>(m ? m : 1));
+        uint64_t n = 0;
+        sa_check(sa_downconvert(e_.handle(), buffer.data, buffer.capacity, dt.dtype, dt.big_endian, (uint64_t)startSample,
+                                (uint64_t)count, freqOff, down, fast ? 1 : 0, out[0].data(), out[1].data(), &n));
+        out[0].resize(n); out[1].resize(n);
+        return out;
+    }
+private:
+    Engine& e_;
+};
+
+struct PowerSpectralDensity {
+    // double[2][K] calculatePsdWelch(double[][] data, double fs, int nfft): row 0 = frequency axis centred on 0,
+    // row 1 = level in dB/Hz
+    static std::vector<std::vector<double>> calculatePsdWelch(Engine& e, const std::vector<std::vector<double>>& data,
+                                                              double fs, int nfft) {
+        std::vector<std::vector<double>> out(2, std::vector<double>((size_t)nfft));
+        sa_check(sa_psd_welch(e.handle(), data[0].data(), data[1].data(), data[0].size(), fs, (uint32_t)nfft, 0,
+                              SA_WIN_HANN, out[0].data(), out[1].data()));
+        return out;
+    }
+};
+
+}  // namespace spectral_analyzer

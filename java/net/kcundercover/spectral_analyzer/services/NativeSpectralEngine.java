@@ -1,0 +1,169 @@
+package net.kcundercover.spectral_analyzer.services;
+
+import java.lang.foreign.Arena;
+import java.lang.foreign.FunctionDescriptor;
+import java.lang.foreign.Linker;
+import java.lang.foreign.MemoryLayout;
+import java.lang.foreign.MemorySegment;
+import java.lang.foreign.StructLayout;
+import java.lang.foreign.SymbolLookup;
+import java.lang.foreign.ValueLayout;
+import java.lang.invoke.MethodHandle;
+import java.nio.MappedByteBuffer;
+
+import static java.lang.foreign.ValueLayout.ADDRESS;
+import static java.lang.foreign.ValueLayout.JAVA_DOUBLE;
+import static java.lang.foreign.ValueLayout.JAVA_INT;
+import static java.lang.foreign.ValueLayout.JAVA_LONG;
+
+/**
+ * Panama (java.lang.foreign) binding of libsa_engine.so -- the reference-side stub a maintainer adds.
+ *
+ * NOT compiled in this repository (no JVM in the build image; Java 21 needs --enable-preview for
+ * java.lang.foreign, final in 22).  It binds exactly the symbols declared in include/sa_engine.h and
+ * is mirrored 1:1 by spectral_analyzer_b200/_capi.py, which IS exercised by the tests.
+ *
+ * No JNI glue and no CPU fallback: if the library or a B200 is missing, construction throws.
+ */
+public final class NativeSpectralEngine implements AutoCloseable {
+    private static final Linker LINKER = Linker.nativeLinker();
+    private static final SymbolLookup LIB = SymbolLookup.libraryLookup(
+            System.getProperty("sa.engine.lib", "libsa_engine.so"), Arena.global());
+
+    private static MethodHandle fn(String name, FunctionDescriptor fd) {
+        return LINKER.downcallHandle(LIB.find(name).orElseThrow(() -> new UnsatisfiedLinkError(name)), fd);
+    }
+
+    // int32 sa_engine_create(int32 device, sa_engine** out)
+    private static final MethodHandle CREATE = fn("sa_engine_create", FunctionDescriptor.of(JAVA_INT, JAVA_INT, ADDRESS));
+    private static final MethodHandle DESTROY = fn("sa_engine_destroy", FunctionDescriptor.ofVoid(ADDRESS));
+    private static final MethodHandle LAST_ERROR = fn("sa_last_error", FunctionDescriptor.of(ADDRESS));
+    private static final MethodHandle PARSE_DT = fn("sa_parse_datatype", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
+    private static final MethodHandle REGISTER = fn("sa_register_host", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, JAVA_INT));
+    private static final MethodHandle UNREGISTER = fn("sa_unregister_host", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    private static final MethodHandle PARAMS_INIT = fn("sa_spectrogram_params_init", FunctionDescriptor.ofVoid(ADDRESS));
+    // int32 sa_spectrogram(engine, iq, iq_bytes, params, out, out_bytes)
+    private static final MethodHandle SPECTROGRAM = fn("sa_spectrogram",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS, ADDRESS, JAVA_LONG));
+    // int32 sa_compute_magnitudes(engine, buffer, capacity, start_byte, nfft, dtype, big_endian, out)
+    private static final MethodHandle MAGNITUDES = fn("sa_compute_magnitudes",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG, JAVA_INT, JAVA_INT, JAVA_INT, ADDRESS));
+    // int32 sa_downconvert(engine, iq, iq_bytes, dtype, be, start, count, freq_off, down, fast, re, im, out_len)
+    private static final MethodHandle DOWNCONVERT = fn("sa_downconvert",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, JAVA_INT, JAVA_INT, JAVA_LONG, JAVA_LONG,
+                    JAVA_DOUBLE, JAVA_INT, JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
+    // int32 sa_psd_welch(engine, re, im, n, fs, nfft, hop, window, out_freq, out_db)
+    private static final MethodHandle PSD_WELCH = fn("sa_psd_welch",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, JAVA_DOUBLE, JAVA_INT, JAVA_LONG,
+                    JAVA_INT, ADDRESS, ADDRESS));
+
+    /** struct sa_spectrogram_params (include/sa_engine.h), natural alignment, 96 bytes. */
+    static final StructLayout PARAMS = MemoryLayout.structLayout(
+            JAVA_INT.withName("struct_size"), JAVA_INT.withName("dtype"), JAVA_INT.withName("big_endian"),
+            JAVA_INT.withName("window"), JAVA_INT.withName("nfft"), JAVA_INT.withName("db_mode"),
+            JAVA_INT.withName("out_kind"), JAVA_INT.withName("precision"), JAVA_LONG.withName("start_sample"),
+            JAVA_LONG.withName("hop"), JAVA_LONG.withName("n_frames"), JAVA_DOUBLE.withName("eof_fill_db"),
+            JAVA_INT.withName("colormap"), JAVA_INT.withName("reserved0"), JAVA_DOUBLE.withName("sample_rate"),
+            JAVA_DOUBLE.withName("min_db"), JAVA_DOUBLE.withName("max_db"));
+
+    private final MemorySegment engine;
+
+    public NativeSpectralEngine(int device) {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment out = a.allocate(ADDRESS);
+            check((int) CREATE.invoke(device, out));
+            engine = out.get(ADDRESS, 0);
+        } catch (RuntimeException e) {
+            throw e;
+        } catch (Throwable t) {
+            throw new IllegalStateException(t);
+        }
+    }
+
+    private static void check(int rc) throws Throwable {
+        if (rc == 0) return;
+        String msg = ((MemorySegment) LAST_ERROR.invoke()).reinterpret(512).getString(0);
+        switch (rc) {
+            case 1: throw new IllegalArgumentException(msg);          // MathIllegalArgumentException analogue
+            case 3: throw new IndexOutOfBoundsException(msg);         // absolute get past the buffer limit
+            default: throw new IllegalStateException("sa_engine " + rc + ": " + msg);
+        }
+    }
+
+    /** Page-locks the mapped .sigmf-data file once after SigMfHelper.load (SigMfHelper.java:78-84). */
+    public void register(MappedByteBuffer buffer) throws Throwable {
+        MemorySegment seg = MemorySegment.ofBuffer(buffer);
+        check((int) REGISTER.invoke(engine, seg, seg.byteSize(), 1));
+    }
+
+    /** Drop-in body of SpectralService.computeMagnitudes (SpectralService.java:33-85). */
+    public double[] computeMagnitudes(MappedByteBuffer buffer, int startByte, int nfft, String datatype) throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            int[] dt = parse(a, datatype);
+            MemorySegment out = a.allocate(JAVA_DOUBLE, nfft);
+            MemorySegment seg = MemorySegment.ofBuffer(buffer);
+            check((int) MAGNITUDES.invoke(engine, seg, seg.byteSize(), (long) startByte, nfft, dt[0], dt[1], out));
+            return out.toArray(JAVA_DOUBLE);
+        }
+    }
+
+    /** Replaces the whole `for t` loop of MainController.updateDisplay (MainController.java:980-999). */
+    public double[][] computeWaterfall(MappedByteBuffer buffer, long currentSampleOffset, int canvasW, int fftSize,
+                                       String datatype) throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            int[] dt = parse(a, datatype);
+            MemorySegment p = a.allocate(PARAMS);
+            PARAMS_INIT.invoke(p);
+            p.set(JAVA_INT, PARAMS.byteOffset(MemoryLayout.PathElement.groupElement("dtype")), dt[0]);
+            p.set(JAVA_INT, PARAMS.byteOffset(MemoryLayout.PathElement.groupElement("big_endian")), dt[1]);
+            p.set(JAVA_INT, PARAMS.byteOffset(MemoryLayout.PathElement.groupElement("nfft")), fftSize);
+            p.set(JAVA_INT, PARAMS.byteOffset(MemoryLayout.PathElement.groupElement("out_kind")), 1 /* SA_OUT_F64_DB */);
+            p.set(JAVA_LONG, PARAMS.byteOffset(MemoryLayout.PathElement.groupElement("start_sample")), currentSampleOffset);
+            p.set(JAVA_LONG, PARAMS.byteOffset(MemoryLayout.PathElement.groupElement("hop")), (long) fftSize);
+            p.set(JAVA_LONG, PARAMS.byteOffset(MemoryLayout.PathElement.groupElement("n_frames")), (long) canvasW);
+            MemorySegment out = a.allocate(JAVA_DOUBLE, (long) canvasW * fftSize);
+            MemorySegment seg = MemorySegment.ofBuffer(buffer);
+            check((int) SPECTROGRAM.invoke(engine, seg, seg.byteSize(), p, out, out.byteSize()));
+            double[][] waterfall = new double[canvasW][];
+            for (int t = 0; t < canvasW; t++)
+                waterfall[t] = out.asSlice((long) t * fftSize * 8, (long) fftSize * 8).toArray(JAVA_DOUBLE);
+            return waterfall;
+        }
+    }
+
+    /** Drop-in body of ExtractDownConvertService.extractAndDownConvert (ExtractDownConvertService.java:54-117). */
+    public double[][] extractAndDownConvert(MappedByteBuffer buffer, long startSample, int count, String datatype,
+                                            double freqOff, int down, boolean fast) throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            int[] dt = parse(a, datatype);
+            long m = count / down;
+            MemorySegment re = a.allocate(JAVA_DOUBLE, Math.max(m, 1)), im = a.allocate(JAVA_DOUBLE, Math.max(m, 1));
+            MemorySegment len = a.allocate(JAVA_LONG);
+            MemorySegment seg = MemorySegment.ofBuffer(buffer);
+            check((int) DOWNCONVERT.invoke(engine, seg, seg.byteSize(), dt[0], dt[1], startSample, (long) count, freqOff,
+                    down, fast ? 1 : 0, re, im, len));
+            int n = (int) len.get(JAVA_LONG, 0);
+            return new double[][] { re.asSlice(0, 8L * n).toArray(JAVA_DOUBLE), im.asSlice(0, 8L * n).toArray(JAVA_DOUBLE) };
+        }
+    }
+
+    /** Replaces PowerSpectralDensity.calculatePsdWelch at AnalysisDialogController.java:308-312. */
+    public double[][] calculatePsdWelch(double[][] data, double fs, int nfft) throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment re = a.allocateFrom(JAVA_DOUBLE, data[0]), im = a.allocateFrom(JAVA_DOUBLE, data[1]);
+            MemorySegment f = a.allocate(JAVA_DOUBLE, nfft), db = a.allocate(JAVA_DOUBLE, nfft);
+            check((int) PSD_WELCH.invoke(engine, re, im, (long) data[0].length, fs, nfft, 0L, 1 /* SA_WIN_HANN */, f, db));
+            return new double[][] { f.toArray(JAVA_DOUBLE), db.toArray(JAVA_DOUBLE) };
+        }
+    }
+
+    private static int[] parse(Arena a, String datatype) throws Throwable {
+        MemorySegment d = a.allocate(JAVA_INT), be = a.allocate(JAVA_INT);
+        check((int) PARSE_DT.invoke(a.allocateFrom(datatype), d, be));
+        return new int[] { d.get(JAVA_INT, 0), be.get(JAVA_INT, 0) };
+    }
+
+    @Override public void close() {
+        try { DESTROY.invoke(engine); } catch (Throwable ignored) { }
+    }
+}

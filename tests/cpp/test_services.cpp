@@ -1,0 +1,51 @@
+// C++ consumer of the drop-in boundary: exercises include/sa_services.hpp against libsa_engine.so the way
+// the reference's Java services would, with known-answer checks (impulse, on-bin tone, error mapping).
+#include <cmath>
+#include <cstdio>
+#include <complex>
+#include <vector>
+
+#include "sa_services.hpp"
+
+using namespace spectral_analyzer;
+
+#define EXPECT(c) do { if (!(c)) { std::printf("FAIL %s:%d %s\n", __FILE__, __LINE__, #c); return 1; } } while (0)
+
+int main() {
+    Engine eng(0);
+    SpectralService svc(eng);
+    const int n = 1024;
+    // on-bin tone k = 37, cf32_le
+    std::vector<float> iq(2 * 4 * n);
+    for (int i = 0; i < 4 * n; i++) {
+        const double ph = 2.0 * M_PI * 37.0 * (i % n) / n;
+        iq[2 * i] = (float)std::cos(ph); iq[2 * i + 1] = (float)std::sin(ph);
+    }
+    MappedByteBuffer buf{iq.data(), iq.size() * sizeof(float)};
+    std::vector<double> mag = svc.computeMagnitudes(buf, 0, n, "cf32_le");
+    int arg = 0;
+    for (int i = 1; i < n; i++) if (mag[i] > mag[arg]) arg = i;
+    EXPECT(arg == (37 + n / 2) % n);                               // fft-shifted, SpectralService.java:78
+    EXPECT(std::fabs(mag[arg] - 20.0 * std::log10((double)n)) < 1e-3);
+    // waterfall: 5 columns requested, 4 available -> last row is -150 (MainController.java:994-998)
+    std::vector<double> wf = svc.computeWaterfall(buf, 0, 5, n, "cf32_le");
+    EXPECT(wf[4 * n + 3] == -150.0 && std::fabs(wf[3 * n + arg] - mag[arg]) < 1e-3);
+    // error mapping
+    bool threw = false;
+    try { svc.computeMagnitudes(buf, 0, 1000, "cf32_le"); } catch (const std::invalid_argument&) { threw = true; }
+    EXPECT(threw);
+    threw = false;
+    try { svc.computeMagnitudes(buf, (int)buf.capacity - 8, n, "cf32_le"); } catch (const std::out_of_range&) { threw = true; }
+    EXPECT(threw);
+    // downconvert the tone to DC and take its PSD
+    ExtractDownConvertService dc(eng);
+    auto z = dc.extractAndDownConvert(buf, 0, 4 * n, "cf32_le", 37.0 / n, 4);
+    EXPECT(z[0].size() == (size_t)n);
+    EXPECT(std::fabs(z[0][n - 1] - 1.0) < 1e-4 && std::fabs(z[1][n - 1]) < 1e-4);
+    auto psd = PowerSpectralDensity::calculatePsdWelch(eng, z, 1.0e6 / 4, 256);
+    int pk = 0;
+    for (int i = 1; i < 256; i++) if (psd[1][i] > psd[1][pk]) pk = i;
+    EXPECT(std::fabs(psd[0][pk]) < 1.0e6 / 4 / 256 * 1.5);
+    std::printf("cpp services ok\n");
+    return 0;
+}
