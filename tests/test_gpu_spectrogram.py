@@ -186,3 +186,35 @@ def test_both_1024_kernels_against_oracle(engine):
     check_db_parity(got_ldg, ref)
     strong = ref > ref.max(axis=1, keepdims=True) - 40
     assert np.abs(got_ldg - got)[strong].max() < 1e-4   # two twiddle sources, same answer to FP32 rounding
+
+
+@pytest.mark.parametrize("cmap", ["Grayscale", "Heatmap"])
+@pytest.mark.parametrize("dt,nfft", [("cu8", 2048), ("cf32_le", 1024)])
+def test_rgba_epilogue_matches_render(engine, cmap, dt, nfft):
+    """SA_OUT_RGBA8 = renderSpectrogram's dB/Hz conversion + getColorForMagnitude
+    (MainController.java:1273-1285, :926-957), one pixel per (frame, bin).  Channels may differ by one
+    LSB (FP32 dB vs FP64 dB); pixels whose normalised level sits on a Heatmap breakpoint (0.2 / 0.5, where
+    the ramp jumps from black to blue) are excluded."""
+    frames, fs = 24, 2.4e6
+    raw = synth.recording(nfft * frames, dt, seed=17)
+    db = co.spectrogram(raw, dt, 0, nfft, nfft, "rect", frames)
+    # choose a colour range that spans the image so that all ramp segments are exercised
+    conv = 10 * np.log10(fs / nfft) + 20 * np.log10(nfft)
+    lo, hi = float(np.percentile(db - conv, 5)), float(db.max() - conv + 3.0)
+    ref = co.render_rgba(db, fs, lo, hi, cmap).astype(np.int32)
+    got = engine.spectrogram(raw, dt, nfft, frames, out_kind="rgba8", colormap=cmap, sample_rate=fs,
+                             min_db=lo, max_db=hi).astype(np.int32)
+    assert got.shape == (frames, nfft, 4) and (got[..., 3] == 255).all()
+    n = np.clip((db - conv - lo) / (hi - lo), 0, 1)
+    safe = np.ones_like(n, bool)
+    if cmap == "Heatmap":
+        safe = (np.abs(n - 0.2) > 1e-4) & (np.abs(n - 0.5) > 1e-4)
+    assert np.abs(got - ref)[safe].max() <= 1
+    assert (np.abs(got - ref)[safe] > 0).mean() < 0.05
+    assert len(np.unique(ref[..., 0])) > 50 or cmap == "Heatmap"
+    # default range of the reference UI (-160 .. -30 dB/Hz)
+    got2 = engine.spectrogram(raw, dt, nfft, frames, out_kind="rgba8", colormap=cmap, sample_rate=fs)
+    ref2 = co.render_rgba(db, fs, -160.0, -30.0, cmap).astype(np.int32)
+    n2 = np.clip((db - conv + 160.0) / 130.0, 0, 1)
+    safe2 = (np.abs(n2 - 0.2) > 1e-4) & (np.abs(n2 - 0.5) > 1e-4)
+    assert np.abs(got2.astype(np.int32) - ref2)[safe2].max() <= 1
