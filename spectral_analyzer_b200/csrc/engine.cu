@@ -41,6 +41,17 @@ const SpecKernelInfo* find_spec_kernel(int prec, int n, int dk, int win, int tma
     return nullptr;
 }
 
+static std::vector<LargeKernelInfo>& large_registry() {
+    static std::vector<LargeKernelInfo> r;
+    return r;
+}
+void register_large_kernel(const LargeKernelInfo& k) { large_registry().push_back(k); }
+const LargeKernelInfo* find_large_kernel(int prec, int n, int dk, int win) {
+    for (const auto& k : large_registry())
+        if (k.prec == prec && k.n == n && k.dk == dk && k.win == win) return &k;
+    return nullptr;
+}
+
 // ---------------- tables ----------------
 void host_window(int window_id, int n, std::vector<double>& w) {
     w.resize(n);
@@ -132,6 +143,66 @@ int Engine::window_table(int window_id, int n, int prec, const void** d_tab) {
     return SA_OK;
 }
 
+int Engine::root_table(int n, int prec, const void** d_tab) {
+    const uint64_t key = ((uint64_t)prec << 32) | (uint32_t)n;
+    auto it = misc_tables.find(key);
+    if (it != misc_tables.end()) { *d_tab = it->second; return SA_OK; }
+    std::vector<double> re((size_t)n), im((size_t)n);
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int j = 0; j < n; j++) { const double ang = -two_pi * (double)j / (double)n; re[j] = std::cos(ang); im[j] = std::sin(ang); }
+    void* d = nullptr;
+    int rc = (prec == SA_PREC_F64) ? upload_pairs<double>(re, im, &d) : upload_pairs<float>(re, im, &d);
+    if (rc) return rc;
+    misc_tables[key] = d;
+    *d_tab = d;
+    return SA_OK;
+}
+
+// Four-step path (large_fft_kernels.cuh): frames are processed in chunks whose workspace stays L2-sized.
+int Engine::launch_spectrogram_large(const void* d_iq, uint64_t n_samples, const sa_spectrogram_params& p, int prec,
+                                     const SpecArgs& base, void* d_out, cudaStream_t stream) {
+    (void)d_iq; (void)n_samples; (void)d_out;
+    const int dk = dtype_kind(p.dtype);
+    const int win = (prec == SA_PREC_F64) ? 1 : (p.window != SA_WIN_RECT ? 1 : 0);
+    const LargeKernelInfo* k = find_large_kernel(prec, (int)p.nfft, dk, win);
+    if (!k) return set_error(SA_ERR_UNSUPPORTED, "no kernel for nfft %u precision %s dtype %d", p.nfft,
+                             prec == SA_PREC_F64 ? "f64" : "f32", p.dtype);
+    LargeArgs a;
+    memset(&a, 0, sizeof(a));
+    a.s = base;
+    // sub-transform tables come from the plans of the in-SM kernels of the same precision
+    const SpecKernelInfo* k1 = find_spec_kernel(prec, k->n1, DK_CF32, 1, 0);
+    const SpecKernelInfo* k2 = find_spec_kernel(prec, k->n2, DK_CF32, 1, 0);
+    if (!k1 || !k2) return set_error(SA_ERR_UNSUPPORTED, "sub-transform plans %d / %d missing", k->n1, k->n2);
+    int rc = twiddle_table(*k1, &a.s.twiddle);
+    if (rc) return rc;
+    rc = twiddle_table(*k2, &a.tw2);
+    if (rc) return rc;
+    rc = root_table((int)p.nfft, prec, &a.tw_n);
+    if (rc) return rc;
+    if (win) { rc = window_table(p.window, (int)p.nfft, prec, &a.s.window); if (rc) return rc; }
+    const size_t elem = (prec == SA_PREC_F64) ? 16 : 8;
+    const uint64_t per_frame = (uint64_t)p.nfft * elem;
+    const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(p.n_frames, (64ull << 20) / per_frame));
+    rc = ensure_scratch(2, chunk * per_frame);
+    if (rc) return rc;
+    a.ws = scratch[2];
+    cudaError_t e = cudaFuncSetAttribute(k->fn_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->smem_cols);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k->fn_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->smem_rows);
+    if (e != cudaSuccess) return cuda_fail(e, "large FFT smem attribute");
+    void* args[] = { &a };
+    for (uint64_t f0 = 0; f0 < p.n_frames; f0 += chunk) {
+        const unsigned nf = (unsigned)std::min<uint64_t>(chunk, p.n_frames - f0);
+        a.frame0 = (long long)f0;
+        e = cudaLaunchKernel(k->fn_cols, dim3(k->n2 / kLargeC, nf), dim3(k->cta_cols), args, k->smem_cols, stream);
+        if (e != cudaSuccess) return cuda_fail(e, "launch large_cols_kernel");
+        e = cudaLaunchKernel(k->fn_rows, dim3(k->n1 / kLargeC, nf), dim3(k->cta_rows), args, k->smem_rows, stream);
+        if (e != cudaSuccess) return cuda_fail(e, "launch large_rows_kernel");
+        launches += 2;
+    }
+    return SA_OK;
+}
+
 int Engine::kernel_grid(const void* fn, int cta, size_t smem, int* blocks_per_sm) {
     auto it = occupancy.find(fn);
     if (it != occupancy.end()) { *blocks_per_sm = it->second; return SA_OK; }
@@ -202,14 +273,6 @@ int Engine::launch_spectrogram(const void* d_iq, uint64_t n_samples, const sa_sp
     if (p.n_frames == 0) return SA_OK;
     const int dk = dtype_kind(p.dtype);
     const int win = (prec == SA_PREC_F64) ? 1 : (p.window != SA_WIN_RECT ? 1 : 0);
-    // TMA-staged variant (needs every frame start 16-byte aligned), else the LDG kernel
-    const uint64_t iq_b = (uint64_t)sa_bytes_per_iq(p.dtype);
-    const bool aligned = ((uintptr_t)d_iq % 16 == 0) && ((p.start_sample * iq_b) % 16 == 0) && ((p.hop * iq_b) % 16 == 0);
-    static const bool no_tma = getenv("SA_NO_TMA") != nullptr;      // A/B switch for the ablation in DESIGN.md
-    const SpecKernelInfo* k = (aligned && !no_tma) ? find_spec_kernel(prec, (int)p.nfft, dk, win, 1) : nullptr;
-    if (!k) k = find_spec_kernel(prec, (int)p.nfft, dk, win, 0);
-    if (!k) return set_error(SA_ERR_UNSUPPORTED, "no kernel for nfft %u precision %s dtype %d", p.nfft,
-                             prec == SA_PREC_F64 ? "f64" : "f32", p.dtype);
     SpecArgs a;
     memset(&a, 0, sizeof(a));
     fill_load_params(a.lp, d_iq, p.dtype, p.big_endian);
@@ -217,9 +280,6 @@ int Engine::launch_spectrogram(const void* d_iq, uint64_t n_samples, const sa_sp
     a.start_sample = (long long)p.start_sample;
     a.hop = (long long)p.hop;
     a.n_frames = (long long)p.n_frames;
-    int rc = twiddle_table(*k, &a.twiddle);
-    if (rc) return rc;
-    if (win) { rc = window_table(p.window, (int)p.nfft, prec, &a.window); if (rc) return rc; }
     a.out = d_out;
     a.out_kind = p.out_kind;
     a.db_mode = p.db_mode;
@@ -230,6 +290,20 @@ int Engine::launch_spectrogram(const void* d_iq, uint64_t n_samples, const sa_sp
         a.inv_range = (float)(1.0 / (p.max_db - p.min_db));
         a.cmap = p.colormap;
     }
+    // transforms too large for one SM's shared memory take the four-step path
+    if (p.nfft > 16384 || (prec == SA_PREC_F64 && p.nfft > 8192))
+        return launch_spectrogram_large(d_iq, n_samples, p, prec, a, d_out, stream);
+    // TMA-staged variant (needs every frame start 16-byte aligned), else the LDG kernel
+    const uint64_t iq_b = (uint64_t)sa_bytes_per_iq(p.dtype);
+    const bool aligned = ((uintptr_t)d_iq % 16 == 0) && ((p.start_sample * iq_b) % 16 == 0) && ((p.hop * iq_b) % 16 == 0);
+    static const bool no_tma = getenv("SA_NO_TMA") != nullptr;      // A/B switch for the ablation in DESIGN.md
+    const SpecKernelInfo* k = (aligned && !no_tma) ? find_spec_kernel(prec, (int)p.nfft, dk, win, 1) : nullptr;
+    if (!k) k = find_spec_kernel(prec, (int)p.nfft, dk, win, 0);
+    if (!k) return set_error(SA_ERR_UNSUPPORTED, "no kernel for nfft %u precision %s dtype %d", p.nfft,
+                             prec == SA_PREC_F64 ? "f64" : "f32", p.dtype);
+    int rc = twiddle_table(*k, &a.twiddle);
+    if (rc) return rc;
+    if (win) { rc = window_table(p.window, (int)p.nfft, prec, &a.window); if (rc) return rc; }
     int bps = 0;
     rc = kernel_grid(k->fn, k->cta, k->smem, &bps);
     if (rc) return rc;
@@ -323,7 +397,7 @@ Engine::~Engine() {
         if (slots[i].stream) cudaStreamDestroy(slots[i].stream);
     }
     for (auto& r : registered) cudaHostUnregister(const_cast<void*>(r));
-    for (int i = 0; i < 2; i++) if (scratch[i]) cudaFree(scratch[i]);
+    for (int i = 0; i < 3; i++) if (scratch[i]) cudaFree(scratch[i]);
 }
 
 int Engine::ensure_scratch(int which, size_t bytes) {

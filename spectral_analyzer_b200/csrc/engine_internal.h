@@ -7,12 +7,14 @@
 
 #include "../../include/sa_engine.h"
 #include "spectrogram_tma_kernel.cuh"
+#include "large_fft_kernels.cuh"
 
 namespace sa {
 
 int set_error(int code, const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 const SpecKernelInfo* find_spec_kernel(int prec, int n, int dk, int win, int tma);
+const LargeKernelInfo* find_large_kernel(int prec, int n, int dk, int win);
 void host_window(int window_id, int n, std::vector<double>& w);
 int dtype_kind(int dtype);
 void fill_load_params(LoadParams& lp, const void* base, int dtype, int big_endian);
@@ -37,8 +39,8 @@ struct Engine {
     std::map<const void*, int> occupancy;            // kernel -> resident CTAs per SM
     std::vector<const void*> registered;             // cudaHostRegister'ed ranges
     Slot slots[kSlots];
-    void* scratch[2] = {nullptr, nullptr};           // device workspaces: [0] annotation plan + taps,
-    size_t scratch_cap[2] = {0, 0};                  //                    [1] Welch plan + partial spectra
+    void* scratch[3] = {nullptr, nullptr, nullptr};  // device workspaces: [0] annotation plan + taps,
+    size_t scratch_cap[3] = {0, 0, 0};               // [1] Welch plan + partial spectra, [2] four-step FFT
 
     ~Engine();
     int twiddle_table(const SpecKernelInfo& k, const void** d_tab);
@@ -46,6 +48,9 @@ struct Engine {
     int kernel_grid(const void* fn, int cta, size_t smem, int* blocks_per_sm);
     int ensure_slot(Slot& s, size_t in_bytes, size_t out_bytes);
     int ensure_scratch(int which, size_t bytes);
+    int root_table(int n, int prec, const void** d_tab);      // W_n^j, j = 0..n-1
+    int launch_spectrogram_large(const void* d_iq, uint64_t n_samples, const sa_spectrogram_params& p, int prec,
+                                 const SpecArgs& base, void* d_out, cudaStream_t stream);
     int launch_spectrogram(const void* d_iq, uint64_t n_samples, const sa_spectrogram_params& p, int prec,
                            void* d_out, cudaStream_t stream);
     int spectrogram_host(const void* iq, uint64_t iq_bytes, const sa_spectrogram_params& p, int prec, void* out);

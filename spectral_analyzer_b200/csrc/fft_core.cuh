@@ -321,13 +321,14 @@ template <typename T, int N> struct Geo {
 // stride-R0 128-bit writes of pass 0 and the unit-stride reads conflict-free
 template <int R0, int PADW> __device__ __forceinline__ int pad_idx(int i) { return i + (i / R0) * PADW; }
 
-template <int TPF> __device__ __forceinline__ void frame_sync() {
-    if constexpr (TPF <= 32) __syncwarp(); else __syncthreads();
+// BSYNC forces a CTA barrier (thread mappings where a frame's threads are spread over several warps)
+template <int TPF, bool BSYNC = false> __device__ __forceinline__ void frame_sync() {
+    if constexpr (TPF <= 32 && !BSYNC) __syncwarp(); else __syncthreads();
 }
 
 // One pass: S radix-R butterflies (window or Stockham twiddle fused into their first stage) and,
 // unless it is the last pass, the exchange through shared memory.
-template <typename T, int N, int PASS, bool WIN, bool REC>
+template <typename T, int N, int PASS, bool WIN, bool REC, bool BSYNC = false>
 __device__ __forceinline__ void fft_pass(cpx<T> (&v)[Plan<T, N>::P], const int t, cpx<T>* __restrict__ sm,
                                          const cpx<T>* __restrict__ tw, const T* __restrict__ win,
                                          const TwSeed<T>& seed) {
@@ -342,7 +343,7 @@ __device__ __forceinline__ void fft_pass(cpx<T> (&v)[Plan<T, N>::P], const int t
         else RadixAll<T, R, S, P, MUL_CPX, G::TW_SMEM, 0>::run(v, nullptr, twp, TPF, seed);
     }
     if constexpr (PASS + 1 < PL::NP) {
-        frame_sync<TPF>();   // every reader of the previous exchange (or previous frame) is done
+        frame_sync<TPF, BSYNC>();   // every reader of the previous exchange (or previous frame) is done
 #pragma unroll
         for (int s = 0; s < S; s++) {
             const int j = t + TPF * s;
@@ -358,7 +359,7 @@ __device__ __forceinline__ void fft_pass(cpx<T> (&v)[Plan<T, N>::P], const int t
                 for (int m = 0; m < R; m++) sm[pad_idx<G::R0, G::PADW>(base + m * NS)] = v[s + m * S];
             }
         }
-        frame_sync<TPF>();
+        frame_sync<TPF, BSYNC>();
 #pragma unroll
         for (int q = 0; q < P; q++) v[q] = sm[pad_idx<G::R0, G::PADW>(t + TPF * q)];
     }
@@ -381,15 +382,15 @@ __device__ __forceinline__ TwSeed<T> load_tw_seed(const cpx<T>* __restrict__ tw,
 
 // Full transform of the registers of one frame; win (T[P], thread-private) multiplies the inputs
 // when WIN is set.
-template <typename T, int N, bool WIN, bool REC = false>
+template <typename T, int N, bool WIN, bool REC = false, bool BSYNC = false>
 __device__ __forceinline__ void fft_frame(cpx<T> (&v)[Plan<T, N>::P], const int t, cpx<T>* __restrict__ sm,
                                           const cpx<T>* __restrict__ tw, const T* __restrict__ win,
                                           const TwSeed<T>& seed) {
     using PL = Plan<T, N>;
-    fft_pass<T, N, 0, WIN, REC>(v, t, sm, tw, win, seed);
-    if constexpr (PL::NP > 1) fft_pass<T, N, 1, WIN, REC>(v, t, sm, tw, win, seed);
-    if constexpr (PL::NP > 2) fft_pass<T, N, 2, WIN, REC>(v, t, sm, tw, win, seed);
-    if constexpr (PL::NP > 3) fft_pass<T, N, 3, WIN, REC>(v, t, sm, tw, win, seed);
+    fft_pass<T, N, 0, WIN, REC, BSYNC>(v, t, sm, tw, win, seed);
+    if constexpr (PL::NP > 1) fft_pass<T, N, 1, WIN, REC, BSYNC>(v, t, sm, tw, win, seed);
+    if constexpr (PL::NP > 2) fft_pass<T, N, 2, WIN, REC, BSYNC>(v, t, sm, tw, win, seed);
+    if constexpr (PL::NP > 3) fft_pass<T, N, 3, WIN, REC, BSYNC>(v, t, sm, tw, win, seed);
 }
 
 }  // namespace sa

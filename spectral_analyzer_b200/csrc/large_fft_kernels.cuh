@@ -1,0 +1,133 @@
+// large_fft_kernels.cuh -- four-step FFT for transforms that do not fit one SM's shared memory
+// (FP32 nfft 32768 / 65536, FP64 nfft 16384 / 32768 / 65536; nfft slider range main-scene.fxml:129).
+//
+// N = N1*N2, n = N2*n1 + n2, k = k1 + N1*k2:
+//   large_cols_kernel : per frame and per group of C columns n2: decode + window, N1-point FFT over n1
+//                       (register/shared-memory FFT of fft_core.cuh, threads of a column spread over
+//                       warps so that the C columns are the fast thread index -> coalesced loads),
+//                       multiply by W_N^(n2*k1), write A[k1][n2] to an L2-sized workspace.
+//   large_rows_kernel : per frame and per group of C rows k1: N2-point FFT over n2 (contiguous loads),
+//                       |X| -> dB, transpose the C x N2 tile through shared memory so that consecutive
+//                       threads store consecutive bins k = k1 + N1*k2, fft-shifted.
+// Same arithmetic contract as spectrogram_kernel (SpectralService.java:33-85, MainController.java:980-999).
+#pragma once
+#include "spectrogram_kernel.cuh"
+
+namespace sa {
+
+constexpr int kLargeC = 16;      // columns / rows per CTA
+
+struct LargeArgs {
+    SpecArgs s;                  // s.twiddle: pair table of the N1-point plan; s.window: T[N]
+    long long frame0;            // first frame of this chunk
+    const void* tw2;             // pair table of the N2-point plan
+    const void* tw_n;            // cpx<T>[N]: W_N^j
+    void* ws;                    // cpx<T>[chunk frames][N1][N2]
+};
+
+template <typename T, int N1, int N2, int DK, bool WIN>
+__global__ void __launch_bounds__(kLargeC * Geo<T, N1>::TPF)
+large_cols_kernel(const LargeArgs a) {
+    using G = Geo<T, N1>;
+    constexpr int P = G::P, TPF = G::TPF, N = N1 * N2, C = kLargeC;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int fl = threadIdx.x % C, t = threadIdx.x / C;          // column is the fast index
+    cpx<T>* sm = reinterpret_cast<cpx<T>*>(smem_raw) + (size_t)fl * G::SM_ELEMS;
+    const long long frame = a.frame0 + blockIdx.y;
+    const long long s0 = a.s.start_sample + frame * a.s.hop;
+    if (s0 + N > a.s.n_samples) return;                           // EOF frame: large_rows_kernel writes the fill row
+    const int n2 = blockIdx.x * C + fl;
+    cpx<T> v[P];
+    if (a.s.lp.swap) {
+#pragma unroll
+        for (int q = 0; q < P; q++) v[q] = Loader<T, DK>::template load<true>(a.s.lp, s0 + (long long)(t + TPF * q) * N2 + n2);
+    } else {
+#pragma unroll
+        for (int q = 0; q < P; q++) v[q] = Loader<T, DK>::template load<false>(a.s.lp, s0 + (long long)(t + TPF * q) * N2 + n2);
+    }
+    if constexpr (WIN) {
+        const T* w = reinterpret_cast<const T*>(a.s.window);
+#pragma unroll
+        for (int q = 0; q < P; q++) { const T wv = __ldg(&w[(t + TPF * q) * N2 + n2]); v[q].x *= wv; v[q].y *= wv; }
+    }
+    TwSeed<T> seed; seed.om = mk2<T>((T)1, (T)0); seed.oh = seed.om;
+    fft_frame<T, N1, false, false, true>(v, t, sm, reinterpret_cast<const cpx<T>*>(a.s.twiddle), nullptr, seed);
+    const cpx<T>* twn = reinterpret_cast<const cpx<T>*>(a.tw_n);
+    cpx<T>* ws = reinterpret_cast<cpx<T>*>(a.ws) + (size_t)blockIdx.y * N;
+#pragma unroll
+    for (int q = 0; q < P; q++) {
+        const int k1 = t + TPF * q;
+        const cpx<T> w = __ldg(&twn[(n2 * k1) & (N - 1)]);
+        ws[(size_t)k1 * N2 + n2] = mk2<T>(fma_t(-w.y, v[q].y, w.x * v[q].x), fma_t(w.y, v[q].x, w.x * v[q].y));
+    }
+}
+
+template <typename T, int N1, int N2>
+__global__ void __launch_bounds__(kLargeC * Geo<T, N2>::TPF)
+large_rows_kernel(const LargeArgs a) {
+    using G = Geo<T, N2>;
+    constexpr int P = G::P, TPF = G::TPF, N = N1 * N2, C = kLargeC, THREADS = C * TPF;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int t = threadIdx.x % TPF, fl = threadIdx.x / TPF;      // element is the fast index
+    cpx<T>* sm = reinterpret_cast<cpx<T>*>(smem_raw) + (size_t)fl * G::SM_ELEMS;
+    const long long frame = a.frame0 + blockIdx.y;
+    const long long s0 = a.s.start_sample + frame * a.s.hop;
+    const bool readable = s0 + N <= a.s.n_samples;                // CTA-uniform, MainController.java:987
+    const int k1 = blockIdx.x * C + fl;
+    T db[P];
+    if (readable) {
+        const cpx<T>* ws = reinterpret_cast<const cpx<T>*>(a.ws) + (size_t)blockIdx.y * N + (size_t)k1 * N2;
+        cpx<T> v[P];
+#pragma unroll
+        for (int q = 0; q < P; q++) v[q] = ws[t + TPF * q];
+        TwSeed<T> seed; seed.om = mk2<T>((T)1, (T)0); seed.oh = seed.om;
+        fft_frame<T, N2, false, false, true>(v, t, sm, reinterpret_cast<const cpx<T>*>(a.tw2), nullptr, seed);
+        if (a.s.db_mode == DBM_MAG_1E10) bins_to_db<T, P, DBM_MAG_1E10>(v, db);
+        else bins_to_db<T, P, DBM_POWER>(v, db);
+    } else {
+#pragma unroll
+        for (int q = 0; q < P; q++) db[q] = (T)a.s.eof_fill;
+    }
+    // transpose the [C rows k1][N2 bins k2] tile so that consecutive threads hold consecutive k = k1 + N1*k2
+    T* tile = reinterpret_cast<T*>(smem_raw);
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < P; q++) tile[(t + TPF * q) * (C + 1) + fl] = db[q];
+    __syncthreads();
+    const int c = threadIdx.x % C, j0 = threadIdx.x / C;
+    const size_t row = (size_t)frame * N;
+    const int kbase = blockIdx.x * C + c;
+    for (int k2 = j0; k2 < N2; k2 += THREADS / C) {
+        const T val = tile[k2 * (C + 1) + c];
+        const size_t o = row + (size_t)((kbase + N1 * k2 + N / 2) & (N - 1));     // SpectralService.java:78
+        if (a.s.out_kind == OUT_F32_DB) reinterpret_cast<float*>(a.s.out)[o] = (float)val;
+        else if (a.s.out_kind == OUT_F64_DB) reinterpret_cast<double*>(a.s.out)[o] = (double)val;
+        else reinterpret_cast<uint32_t*>(a.s.out)[o] = colormap_rgba((float)val, a.s);
+    }
+}
+
+struct LargeKernelInfo {
+    const void* fn_cols; const void* fn_rows;
+    int prec, n, n1, n2, dk, win;
+    int cta_cols, cta_rows;
+    size_t smem_cols, smem_rows;
+};
+
+void register_large_kernel(const LargeKernelInfo& k);     // engine.cu
+
+template <typename T, int N1, int N2, int DK, bool WIN>
+LargeKernelInfo make_large_info(int prec) {
+    LargeKernelInfo k;
+    k.fn_cols = (const void*)&large_cols_kernel<T, N1, N2, DK, WIN>;
+    k.fn_rows = (const void*)&large_rows_kernel<T, N1, N2>;
+    k.prec = prec; k.n = N1 * N2; k.n1 = N1; k.n2 = N2; k.dk = DK; k.win = WIN ? 1 : 0;
+    k.cta_cols = kLargeC * Geo<T, N1>::TPF;
+    k.cta_rows = kLargeC * Geo<T, N2>::TPF;
+    k.smem_cols = (size_t)kLargeC * Geo<T, N1>::SM_ELEMS * sizeof(cpx<T>);
+    const size_t ex = (size_t)kLargeC * Geo<T, N2>::SM_ELEMS * sizeof(cpx<T>);
+    const size_t tile = (size_t)N2 * (kLargeC + 1) * sizeof(T);
+    k.smem_rows = ex > tile ? ex : tile;
+    return k;
+}
+
+}  // namespace sa

@@ -46,7 +46,7 @@ def test_integer_decode_bit_exact(engine, dt):
         assert lin.max() <= 2e-6 * 10 ** (ref.max() / 20.0), (dt, v)
 
 
-@pytest.mark.parametrize("nfft", [64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384])
+@pytest.mark.parametrize("nfft", [64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536])
 def test_reference_parity_mode_all_sizes(engine, nfft):
     """rect window, hop = nfft, 20*log10(|X|+1e-10): the reference's own framing."""
     frames = 9
@@ -69,7 +69,7 @@ def test_dtypes_windows_hops(engine, dt, nfft, win, hop):
 
 
 @pytest.mark.parametrize("dt", ["cf64_le", "cf64_be", "cf32_le", "ci16_le", "cu8"])
-@pytest.mark.parametrize("nfft", [64, 512, 1024, 8192])
+@pytest.mark.parametrize("nfft", [64, 512, 1024, 8192, 16384, 32768, 65536])
 def test_fp64_path_tight(engine, dt, nfft):
     frames = 5
     raw = synth.recording(nfft * frames, dt, seed=5)
@@ -218,3 +218,31 @@ def test_rgba_epilogue_matches_render(engine, cmap, dt, nfft):
     n2 = np.clip((db - conv + 160.0) / 130.0, 0, 1)
     safe2 = (np.abs(n2 - 0.2) > 1e-4) & (np.abs(n2 - 0.5) > 1e-4)
     assert np.abs(got2.astype(np.int32) - ref2)[safe2].max() <= 1
+
+
+@pytest.mark.parametrize("dt", ["cf32_le", "ci16_be", "cu8"])
+@pytest.mark.parametrize("nfft,win,hop", [(32768, "hann", 16384), (65536, "blackman_harris", 65536), (65536, "hann", 5000)])
+def test_large_four_step_fp32(engine, dt, nfft, win, hop):
+    """nfft above one SM's shared memory: four-step kernels (large_fft_kernels.cuh)."""
+    frames = 5
+    raw = synth.recording((frames - 2) * hop + nfft + 11, dt, seed=41)       # the last frame runs past EOF
+    ref = co.spectrogram(raw, dt, 7, nfft, hop, win, frames)
+    got = engine.spectrogram(raw, dt, nfft, frames, hop=hop, window=win, start_sample=7)
+    assert (ref[-1] == -150.0).all() and (got[-1] == -150.0).all()
+    check_db_parity(got[:-1], ref[:-1])
+
+
+def test_config5_cf64_65536_hann(engine):
+    """BASELINE config 5 in miniature: cf64 recording, 65536-point Hann FFT on the FP64 path."""
+    nfft, frames = 65536, 3
+    raw = synth.recording(nfft * frames, "cf64_le", seed=5)
+    ref = co.spectrogram(raw, "cf64_le", 0, nfft, nfft, "hann", frames)
+    got = engine.spectrogram(raw, "cf64_le", nfft, frames, window="hann", out_kind="f64")
+    assert got.dtype == np.float64
+    check_db_parity(got, ref, strong_tol=1e-9, floor_tol=1e-6)
+    # 16-bit stereo WAV: 44-byte header, ci16_le (NonconformingDatasetHelper.java:137-156); the mapped buffer
+    # starts after the header (SigMfHelper.java:84), i.e. only 4-byte aligned in the file
+    body = synth.recording(1024 * 9, "ci16_le", seed=6)
+    wav = np.concatenate([np.zeros(44, np.uint8), body])
+    got = engine.spectrogram(wav[44:], "ci16_le", 1024, 9)
+    check_db_parity(got, co.spectrogram(body, "ci16_le", 0, 1024, 1024, "rect", 9))
