@@ -1,0 +1,128 @@
+#!/usr/bin/env python
+"""bench_configs.py -- device-resident throughput of the other BASELINE.json configurations (not the
+headline line; bench.py owns that).  Prints one JSON object per configuration with the achieved fraction
+of the HBM roofline from the algorithmic bytes of SURVEY.md 8d.  Synthetic data, one GPU.
+
+    python bench_configs.py [--scale 1.0]     # --scale shrinks the sample counts (smoke runs)
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import spectral_analyzer_b200 as sa                      # noqa: E402
+from spectral_analyzer_b200 import _capi                 # noqa: E402
+from bench import hbm_peak                               # noqa: E402
+
+
+def timed(fn, steps, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record()
+    for i in range(steps):
+        fn()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    t = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(steps))
+    return t[len(t) // 2]
+
+
+def spectrogram_case(eng, name, datatype, n_samples, nfft, hop, window, out_kind, steps, **kw):
+    kind = datatype.split("_")[0]
+    bps = {"cf32": 8, "ci16": 4, "cu8": 2, "ci8": 2, "cf64": 16}[kind]
+    dev = torch.device("cuda", 0)
+    if kind == "cf32":
+        raw = torch.randn(2 * n_samples, device=dev, dtype=torch.float32).mul_(0.1)
+    elif kind == "cf64":
+        raw = torch.randn(2 * n_samples, device=dev, dtype=torch.float64).mul_(0.1)
+    elif kind == "ci16":
+        raw = torch.randint(-20000, 20000, (2 * n_samples,), device=dev, dtype=torch.int16)
+    else:
+        raw = torch.randint(0, 255, (2 * n_samples,), device=dev, dtype=torch.uint8)
+    frames = (n_samples - nfft) // hop + 1
+    obytes = {"f32": 4, "f64": 8, "rgba8": 4}[out_kind]
+    out = torch.empty(frames * nfft * obytes, device=dev, dtype=torch.uint8)
+    p = eng.make_params(datatype, nfft, hop, window, n_frames=frames, out=out_kind, **kw)
+    stream = torch.cuda.current_stream().cuda_stream
+    ms = timed(lambda: eng.spectrogram_device(raw.data_ptr(), n_samples * bps, p, out.data_ptr(), out.numel(), stream), steps)
+    alg = n_samples * bps + frames * nfft * obytes
+    peak, kind_p = hbm_peak()
+    res = {"config": name, "datatype": datatype, "samples": n_samples, "nfft": nfft, "hop": hop, "window": window,
+           "out": out_kind, "ms": round(ms, 4), "Msamples_per_s": round(frames * hop / ms / 1e3, 1),
+           "alg_bytes": alg, "GBps": round(alg / ms / 1e6, 1), "roofline_frac": round(alg / ms / 1e6 / peak, 4),
+           "peak_kind": kind_p}
+    del raw, out
+    torch.cuda.empty_cache()
+    return res
+
+
+def annotation_case(eng, n_samples, n_ann, count, down, steps):
+    dev = torch.device("cuda", 0)
+    raw = torch.randn(2 * n_samples, device=dev, dtype=torch.float32).mul_(0.1)
+    rng = np.random.default_rng(3)
+    anns = (_capi.Annotation * n_ann)()
+    offs = (C.c_uint64 * n_ann)()
+    m = count // down
+    for i in range(n_ann):
+        anns[i] = _capi.Annotation(int(rng.integers(0, n_samples - count)), count, float(rng.uniform(-0.4, 0.4)), down, 0)
+        offs[i] = i * 2 * m
+    out_iq = torch.empty(n_ann * 2 * m, device=dev, dtype=torch.float64)
+    out_psd = torch.empty(n_ann * 8192, device=dev, dtype=torch.float64)
+    stream = torch.cuda.current_stream().cuda_stream
+    L = _capi.lib()
+
+    def run():
+        _capi.check(L.sa_downconvert_psd_batch_device(eng.handle, raw.data_ptr(), n_samples * 8, 0, 0, 1.0e6, anns, n_ann,
+                                                      8192, 2048, 1, out_iq.data_ptr(), offs, out_psd.data_ptr(), stream))
+    ms = timed(run, steps)
+    alg = n_ann * (8 * count + 16 * m + 8 * 8192)
+    peak, kind_p = hbm_peak()
+    return {"config": "C3 annotation analysis", "annotations": n_ann, "count": count, "down": down, "psd_nfft": 8192,
+            "ms": round(ms, 4), "Msamples_per_s": round(n_ann * count / ms / 1e3, 1), "alg_bytes": alg,
+            "GBps": round(alg / ms / 1e6, 1), "roofline_frac": round(alg / ms / 1e6 / peak, 4), "peak_kind": kind_p}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--only", default="", help="substring filter on the configuration name")
+    args = ap.parse_args()
+    sc = lambda n: max(1 << 20, int(n * args.scale))
+    eng = sa.Engine(0)
+    res = []
+    cases = []
+    cases.append(('C1-parity (reference framing)', lambda: spectrogram_case(eng, "C1-parity (reference framing)", "cf32_le", sc(1 << 28), 1024, 1024, "rect", "f32", args.steps)))
+    cases.append(('C2 ci16 4096 Blackman-Harris', lambda: spectrogram_case(eng, "C2 ci16 4096 Blackman-Harris", "ci16_le", sc(1 << 30), 4096, 4096, "blackman_harris", "f32", args.steps)))
+    cases.append(('C2b ci16 4096 Blackman-Harris 50% overlap', lambda: spectrogram_case(eng, "C2b ci16 4096 Blackman-Harris 50% overlap", "ci16_le", sc(1 << 29), 4096, 2048, "blackman_harris", "f32", args.steps)))
+    cases.append(('C3 annotation analysis', lambda: annotation_case(eng, sc(1 << 29), 500, 1 << 20, 16, args.steps)))
+    cases.append(("C4 cu8 2048 RGBA heatmap (1-GPU slice)", lambda: spectrogram_case(
+        eng, "C4 cu8 2048 RGBA heatmap (1-GPU slice)", "cu8", sc(1 << 31), 2048, 2048, "rect", "rgba8", args.steps,
+        colormap="Heatmap", sample_rate=2.4e6)))
+    cases.append(("C4b cu8 2048 Hann RGBA", lambda: spectrogram_case(
+        eng, "C4b cu8 2048 Hann RGBA", "cu8", sc(1 << 30), 2048, 2048, "hann", "rgba8", args.steps,
+        colormap="Heatmap", sample_rate=2.4e6)))
+    cases.append(("C4c cu8 2048 rect f32 dB", lambda: spectrogram_case(
+        eng, "C4c cu8 2048 rect f32 dB", "cu8", sc(1 << 30), 2048, 2048, "rect", "f32", args.steps)))
+    cases.append(('C5 cf64 65536 Hann f64', lambda: spectrogram_case(eng, "C5 cf64 65536 Hann f64", "cf64_le", sc(1 << 26), 65536, 65536, "hann", "f64", args.steps)))
+    cases.append(('cf32 65536 Hann (four-step FP32)', lambda: spectrogram_case(eng, "cf32 65536 Hann (four-step FP32)", "cf32_le", sc(1 << 27), 65536, 65536, "hann", "f32", args.steps)))
+    cases.append(('cf32 256 rect', lambda: spectrogram_case(eng, "cf32 256 rect", "cf32_le", sc(1 << 28), 256, 256, "rect", "f32", args.steps)))
+    cases.append(('cf32 16384 Hann', lambda: spectrogram_case(eng, "cf32 16384 Hann", "cf32_le", sc(1 << 28), 16384, 16384, "hann", "f32", args.steps)))
+    for name, fn in cases:
+        if args.only in name:
+            res.append(fn())
+    for r in res:
+        print(json.dumps(r))
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()
