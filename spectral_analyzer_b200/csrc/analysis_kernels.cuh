@@ -56,6 +56,85 @@ __device__ __forceinline__ float2 load_mixed(const DcArgs& a, const DcAnn& an, l
     return nco_mix(make_float2(x.x, x.y), an.phase_step * (unsigned long long)n);
 }
 
+// e^{-2 pi i phase / 2^64} as (cos, -sin)
+__device__ __forceinline__ float2 nco_phasor(unsigned long long phase) {
+    const float ang = (float)(int)(unsigned)(phase >> 32) * (6.283185307179586f / 4294967296.0f);
+    float s, c;
+    __sincosf(ang, &s, &c);
+    return make_float2(c, -s);
+}
+__device__ __forceinline__ float2 cmul(float2 x, float2 p) {
+    return make_float2(__fmaf_rn(x.x, p.x, -x.y * p.y), __fmaf_rn(x.x, p.y, x.y * p.x));
+}
+
+// Stages the decoded + mixed samples n = nlo .. nlo + n_stage - 1 of one tile: stage[i + (i / D) * pad].
+// Samples are fetched as 16-byte groups (2 cf32 / 4 ci16 / 8 cu8 pairs) aligned in GLOBAL memory, kDcUnroll
+// groups in flight per thread; the NCO phasor of a group's first sample comes from the exact 64-bit phase and
+// advances by one complex multiply per sample inside the group.
+constexpr int kDcUnroll = 4;
+
+template <int DK>
+__device__ __forceinline__ void dc_stage_tile(const DcArgs& a, const DcAnn& an, float2* __restrict__ stage,
+                                              const long long nlo, const int n_stage, const int D, const int pad) {
+    constexpr int bps = DK == DK_CF32 ? 8 : DK == DK_CI16 ? 4 : DK == DK_C8 ? 2 : 16;
+    constexpr int V = 16 / bps;                                  // samples per 16-byte group
+    const char* base = reinterpret_cast<const char*>(a.lp.base);
+    const long long g_lo = an.start_sample + nlo;                // global sample of staged index 0 (may be < 0)
+    // staged index of the first group is -shift: groups start on 16-byte boundaries of the capture
+    const int shift = (int)((((unsigned long long)(uintptr_t)base / bps) + (unsigned long long)(g_lo + (1LL << 40) * V)) % V);
+    const int n_groups = (n_stage + shift + V - 1) / V;
+    const float2 wstep = nco_phasor(an.phase_step);
+    for (int k0 = threadIdx.x; k0 < n_groups; k0 += kDcThreads * kDcUnroll) {
+        uint4 raw[kDcUnroll];
+        bool vec[kDcUnroll];
+#pragma unroll
+        for (int u = 0; u < kDcUnroll; u++) {
+            const int k = k0 + u * kDcThreads;
+            const long long n0 = nlo + (long long)k * V - shift;  // annotation-relative sample of the group
+            const long long g0 = an.start_sample + n0;
+            vec[u] = (k < n_groups) && (n0 >= 0) && (g0 + V <= a.n_samples);
+            raw[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (vec[u]) raw[u] = __ldg(reinterpret_cast<const uint4*>(base + g0 * bps));
+        }
+#pragma unroll
+        for (int u = 0; u < kDcUnroll; u++) {
+            const int k = k0 + u * kDcThreads;
+            if (k >= n_groups) break;
+            const int i0 = k * V - shift;
+            const long long n0 = nlo + i0;
+            int q = (i0 >= 0 ? i0 : 0) / D, rem = (i0 >= 0 ? i0 : 0) - q * D;
+            float2 ph = nco_phasor(an.phase_step * (unsigned long long)n0);
+            const uint32_t w[4] = { raw[u].x, raw[u].y, raw[u].z, raw[u].w };
+#pragma unroll
+            for (int j = 0; j < V; j++) {
+                const int i = i0 + j;
+                float2 x;
+                if (vec[u]) {
+                    cpx<float> d;
+                    if (a.lp.swap) {
+                        if constexpr (DK == DK_CF32) d = Loader<float, DK>::template decode<true>(a.lp, make_uint2(w[2 * j], w[2 * j + 1]));
+                        else if constexpr (DK == DK_CI16) d = Loader<float, DK>::template decode<true>(a.lp, w[j]);
+                        else if constexpr (DK == DK_C8) d = Loader<float, DK>::template decode<true>(a.lp, (uint16_t)(w[j / 2] >> (16 * (j & 1))));
+                        else d = Loader<float, DK>::template decode<true>(a.lp, raw[u]);
+                    } else {
+                        if constexpr (DK == DK_CF32) d = Loader<float, DK>::template decode<false>(a.lp, make_uint2(w[2 * j], w[2 * j + 1]));
+                        else if constexpr (DK == DK_CI16) d = Loader<float, DK>::template decode<false>(a.lp, w[j]);
+                        else if constexpr (DK == DK_C8) d = Loader<float, DK>::template decode<false>(a.lp, (uint16_t)(w[j / 2] >> (16 * (j & 1))));
+                        else d = Loader<float, DK>::template decode<false>(a.lp, raw[u]);
+                    }
+                    x = cmul(make_float2(d.x, d.y), ph);
+                } else {
+                    // group touching the zero history or the end of the capture: per-sample path
+                    x = (i >= 0 && i < n_stage) ? load_mixed<DK>(a, an, n0 + j) : make_float2(0.f, 0.f);
+                }
+                if (i >= 0 && i < n_stage) stage[i + q * pad] = x;
+                if (i >= 0) { if (++rem == D) { rem = 0; q++; } }
+                if (j + 1 < V) ph = cmul(ph, wstep);
+            }
+        }
+    }
+}
+
 // Staged kernel (down <= kDcMaxDown): one tile = an.nb consecutive outputs of one annotation.
 // Samples are decoded and mixed ONCE into shared memory; thread b then forms the 8 polyphase
 // partial sums C_p[b] = sum_r h[Dp + r] y[bD - r] of input block b, and
@@ -80,15 +159,7 @@ downconvert_kernel(const DcArgs a) {
     const float* ht = h + 8 * D + 1;
     const long long nlo = an.fast ? m0 * D : (m0 - 8) * D;
 
-    {   // stage: i -> phys(i) = i + (i / D) * pad, incrementally
-        int i = threadIdx.x, q = i / D, rem = i - q * D;
-        const int dq = kDcThreads / D, dr = kDcThreads - dq * D;
-        for (; i < n_stage; i += kDcThreads) {
-            stage[i + q * pad] = load_mixed<DK>(a, an, nlo + i);
-            q += dq; rem += dr;
-            if (rem >= D) { rem -= D; q++; }
-        }
-    }
+    dc_stage_tile<DK>(a, an, stage, nlo, n_stage, D, pad);
     __syncthreads();
     double* out_re = a.out + an.out_off + m0;
     double* out_im = out_re + an.m_out;

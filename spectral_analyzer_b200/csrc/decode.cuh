@@ -18,8 +18,9 @@ enum { DK_CF32 = 0, DK_CI16 = 1, DK_C8 = 2, DK_CF64 = 3 };
 struct LoadParams {
     const void* base;     // sample 0 of the capture (device pointer, aligned to one IQ pair)
     int         swap;     // 1: big-endian data
-    uint32_t    c8_flip;  // 0x0000 for cu8, 0x8080 for ci8 (sign bit flip -> offset binary)
+    uint32_t    c8_flip;  // 0 for cu8, 0x80808080 for ci8 (sign bit flip -> offset binary)
     float       c8_off;   // 127.5/128 for cu8, 1.0 for ci8
+    float       c8_c;     // 256 + c8_off (one-FMA decode of spectrogram_mid_kernel.cuh)
 };
 
 __device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }

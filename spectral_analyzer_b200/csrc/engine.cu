@@ -158,6 +158,31 @@ int Engine::root_table(int n, int prec, const void** d_tab) {
     return SA_OK;
 }
 
+// Pass-1 twiddle pairs of spectrogram_mid_kernel: [m' < 16][r < R0] -> (W^(r m'), W^(r (m'+16))), W = W_{32 R0}
+int Engine::mid_t1_table(int n, const void** d_tab) {
+    const uint64_t key = (3ull << 40) | (uint32_t)n;
+    auto it = misc_tables.find(key);
+    if (it != misc_tables.end()) { *d_tab = it->second; return SA_OK; }
+    const int r0 = n / 1024, len = 32 * r0;
+    std::vector<double> re((size_t)32 * r0), im((size_t)32 * r0);
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int mp = 0; mp < 16; mp++)
+        for (int r = 0; r < r0; r++)
+            for (int h = 0; h < 2; h++) {
+                const int e = (r * (mp + 16 * h)) % len;
+                const double ang = -two_pi * (double)e / (double)len;
+                const size_t idx = ((size_t)mp * r0 + r) * 2 + h;
+                re[idx] = std::cos(ang);
+                im[idx] = std::sin(ang);
+            }
+    void* d = nullptr;
+    int rc = upload_pairs<float>(re, im, &d);
+    if (rc) return rc;
+    misc_tables[key] = d;
+    *d_tab = d;
+    return SA_OK;
+}
+
 // Four-step path (large_fft_kernels.cuh): frames are processed in chunks whose workspace stays L2-sized.
 int Engine::launch_spectrogram_large(const void* d_iq, uint64_t n_samples, const sa_spectrogram_params& p, int prec,
                                      const SpecArgs& base, void* d_out, cudaStream_t stream) {
@@ -231,8 +256,9 @@ int dtype_kind(int dtype) {
 void fill_load_params(LoadParams& lp, const void* base, int dtype, int big_endian) {
     lp.base = base;
     lp.swap = big_endian ? 1 : 0;
-    lp.c8_flip = (dtype == SA_CI8) ? 0x8080u : 0u;
+    lp.c8_flip = (dtype == SA_CI8) ? 0x80808080u : 0u;
     lp.c8_off = (dtype == SA_CI8) ? 1.0f : 127.5f / 128.0f;
+    lp.c8_c = 256.0f + lp.c8_off;
 }
 
 static bool is_pow2(uint64_t x) { return x && !(x & (x - 1)); }
@@ -285,9 +311,9 @@ int Engine::launch_spectrogram(const void* d_iq, uint64_t n_samples, const sa_sp
     a.db_mode = p.db_mode;
     a.eof_fill = p.eof_fill_db;
     if (p.out_kind == SA_OUT_RGBA8) {
-        a.conv = (float)(10.0 * std::log10(p.sample_rate / (double)p.nfft) + 20.0 * std::log10((double)p.nfft));
-        a.min_db = (float)p.min_db;
+        const double conv = 10.0 * std::log10(p.sample_rate / (double)p.nfft) + 20.0 * std::log10((double)p.nfft);
         a.inv_range = (float)(1.0 / (p.max_db - p.min_db));
+        a.cmap_bias = (float)(-(conv + p.min_db) / (p.max_db - p.min_db));
         a.cmap = p.colormap;
     }
     // transforms too large for one SM's shared memory take the four-step path
@@ -296,12 +322,21 @@ int Engine::launch_spectrogram(const void* d_iq, uint64_t n_samples, const sa_sp
     // TMA-staged variant (needs every frame start 16-byte aligned), else the LDG kernel
     const uint64_t iq_b = (uint64_t)sa_bytes_per_iq(p.dtype);
     const bool aligned = ((uintptr_t)d_iq % 16 == 0) && ((p.start_sample * iq_b) % 16 == 0) && ((p.hop * iq_b) % 16 == 0);
-    static const bool no_tma = getenv("SA_NO_TMA") != nullptr;      // A/B switch for the ablation in DESIGN.md
+    static const bool no_tma = getenv("SA_NO_TMA") != nullptr;      // A/B switches for the ablations in DESIGN.md
+    static const bool no_mid = getenv("SA_NO_MID") != nullptr;
     const SpecKernelInfo* k = (aligned && !no_tma) ? find_spec_kernel(prec, (int)p.nfft, dk, win, 1) : nullptr;
+    if (!k && aligned && !no_mid) k = find_spec_kernel(prec, (int)p.nfft, dk, win, 2);     // small-radix-first plan
     if (!k) k = find_spec_kernel(prec, (int)p.nfft, dk, win, 0);
     if (!k) return set_error(SA_ERR_UNSUPPORTED, "no kernel for nfft %u precision %s dtype %d", p.nfft,
                              prec == SA_PREC_F64 ? "f64" : "f32", p.dtype);
-    int rc = twiddle_table(*k, &a.twiddle);
+    int rc;
+    if (k->tma == 2) {
+        rc = mid_t1_table(k->n, &a.twiddle);
+        if (rc) return rc;
+        rc = root_table(k->n, prec, &a.aux);
+    } else {
+        rc = twiddle_table(*k, &a.twiddle);
+    }
     if (rc) return rc;
     if (win) { rc = window_table(p.window, (int)p.nfft, prec, &a.window); if (rc) return rc; }
     int bps = 0;

@@ -7,6 +7,7 @@
 
 #include "../../include/sa_engine.h"
 #include "spectrogram_tma_kernel.cuh"
+#include "spectrogram_mid_kernel.cuh"
 #include "large_fft_kernels.cuh"
 
 namespace sa {
@@ -49,6 +50,7 @@ struct Engine {
     int ensure_slot(Slot& s, size_t in_bytes, size_t out_bytes);
     int ensure_scratch(int which, size_t bytes);
     int root_table(int n, int prec, const void** d_tab);      // W_n^j, j = 0..n-1
+    int mid_t1_table(int n, const void** d_tab);              // pass-1 twiddle pairs of spectrogram_mid_kernel
     int launch_spectrogram_large(const void* d_iq, uint64_t n_samples, const sa_spectrogram_params& p, int prec,
                                  const SpecArgs& base, void* d_out, cudaStream_t stream);
     int launch_spectrogram(const void* d_iq, uint64_t n_samples, const sa_spectrogram_params& p, int prec,

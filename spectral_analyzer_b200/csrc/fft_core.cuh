@@ -213,8 +213,9 @@ __device__ __forceinline__ void radix_fft(cpx<T> (&v)[P], const T* __restrict__ 
         const cpx<T> x = v[OFF + STR * m], y = v[OFF + STR * (m + R / 2)];
         cpx<T> o0, o1;
         if constexpr (MUL == MUL_REAL) {
-            static_assert(MUL != MUL_REAL || (STR == 1 && OFF == 0), "the window is applied in pass 0 (one butterfly per thread)");
-            const cpx<T> wp = *reinterpret_cast<const cpx<T>*>(wr + 2 * m);
+            // window row in pair order: factors of register e and e + P/2 are adjacent (e = OFF + STR*m < P/2)
+            static_assert(MUL != MUL_REAL || (STR * R == P), "the window is applied in pass 0");
+            const cpx<T> wp = *reinterpret_cast<const cpx<T>*>(wr + 2 * (OFF + STR * m));
             const T wa = wp.x, wb = wp.y;
             const T tx = wa * x.x, ty = wa * x.y;
             o0 = mk2<T>(fma_t(wb, y.x, tx), fma_t(wb, y.y, ty));

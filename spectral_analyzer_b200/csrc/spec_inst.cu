@@ -1,6 +1,7 @@
 // spec_inst.cu -- explicit instantiations of spectrogram_kernel, one object file per
 // (precision, nfft) so the build parallelises: compiled with -DSA_INST_PREC=1|2 -DSA_INST_N=<nfft>.
 #include "spectrogram_tma_kernel.cuh"
+#include "spectrogram_mid_kernel.cuh"
 
 #ifndef SA_INST_PREC
 #error "compile with -DSA_INST_PREC=1|2 -DSA_INST_N=<nfft>"
@@ -26,6 +27,15 @@ struct Registrar {
         register_spec_kernel(make_spec_tma_info<float, SA_INST_N, DK_CI16, true>(1));
         register_spec_kernel(make_spec_tma_info<float, SA_INST_N, DK_C8, false>(1));
         register_spec_kernel(make_spec_tma_info<float, SA_INST_N, DK_C8, true>(1));
+#endif
+#if SA_INST_N >= 2048
+        // small-radix-first plan with 128-bit loads, taken when the frames are 16-byte aligned
+        register_spec_kernel(make_spec_mid_info<SA_INST_N, DK_CF32, false>());
+        register_spec_kernel(make_spec_mid_info<SA_INST_N, DK_CF32, true>());
+        register_spec_kernel(make_spec_mid_info<SA_INST_N, DK_CI16, false>());
+        register_spec_kernel(make_spec_mid_info<SA_INST_N, DK_CI16, true>());
+        register_spec_kernel(make_spec_mid_info<SA_INST_N, DK_C8, false>());
+        register_spec_kernel(make_spec_mid_info<SA_INST_N, DK_C8, true>());
 #endif
 #else
         // FP64 arithmetic (cf64 input, or any input when the caller asks for SA_PREC_F64);

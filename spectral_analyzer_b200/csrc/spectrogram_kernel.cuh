@@ -22,13 +22,13 @@ struct SpecArgs {
     long long   n_frames;
     const void* window;        // T[N] or nullptr
     const void* twiddle;       // cpx<T>[Geo::TW_ELEMS]
+    const void* aux;           // spectrogram_mid_kernel: cpx<T>[N] roots W_N^j
     void*       out;
     int         out_kind;
     int         db_mode;
     double      eof_fill;      // -150.0, MainController.java:996-997
     // renderSpectrogram parameters (RGBA8 only)
-    float       conv;          // 10*log10(fs/N) + 20*log10(N), :1273-1274
-    float       min_db;
+    float       cmap_bias;     // -(conv + min_db) * inv_range, conv = 10*log10(fs/N) + 20*log10(N) (:1273-1274)
     float       inv_range;     // 1/(max_db - min_db), :929
     int         cmap;
 };
@@ -77,20 +77,32 @@ __device__ __forceinline__ void bins_to_db(const cpx<T> (&v)[P], T (&db)[P]) {
 }
 
 // getColorForMagnitude (MainController.java:926-957) on float components, channels packed
-// R | G<<8 | B<<16 | A<<24 with floor(c*255 + 0.5)
+// R | G<<8 | B<<16 | A<<24.  n = clamp((dB - conv - min)/(max - min), 0, 1) is one saturating FMA
+// (cmap_bias = -(conv + min_db) * inv_range, NaN -> 0); the Heatmap ramps are saturating FMAs too:
+//   r = sat((n - 0.2)/0.3)   (0 below 0.2, the BLUE->RED ramp, 1 from 0.5 on)
+//   g = sat(2 n - 1)         (0 below 0.5, the RED->YELLOW ramp)
+//   b = n >= 0.2 ? 1 - r : 0
+// and round(c * 255) is the low mantissa byte of c * 255 + 1.5 * 2^23 (no F2I).
+template <int HEAT>
+__device__ __forceinline__ uint32_t colormap_px(const float db, const float scale, const float bias) {
+    const float n = __saturatef(__fmaf_rn(db, scale, bias));
+    constexpr float MAGIC = 12582912.0f;
+    if constexpr (HEAT) {
+        const float r = __saturatef(__fmaf_rn(n, 1.0f / 0.3f, -0.2f / 0.3f));
+        const float g = __saturatef(__fmaf_rn(n, 2.0f, -1.0f));
+        const float b = n >= 0.2f ? 1.0f - r : 0.0f;
+        const uint32_t R = __float_as_uint(__fmaf_rn(r, 255.0f, MAGIC));
+        const uint32_t G = __float_as_uint(__fmaf_rn(g, 255.0f, MAGIC));
+        const uint32_t B = __float_as_uint(__fmaf_rn(b, 255.0f, MAGIC));
+        const uint32_t rg = __byte_perm(R, G, 0x0040);          // byte0 = R, byte1 = G
+        return __byte_perm(rg, B, 0x0410) | 0xFF000000u;        // byte2 = B (byte 3 overwritten by alpha)
+    } else {
+        const uint32_t V = __float_as_uint(__fmaf_rn(n, 255.0f, MAGIC));
+        return __byte_perm(V, 0xFF000000u, 0x7000);             // R = G = B = V, A = 255
+    }
+}
 __device__ __forceinline__ uint32_t colormap_rgba(float db, const SpecArgs& a) {
-    float n = (db - a.conv - a.min_db) * a.inv_range;
-    n = fminf(fmaxf(n, 0.0f), 1.0f);           // NaN -> 0 via fmaxf
-    float r, g, b;
-    if (a.cmap == 1) {                          // Heatmap :944-953
-        if (n < 0.2f)      { r = 0.f; g = 0.f; b = 0.f; }
-        else if (n < 0.5f) { const float u = (n - 0.2f) * (1.0f / 0.3f); r = u; g = 0.f; b = 1.0f - u; }
-        else               { const float u = (n - 0.5f) * 2.0f; r = 1.f; g = u; b = 0.f; }
-    } else { r = g = b = n; }                   // Grayscale :939-942
-    const uint32_t R = (uint32_t)floorf(__fmaf_rn(r, 255.0f, 0.5f));
-    const uint32_t G = (uint32_t)floorf(__fmaf_rn(g, 255.0f, 0.5f));
-    const uint32_t B = (uint32_t)floorf(__fmaf_rn(b, 255.0f, 0.5f));
-    return R | (G << 8) | (B << 16) | 0xFF000000u;
+    return a.cmap == 1 ? colormap_px<1>(db, a.inv_range, a.cmap_bias) : colormap_px<0>(db, a.inv_range, a.cmap_bias);
 }
 
 template <int DK> __host__ __device__ constexpr int bytes_per_iq_kind() {
@@ -183,8 +195,14 @@ __device__ __forceinline__ void store_row(const SpecArgs& a, const long long fra
         for (int q = 0; q < P; q++) o[(k0 + TPF * q) & (N - 1)] = (double)db[q];
     } else {
         uint32_t* o = reinterpret_cast<uint32_t*>(a.out) + row;
+        const float sc = a.inv_range, bi = a.cmap_bias;
+        if (a.cmap == 1) {
 #pragma unroll
-        for (int q = 0; q < P; q++) o[(k0 + TPF * q) & (N - 1)] = colormap_rgba((float)db[q], a);
+            for (int q = 0; q < P; q++) o[(k0 + TPF * q) & (N - 1)] = colormap_px<1>((float)db[q], sc, bi);
+        } else {
+#pragma unroll
+            for (int q = 0; q < P; q++) o[(k0 + TPF * q) & (N - 1)] = colormap_px<0>((float)db[q], sc, bi);
+        }
     }
 }
 

@@ -1,0 +1,225 @@
+// spectrogram_mid_kernel.cuh -- FP32 spectrogram for nfft 2048 .. 16384 with 16-byte aligned frames.
+//
+// Same arithmetic contract and output as spectrogram_kernel (SpectralService.java:33-85 inside the frame
+// loop of MainController.java:980-999), but the plan puts the SMALL radix first:
+//   N = R0 * 32 * 32, R0 = N/1024 in {2, 4, 8, 16}, 32 points per thread, TPF = N/32 threads per frame.
+//   pass 0  radix R0, S = 32/R0 butterflies per thread, window folded into the first stage.  Thread t owns
+//           the S CONSECUTIVE samples S*t .. S*t+S-1 of each of the R0 slices of the frame, so the raw bytes
+//           arrive as 128-bit loads (cu8: 8 samples per load) and the thread's 32 outputs are one
+//           contiguous 256-byte block of the exchange buffer.
+//   pass 1  radix 32; twiddles W_{32 R0}^{(t mod R0) m} come from a tiny shared-memory table (R0 x 32).
+//   pass 2  radix 32; twiddles W_N^{t m} by the packed register recurrence seeded with W_N^t.
+// Against the general plan (32 * 32 * R0: twiddle pairs for two passes from global memory) this removes
+// every per-frame twiddle LDG and the scalar radix-R0 tail with its 8 distinct twiddle sets per thread.
+// Exchange buffer: one pad element per 32 (index i + i/32) keeps all three access patterns at the
+// two-wavefront minimum of 64-bit accesses.
+#pragma once
+#include "spectrogram_kernel.cuh"
+
+#ifndef SA_MID_REC1
+#define SA_MID_REC1 0
+#endif
+
+namespace sa {
+
+template <int N> struct MidGeo {
+    static constexpr int P = 32, R0 = N / 1024, S = P / R0, TPF = N / P;
+    static constexpr int CTA = TPF > 128 ? TPF : 128;
+    static constexpr int FPC = CTA / TPF;
+    static constexpr int MINB = 512 / CTA;
+    static constexpr int SM_ELEMS = N + N / 32;
+    static constexpr int WROW = P + 2;
+    static constexpr size_t EX_BYTES = (size_t)FPC * SM_ELEMS * sizeof(float2);
+    static constexpr size_t T1_BYTES = (size_t)16 * R0 * sizeof(float4);
+    static constexpr size_t WIN_BYTES = (size_t)TPF * WROW * sizeof(float);
+};
+
+__device__ __forceinline__ int mid_pad(int i) { return i + (i >> 5); }
+
+// barrier over the TPF threads of one frame (named barrier when a CTA holds several frames)
+template <int TPF, int FPC> __device__ __forceinline__ void mid_sync(const int fl) {
+    if constexpr (FPC == 1) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(fl + 1), "n"(TPF) : "memory");
+}
+
+__device__ __forceinline__ uint4 ldg_stream16(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint2 ldg_stream8(const void* p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t ldg_stream4(const void* p) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+
+// S consecutive samples starting at p -> v[OFF + i], i < S (decode of decode.cuh, same values bit for bit)
+template <int DK, int S, bool SWAP, int OFF>
+__device__ __forceinline__ void mid_load_slice(const LoadParams& lp, const char* __restrict__ p, float2 (&v)[32]) {
+    constexpr int BYTES = S * bytes_per_iq_kind<DK>();
+    static_assert(BYTES >= 4 && BYTES % 4 == 0, "slice must be whole words");
+    uint32_t w[BYTES / 4];
+    if constexpr (BYTES >= 16) {
+#pragma unroll
+        for (int i = 0; i < BYTES / 16; i++) {
+            const uint4 x = ldg_stream16(p + 16 * i);
+            w[4 * i] = x.x; w[4 * i + 1] = x.y; w[4 * i + 2] = x.z; w[4 * i + 3] = x.w;
+        }
+    } else if constexpr (BYTES == 8) {
+        const uint2 x = ldg_stream8(p);
+        w[0] = x.x; w[1] = x.y;
+    } else {
+        w[0] = ldg_stream4(p);
+    }
+#pragma unroll
+    for (int i = 0; i < S; i++) {
+        if constexpr (DK == DK_CF32) {
+            v[OFF + i] = Loader<float, DK_CF32>::template decode<SWAP>(lp, make_uint2(w[2 * i], w[2 * i + 1]));
+        } else if constexpr (DK == DK_CI16) {
+            v[OFF + i] = Loader<float, DK_CI16>::template decode<SWAP>(lp, w[i]);
+        } else {
+            // two cu8/ci8 IQ pairs per word: byte -> bits 8..15 of a 2^23-exponent float (value 2^23 + 256 u),
+            // then one exact FMA: (2^23 + 256 u) * 2^-15 - (256 + off) = u/128 - off   (off = 255/256 or 1)
+            const uint32_t x = w[i / 2] ^ lp.c8_flip;
+            const uint32_t sel = (i & 1) ? 0x7424u : 0x7404u;
+            const float a = __uint_as_float(__byte_perm(x, 0x4B000000u, sel));
+            const float b = __uint_as_float(__byte_perm(x, 0x4B000000u, sel + 0x10u));
+            v[OFF + i] = make_float2(__fmaf_rn(a, 1.0f / 32768.0f, -lp.c8_c), __fmaf_rn(b, 1.0f / 32768.0f, -lp.c8_c));
+        }
+    }
+}
+
+template <int DK, int N, bool SWAP, int M = 0>
+__device__ __forceinline__ void mid_load_frame(const LoadParams& lp, const char* __restrict__ frame_base, const int t,
+                                               float2 (&v)[32]) {
+    using G = MidGeo<N>;
+    constexpr int bps = bytes_per_iq_kind<DK>();
+    mid_load_slice<DK, G::S, SWAP, G::S * M>(lp, frame_base + ((size_t)M * (N / G::R0) + (size_t)G::S * t) * bps, v);
+    if constexpr (M + 1 < G::R0) mid_load_frame<DK, N, SWAP, M + 1>(lp, frame_base, t, v);
+}
+
+template <int N, int DK, bool WIN>
+__global__ void __launch_bounds__(MidGeo<N>::CTA, MidGeo<N>::MINB)
+spectrogram_mid_kernel(const SpecArgs a) {
+    using G = MidGeo<N>;
+    constexpr int P = 32, R0 = G::R0, S = G::S, TPF = G::TPF, FPC = G::FPC;
+    constexpr int bps = bytes_per_iq_kind<DK>();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int fl = threadIdx.x / TPF, t = threadIdx.x % TPF;
+    float2* sm = reinterpret_cast<float2*>(smem_raw) + (size_t)fl * G::SM_ELEMS;
+    TwPair<float>* t1 = reinterpret_cast<TwPair<float>*>(smem_raw + G::EX_BYTES);
+    float* wsm = reinterpret_cast<float*>(smem_raw + G::EX_BYTES + G::T1_BYTES);
+
+    // tables: pass-1 twiddle pairs [m' < 16][r < R0]; window rows in first-stage pair order
+    {
+        const float4* src = reinterpret_cast<const float4*>(a.twiddle);
+        float4* dst = reinterpret_cast<float4*>(t1);
+        for (int i = threadIdx.x; i < 16 * R0; i += G::CTA) dst[i] = __ldg(&src[i]);
+    }
+    if constexpr (WIN) {
+        const float* w = reinterpret_cast<const float*>(a.window);
+        for (int i = threadIdx.x; i < N; i += G::CTA) {
+            // sample i = m*(N/R0) + S*tt + ii  ->  register e = ii + S*m of thread tt
+            const int m = i / (N / R0), rem = i % (N / R0), tt = rem / S, ii = rem % S;
+            const int e = ii + S * m;
+            const int slot = e < P / 2 ? 2 * e : 2 * (e - P / 2) + 1;
+            wsm[tt * G::WROW + slot] = __ldg(&w[i]);
+        }
+    }
+    __syncthreads();
+    const float* win = wsm + t * G::WROW;
+    TwSeed<float> seed;
+    {
+        const float2* root = reinterpret_cast<const float2*>(a.aux);       // W_N^j
+        seed.om = __ldg(&root[t]);
+        seed.oh = __ldg(&root[(16 * t) & (N - 1)]);
+    }
+#if !SA_MID_REC1
+    const TwPair<float>* t1_row = t1 + (t % R0);
+#else
+    TwSeed<float> seed1;                         // pass-1 twiddles W_{32 R0}^{(t mod R0) m} by recurrence as well
+    {
+        const float2* root = reinterpret_cast<const float2*>(a.aux);
+        seed1.om = __ldg(&root[32 * (t % R0)]);
+        seed1.oh = __ldg(&root[(512 * (t % R0)) & (N - 1)]);
+    }
+    (void)t1;
+#endif
+
+    const long long n_blocks = (a.n_frames + FPC - 1) / FPC;
+    const int new_bytes = (int)(a.hop < N ? a.hop : N) * bps;
+    const char* base = reinterpret_cast<const char*>(a.lp.base);
+    for (long long fb = blockIdx.x; fb < n_blocks; fb += gridDim.x) {
+        const long long frame = fb * FPC + fl;
+        const long long s0 = a.start_sample + frame * a.hop;              // MainController.java:984
+        {   // pull the new samples of this slot's NEXT frame into L2 while the current one is transformed
+            const long long nf = frame + (long long)gridDim.x * FPC;
+            const long long ns_end = a.start_sample + nf * a.hop + N;
+            if (nf < a.n_frames && ns_end <= a.n_samples) {
+                const char* pf = base + ns_end * bps - new_bytes;
+                for (int off = t * 128; off < new_bytes; off += TPF * 128)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + off));
+            }
+        }
+        if (frame >= a.n_frames) continue;                                // uniform over the frame's threads
+        if (s0 + N > a.n_samples) { store_fill<float, N>(a, frame, t); continue; }   // :987, :994-998
+
+        float2 v[P];
+        if (a.lp.swap) mid_load_frame<DK, N, true>(a.lp, base + s0 * bps, t, v);
+        else           mid_load_frame<DK, N, false>(a.lp, base + s0 * bps, t, v);
+
+        // pass 0: S radix-R0 butterflies on v[i + S*m]
+        RadixAll<float, R0, S, P, WIN ? MUL_REAL : MUL_NONE, false, 0>::run(v, win, nullptr, 0, seed);
+        mid_sync<TPF, FPC>(fl);                  // the previous frame's exchange has been read back
+        {
+            float2* dst = sm + 33 * t;           // outputs j*R0 + m, j = S*t + i: the block [32 t, 32 t + 32)
+#pragma unroll
+            for (int i = 0; i < S; i++)
+#pragma unroll
+                for (int m = 0; m < R0; m++) dst[i * R0 + m] = v[i + S * m];
+        }
+        mid_sync<TPF, FPC>(fl);
+#pragma unroll
+        for (int q = 0; q < P; q++) v[q] = sm[mid_pad(t) + q * (TPF + TPF / 32)];
+
+        // pass 1: radix 32, Ns = R0
+#if SA_MID_REC1
+        radix_fft<float, 32, 1, 0, P, MUL_REC, false>(v, nullptr, nullptr, 0, seed1);
+#else
+        radix_fft<float, 32, 1, 0, P, MUL_CPX, true>(v, nullptr, t1_row, R0, seed);
+#endif
+        mid_sync<TPF, FPC>(fl);
+        {
+            float2* dst = sm + (t / R0) * (33 * R0) + (t % R0);
+#pragma unroll
+            for (int m = 0; m < 32; m++) dst[m * R0 + ((m * R0) >> 5)] = v[m];
+        }
+        mid_sync<TPF, FPC>(fl);
+#pragma unroll
+        for (int q = 0; q < P; q++) v[q] = sm[mid_pad(t) + q * (TPF + TPF / 32)];
+
+        // pass 2: radix 32, Ns = 32 R0 = TPF, twiddle W_N^(t m) by recurrence
+        radix_fft<float, 32, 1, 0, P, MUL_REC, false>(v, nullptr, nullptr, 0, seed);
+        store_row<float, N>(a, frame, t, v);
+    }
+}
+
+template <int N, int DK, bool WIN>
+SpecKernelInfo make_spec_mid_info() {
+    using G = MidGeo<N>;
+    SpecKernelInfo k;
+    k.fn = (const void*)&spectrogram_mid_kernel<N, DK, WIN>;
+    k.prec = 1; k.n = N; k.dk = DK; k.win = WIN ? 1 : 0;
+    k.cta = G::CTA; k.fpc = G::FPC; k.minb = G::MINB;
+    k.smem = G::EX_BYTES + G::T1_BYTES + (WIN ? G::WIN_BYTES : 0);
+    k.p = 32; k.np = 3; k.tma = 2;
+    k.radix[0] = G::R0; k.radix[1] = 32; k.radix[2] = 32; k.radix[3] = 1;
+    return k;
+}
+
+}  // namespace sa
