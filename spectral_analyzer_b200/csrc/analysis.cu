@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <tuple>
 
 using namespace sa;
 
@@ -53,12 +54,17 @@ const WelchKernel* find_welch(int n) {
     return nullptr;
 }
 
-const void* dc_kernel(int dk, bool wide) {
+// which: 0 staged kernel with taps from global memory, 1 staged kernel with taps in the parameter bank, 2 wide
+template <int DK> const void* dc_kernel_of(int which) {
+    return which == 2 ? (const void*)&downconvert_wide_kernel<DK>
+         : which == 1 ? (const void*)&downconvert_kernel<DK, true> : (const void*)&downconvert_kernel<DK, false>;
+}
+const void* dc_kernel(int dk, int which) {
     switch (dk) {
-        case DK_CF32: return wide ? (const void*)&downconvert_wide_kernel<DK_CF32> : (const void*)&downconvert_kernel<DK_CF32>;
-        case DK_CI16: return wide ? (const void*)&downconvert_wide_kernel<DK_CI16> : (const void*)&downconvert_kernel<DK_CI16>;
-        case DK_C8:   return wide ? (const void*)&downconvert_wide_kernel<DK_C8>   : (const void*)&downconvert_kernel<DK_C8>;
-        default:      return wide ? (const void*)&downconvert_wide_kernel<DK_CF64> : (const void*)&downconvert_kernel<DK_CF64>;
+        case DK_CF32: return dc_kernel_of<DK_CF32>(which);
+        case DK_CI16: return dc_kernel_of<DK_CI16>(which);
+        case DK_C8:   return dc_kernel_of<DK_C8>(which);
+        default:      return dc_kernel_of<DK_CF64>(which);
     }
 }
 
@@ -165,8 +171,6 @@ static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, i
     std::vector<DcAnn> plan(n_ann);
     std::vector<float> taps;
     std::map<int, int> taps_off;
-    long long max_tiles_staged = 0, max_tiles_wide = 0;
-    size_t max_smem = 0;
     for (uint32_t i = 0; i < n_ann; i++) {
         DcAnn& a = plan[i];
         const int D = anns[i].down;
@@ -188,24 +192,29 @@ static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, i
             for (int r = 0; r < D; r++) for (int p = 0; p < 8; p++) taps.push_back((float)h[D * p + r]);
         }
         a.taps_off = taps_off[D];
+        a.qmagic = D > 1 ? (unsigned)(((1ull << 32) + (unsigned long long)D - 1) / (unsigned long long)D) : 0u;
         const bool wide = a.fast ? (D > kDcStage / 8) : (D > kDcMaxDown);
         if (wide) {
             a.nb = 0;                       // marks the warp-per-output kernel
-            max_tiles_wide = std::max<long long>(max_tiles_wide, (a.m_out + 7) / 8);
         } else {
             const int nblk = std::max(8, std::min(kDcThreads, kDcStage / D));
             a.nb = a.fast ? nblk : nblk - 7;
-            max_tiles_staged = std::max<long long>(max_tiles_staged, (a.m_out + a.nb - 1) / a.nb);
-            max_smem = std::max(max_smem, dc_smem_bytes(D, a.nb, a.fast));
         }
     }
-    const size_t ann_bytes = (plan.size() * sizeof(DcAnn) + 255) & ~(size_t)255;
+    // launches are grouped by (kernel, fast, down): the device list is the plan sorted by that key
+    std::vector<uint32_t> order(n_ann);
+    for (uint32_t i = 0; i < n_ann; i++) order[i] = i;
+    auto key = [&](uint32_t i) { return std::make_tuple(plan[i].nb == 0 ? 1 : 0, plan[i].fast, plan[i].down); };
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return key(x) < key(y); });
+    std::vector<DcAnn> sorted(n_ann);
+    for (uint32_t i = 0; i < n_ann; i++) sorted[i] = plan[order[i]];
+    const size_t ann_bytes = (sorted.size() * sizeof(DcAnn) + 255) & ~(size_t)255;
     const size_t taps_bytes = (taps.size() * sizeof(float) + 255) & ~(size_t)255;
     int rc = eng->ensure_scratch(0, ann_bytes + taps_bytes);
     if (rc) return rc;
     DcAnn* d_anns = (DcAnn*)eng->scratch[0];
     float* d_taps = (float*)((char*)eng->scratch[0] + ann_bytes);
-    cudaError_t e = cudaMemcpyAsync(d_anns, plan.data(), plan.size() * sizeof(DcAnn), cudaMemcpyHostToDevice, stream);
+    cudaError_t e = cudaMemcpyAsync(d_anns, sorted.data(), sorted.size() * sizeof(DcAnn), cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice, stream);
     if (e != cudaSuccess) return cuda_fail(e, "upload annotation plan");
 
@@ -216,20 +225,44 @@ static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, i
     da.anns = d_anns;
     da.taps = d_taps;
     da.out = d_out_iq;
-    void* args[] = { &da };
-    if (max_tiles_staged > 0) {
-        const void* fn = dc_kernel(dk, false);
-        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
-        if (e != cudaSuccess) return cuda_fail(e, "downconvert smem attribute");
-        e = cudaLaunchKernel(fn, dim3((unsigned)max_tiles_staged, n_ann), dim3(kDcThreads), args, max_smem, stream);
-        if (e != cudaSuccess) return cuda_fail(e, "launch downconvert_kernel");
-        eng->launches++;
-    }
-    if (max_tiles_wide > 0) {
-        const void* fn = dc_kernel(dk, true);
-        e = cudaLaunchKernel(fn, dim3((unsigned)max_tiles_wide, n_ann), dim3(256), args, 0, stream);
-        if (e != cudaSuccess) return cuda_fail(e, "launch downconvert_wide_kernel");
-        eng->launches++;
+    static DcTapParams tp;               // guarded by the engine mutex; copied into the launch by cudaLaunchKernel
+    void* args[] = { &da, &tp };
+    for (uint32_t g0 = 0; g0 < n_ann;) {
+        uint32_t g1 = g0 + 1;
+        while (g1 < n_ann && key(order[g1]) == key(order[g0])) g1++;
+        const DcAnn& first = sorted[g0];
+        da.ann_base = (int)g0;
+        if (first.nb == 0) {              // warp-per-output kernel: all wide annotations in one launch
+            g1 = n_ann;
+            long long tiles = 0;
+            for (uint32_t i = g0; i < g1; i++) tiles = std::max<long long>(tiles, (sorted[i].m_out + 7) / 8);
+            if (tiles > 0) {
+                e = cudaLaunchKernel(dc_kernel(dk, 2), dim3((unsigned)tiles, g1 - g0), dim3(256), args, 0, stream);
+                if (e != cudaSuccess) return cuda_fail(e, "launch downconvert_wide_kernel");
+                eng->launches++;
+            }
+        } else {
+            long long tiles = 0;
+            for (uint32_t i = g0; i < g1; i++) tiles = std::max<long long>(tiles, (sorted[i].m_out + first.nb - 1) / first.nb);
+            const int D = first.down;
+            const bool ptaps = !first.fast && D <= kDcParamMaxDown;
+            if (ptaps) {
+                const float* h = taps.data() + first.taps_off;
+                tp.h_last = h[8 * D];
+                tp.down = D;
+                memcpy(tp.ht, h + 8 * D + 1, sizeof(float) * 8 * (size_t)D);
+            }
+            const size_t smem = dc_smem_bytes(D, first.nb, first.fast);
+            const void* fn = dc_kernel(dk, ptaps ? 1 : 0);
+            if (tiles > 0) {
+                e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return cuda_fail(e, "downconvert smem attribute");
+                e = cudaLaunchKernel(fn, dim3((unsigned)tiles, g1 - g0), dim3(kDcThreads), args, smem, stream);
+                if (e != cudaSuccess) return cuda_fail(e, "launch downconvert_kernel");
+                eng->launches++;
+            }
+        }
+        g0 = g1;
     }
     if (!d_out_psd) return SA_OK;
     std::vector<WelchJob> jobs(n_ann);

@@ -24,6 +24,7 @@ struct DcAnn {
     int fast;
     int nb;                          // outputs per tile of the staged kernel
     int taps_off;                    // offset (floats) of this D's tap block in the tap table
+    unsigned qmagic;                 // ceil(2^32 / down) (0 for down == 1): staged-index / down by umulhi
 };
 
 struct DcArgs {
@@ -32,6 +33,17 @@ struct DcArgs {
     const DcAnn* anns;
     const float* taps;               // per D: h[0..8D] natural order, then ht[r*8 + p] = h[D*p + r]
     double* out;                     // planar: re[M] then im[M] per annotation
+    int ann_base;                    // first annotation of this launch (launches are grouped by down)
+};
+
+// Taps of ONE decimation factor as a kernel parameter: every lane of a warp uses the same 8 taps per
+// step, so they are read through the constant bank (uniform datapath) instead of the LSU.
+constexpr int kDcParamMaxDown = 256;
+struct DcTapParams {
+    float h_last;                    // h[8D]
+    int   down;
+    int   pad_[2];
+    float ht[8 * kDcParamMaxDown];   // ht[r*8 + p] = h[D*p + r]
 };
 
 constexpr int kDcThreads = 256;
@@ -68,70 +80,63 @@ __device__ __forceinline__ float2 cmul(float2 x, float2 p) {
 }
 
 // Stages the decoded + mixed samples n = nlo .. nlo + n_stage - 1 of one tile: stage[i + (i / D) * pad].
-// Samples are fetched as 16-byte groups (2 cf32 / 4 ci16 / 8 cu8 pairs) aligned in GLOBAL memory, kDcUnroll
-// groups in flight per thread; the NCO phasor of a group's first sample comes from the exact 64-bit phase and
-// advances by one complex multiply per sample inside the group.
-constexpr int kDcUnroll = 4;
+// One sample per thread and step (coalesced), kDcUnroll independent loads in flight per thread before the
+// first is consumed; the NCO phase of every sample comes from the exact 64-bit accumulator.  Samples before
+// the annotation start (n < 0) are the zero history of the causal filter.
+constexpr int kDcUnroll = 8;
+
+__device__ __forceinline__ void sts64(uint32_t addr, float x, float y) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(x), "f"(y) : "memory");
+}
+
+template <int DK, bool SWAP, bool INTERIOR>
+__device__ __forceinline__ void dc_stage_tile_impl(const DcArgs& a, const DcAnn& an, float2* __restrict__ stage,
+                                                   const long long nlo, const int n_stage, const int pad) {
+    using LD = Loader<float, DK>;
+    using raw_t = typename LD::raw_t;
+    const raw_t* src = reinterpret_cast<const raw_t*>(a.lp.base) + (an.start_sample + nlo) + threadIdx.x;
+    // the phasor advances kDcThreads samples per step: one complex multiply by wstep (packed: P = (c, -s),
+    // Q = i P, P' = P.x W + P.y (i W)), re-seeded from the exact 64-bit phase at every batch of kDcUnroll samples
+    const float2 wstep = nco_phasor(an.phase_step * (unsigned long long)kDcThreads);
+    const pk2 W = pack2(wstep.x, wstep.y), iW = pack2(-wstep.y, wstep.x);
+    const unsigned qmagic = pad ? an.qmagic : 0u;                // i / D == umulhi(i, ceil(2^32 / D)) for i*D < 2^32
+    const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+    for (int i = threadIdx.x; i < n_stage; i += kDcThreads * kDcUnroll, src += kDcThreads * kDcUnroll) {
+        raw_t raw[kDcUnroll];
+#pragma unroll
+        for (int u = 0; u < kDcUnroll; u++) {
+            const int ii = i + u * kDcThreads;
+            raw[u] = raw_t();
+            if (ii < n_stage && (INTERIOR || nlo + ii >= 0)) raw[u] = __ldg(src + u * kDcThreads);
+        }
+        const float2 ph0 = nco_phasor(an.phase_step * (unsigned long long)(nlo + i));
+        pk2 P = pack2(ph0.x, ph0.y);
+#pragma unroll
+        for (int u = 0; u < kDcUnroll; u++) {
+            const int ii = i + u * kDcThreads;
+            const cpx<float> d = LD::template decode<SWAP>(a.lp, raw[u]);
+            float px, py;
+            unpack2(P, px, py);
+            // y = d * P = d.x (P.x, P.y) + d.y (-P.y, P.x)
+            pk2 Y = fma2(pack2(d.y, d.y), pack2(-py, px), mul2(pack2(d.x, d.x), P));
+            if (!INTERIOR && nlo + ii < 0) Y = pack2(0.f, 0.f);
+            float yx, yy;
+            unpack2(Y, yx, yy);
+            if (ii < n_stage) sts64(stage_s + 8u * (unsigned)(ii + (int)__umulhi((unsigned)ii, qmagic)), yx, yy);
+            if (u + 1 < kDcUnroll) P = fma2(pack2(py, py), iW, mul2(pack2(px, px), W));
+        }
+    }
+}
 
 template <int DK>
 __device__ __forceinline__ void dc_stage_tile(const DcArgs& a, const DcAnn& an, float2* __restrict__ stage,
-                                              const long long nlo, const int n_stage, const int D, const int pad) {
-    constexpr int bps = DK == DK_CF32 ? 8 : DK == DK_CI16 ? 4 : DK == DK_C8 ? 2 : 16;
-    constexpr int V = 16 / bps;                                  // samples per 16-byte group
-    const char* base = reinterpret_cast<const char*>(a.lp.base);
-    const long long g_lo = an.start_sample + nlo;                // global sample of staged index 0 (may be < 0)
-    // staged index of the first group is -shift: groups start on 16-byte boundaries of the capture
-    const int shift = (int)((((unsigned long long)(uintptr_t)base / bps) + (unsigned long long)(g_lo + (1LL << 40) * V)) % V);
-    const int n_groups = (n_stage + shift + V - 1) / V;
-    const float2 wstep = nco_phasor(an.phase_step);
-    for (int k0 = threadIdx.x; k0 < n_groups; k0 += kDcThreads * kDcUnroll) {
-        uint4 raw[kDcUnroll];
-        bool vec[kDcUnroll];
-#pragma unroll
-        for (int u = 0; u < kDcUnroll; u++) {
-            const int k = k0 + u * kDcThreads;
-            const long long n0 = nlo + (long long)k * V - shift;  // annotation-relative sample of the group
-            const long long g0 = an.start_sample + n0;
-            vec[u] = (k < n_groups) && (n0 >= 0) && (g0 + V <= a.n_samples);
-            raw[u] = make_uint4(0u, 0u, 0u, 0u);
-            if (vec[u]) raw[u] = __ldg(reinterpret_cast<const uint4*>(base + g0 * bps));
-        }
-#pragma unroll
-        for (int u = 0; u < kDcUnroll; u++) {
-            const int k = k0 + u * kDcThreads;
-            if (k >= n_groups) break;
-            const int i0 = k * V - shift;
-            const long long n0 = nlo + i0;
-            int q = (i0 >= 0 ? i0 : 0) / D, rem = (i0 >= 0 ? i0 : 0) - q * D;
-            float2 ph = nco_phasor(an.phase_step * (unsigned long long)n0);
-            const uint32_t w[4] = { raw[u].x, raw[u].y, raw[u].z, raw[u].w };
-#pragma unroll
-            for (int j = 0; j < V; j++) {
-                const int i = i0 + j;
-                float2 x;
-                if (vec[u]) {
-                    cpx<float> d;
-                    if (a.lp.swap) {
-                        if constexpr (DK == DK_CF32) d = Loader<float, DK>::template decode<true>(a.lp, make_uint2(w[2 * j], w[2 * j + 1]));
-                        else if constexpr (DK == DK_CI16) d = Loader<float, DK>::template decode<true>(a.lp, w[j]);
-                        else if constexpr (DK == DK_C8) d = Loader<float, DK>::template decode<true>(a.lp, (uint16_t)(w[j / 2] >> (16 * (j & 1))));
-                        else d = Loader<float, DK>::template decode<true>(a.lp, raw[u]);
-                    } else {
-                        if constexpr (DK == DK_CF32) d = Loader<float, DK>::template decode<false>(a.lp, make_uint2(w[2 * j], w[2 * j + 1]));
-                        else if constexpr (DK == DK_CI16) d = Loader<float, DK>::template decode<false>(a.lp, w[j]);
-                        else if constexpr (DK == DK_C8) d = Loader<float, DK>::template decode<false>(a.lp, (uint16_t)(w[j / 2] >> (16 * (j & 1))));
-                        else d = Loader<float, DK>::template decode<false>(a.lp, raw[u]);
-                    }
-                    x = cmul(make_float2(d.x, d.y), ph);
-                } else {
-                    // group touching the zero history or the end of the capture: per-sample path
-                    x = (i >= 0 && i < n_stage) ? load_mixed<DK>(a, an, n0 + j) : make_float2(0.f, 0.f);
-                }
-                if (i >= 0 && i < n_stage) stage[i + q * pad] = x;
-                if (i >= 0) { if (++rem == D) { rem = 0; q++; } }
-                if (j + 1 < V) ph = cmul(ph, wstep);
-            }
-        }
+                                              const long long nlo, const int n_stage, const int pad) {
+    if (nlo >= 0) {
+        if (a.lp.swap) dc_stage_tile_impl<DK, true, true>(a, an, stage, nlo, n_stage, pad);
+        else           dc_stage_tile_impl<DK, false, true>(a, an, stage, nlo, n_stage, pad);
+    } else {
+        if (a.lp.swap) dc_stage_tile_impl<DK, true, false>(a, an, stage, nlo, n_stage, pad);
+        else           dc_stage_tile_impl<DK, false, false>(a, an, stage, nlo, n_stage, pad);
     }
 }
 
@@ -139,11 +144,11 @@ __device__ __forceinline__ void dc_stage_tile(const DcArgs& a, const DcAnn& an, 
 // Samples are decoded and mixed ONCE into shared memory; thread b then forms the 8 polyphase
 // partial sums C_p[b] = sum_r h[Dp + r] y[bD - r] of input block b, and
 // z[m] = sum_p C_p[m - p] + h[8D] y[(m-8)D].
-template <int DK>
-__global__ void __launch_bounds__(kDcThreads)
-downconvert_kernel(const DcArgs a) {
+template <int DK, bool PTAPS>
+__global__ void __launch_bounds__(kDcThreads, 4)
+downconvert_kernel(const DcArgs a, const __grid_constant__ DcTapParams tp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const DcAnn an = a.anns[blockIdx.y];
+    const DcAnn an = a.anns[a.ann_base + blockIdx.y];
     const int D = an.down;
     const long long m0 = (long long)blockIdx.x * an.nb;
     if (an.nb == 0 || m0 >= an.m_out) return;      // nb == 0: handled by downconvert_wide_kernel
@@ -159,7 +164,7 @@ downconvert_kernel(const DcArgs a) {
     const float* ht = h + 8 * D + 1;
     const long long nlo = an.fast ? m0 * D : (m0 - 8) * D;
 
-    dc_stage_tile<DK>(a, an, stage, nlo, n_stage, D, pad);
+    dc_stage_tile<DK>(a, an, stage, nlo, n_stage, pad);
     __syncthreads();
     double* out_re = a.out + an.out_off + m0;
     double* out_im = out_re + an.m_out;
@@ -174,41 +179,49 @@ downconvert_kernel(const DcArgs a) {
         }
         return;
     }
+    float2* csm_t = reinterpret_cast<float2*>(csm);               // C_p[b] at csm_t[p * nblk + b]
     for (int b = threadIdx.x; b < nblk; b += kDcThreads) {
-        float2 acc[8];
+        // accumulators packed over p: ax[i] = (Re C_2i, Re C_2i+1), ay[i] likewise (FFMA2: the tap pairs
+        // arrive adjacent from the 128-bit loads, the sample is broadcast into both lanes)
+        pk2 ax[4], ay[4];
 #pragma unroll
-        for (int p = 0; p < 8; p++) acc[p] = make_float2(0.f, 0.f);
+        for (int p = 0; p < 4; p++) { ax[p] = pack2(0.f, 0.f); ay[p] = pack2(0.f, 0.f); }
         // block b (local) holds staged indices (b+1)*D - r, r = 0..D-1
         const float2* s_hi = stage + (b + 1) * (D + pad);       // r = 0 sits here (next block's slot 0)
         const float2* s_lo = stage + b * (D + pad) + D;         // r > 0: b*(D+pad) + D - r
         const float4* t4 = reinterpret_cast<const float4*>(ht);
         for (int r = 0; r < D; r++) {
             const float2 s = (r == 0) ? s_hi[0] : s_lo[-r];
-            const float4 ta = t4[2 * r], tb = t4[2 * r + 1];
-            acc[0].x = __fmaf_rn(ta.x, s.x, acc[0].x); acc[0].y = __fmaf_rn(ta.x, s.y, acc[0].y);
-            acc[1].x = __fmaf_rn(ta.y, s.x, acc[1].x); acc[1].y = __fmaf_rn(ta.y, s.y, acc[1].y);
-            acc[2].x = __fmaf_rn(ta.z, s.x, acc[2].x); acc[2].y = __fmaf_rn(ta.z, s.y, acc[2].y);
-            acc[3].x = __fmaf_rn(ta.w, s.x, acc[3].x); acc[3].y = __fmaf_rn(ta.w, s.y, acc[3].y);
-            acc[4].x = __fmaf_rn(tb.x, s.x, acc[4].x); acc[4].y = __fmaf_rn(tb.x, s.y, acc[4].y);
-            acc[5].x = __fmaf_rn(tb.y, s.x, acc[5].x); acc[5].y = __fmaf_rn(tb.y, s.y, acc[5].y);
-            acc[6].x = __fmaf_rn(tb.z, s.x, acc[6].x); acc[6].y = __fmaf_rn(tb.z, s.y, acc[6].y);
-            acc[7].x = __fmaf_rn(tb.w, s.x, acc[7].x); acc[7].y = __fmaf_rn(tb.w, s.y, acc[7].y);
+            float4 ta, tb;
+            if constexpr (PTAPS) {
+                ta = make_float4(tp.ht[8 * r], tp.ht[8 * r + 1], tp.ht[8 * r + 2], tp.ht[8 * r + 3]);
+                tb = make_float4(tp.ht[8 * r + 4], tp.ht[8 * r + 5], tp.ht[8 * r + 6], tp.ht[8 * r + 7]);
+            } else {
+                ta = __ldg(&t4[2 * r]); tb = __ldg(&t4[2 * r + 1]);
+            }
+            const pk2 sx = pack2(s.x, s.x), sy = pack2(s.y, s.y);
+            const pk2 t01 = pack2(ta.x, ta.y), t23 = pack2(ta.z, ta.w), t45 = pack2(tb.x, tb.y), t67 = pack2(tb.z, tb.w);
+            ax[0] = fma2(t01, sx, ax[0]); ay[0] = fma2(t01, sy, ay[0]);
+            ax[1] = fma2(t23, sx, ax[1]); ay[1] = fma2(t23, sy, ay[1]);
+            ax[2] = fma2(t45, sx, ax[2]); ay[2] = fma2(t45, sy, ay[2]);
+            ax[3] = fma2(t67, sx, ax[3]); ay[3] = fma2(t67, sy, ay[3]);
         }
-        float4* c = csm + 4 * b;
-        c[0] = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
-        c[1] = make_float4(acc[2].x, acc[2].y, acc[3].x, acc[3].y);
-        c[2] = make_float4(acc[4].x, acc[4].y, acc[5].x, acc[5].y);
-        c[3] = make_float4(acc[6].x, acc[6].y, acc[7].x, acc[7].y);
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            float x0, x1, y0, y1;
+            unpack2(ax[p], x0, x1); unpack2(ay[p], y0, y1);
+            csm_t[(2 * p) * nblk + b] = make_float2(x0, y0);
+            csm_t[(2 * p + 1) * nblk + b] = make_float2(x1, y1);
+        }
     }
     __syncthreads();
-    const float2* c2 = reinterpret_cast<const float2*>(csm);
     const float h_last = h[8 * D];
     for (int j = threadIdx.x; j < nbt; j += kDcThreads) {
         // output m = m0 + j uses local blocks (j + 7 - p), p = 0..7, and staged sample j*D
         const float2 s = stage[j * (D + pad)];
         float zr = h_last * s.x, zi = h_last * s.y;
 #pragma unroll
-        for (int p = 0; p < 8; p++) { const float2 c = c2[(j + 7 - p) * 8 + p]; zr += c.x; zi += c.y; }
+        for (int p = 0; p < 8; p++) { const float2 c = csm_t[p * nblk + (j + 7 - p)]; zr += c.x; zi += c.y; }
         out_re[j] = (double)zr;
         out_im[j] = (double)zi;
     }
@@ -218,7 +231,7 @@ downconvert_kernel(const DcArgs a) {
 template <int DK>
 __global__ void __launch_bounds__(256)
 downconvert_wide_kernel(const DcArgs a) {
-    const DcAnn an = a.anns[blockIdx.y];
+    const DcAnn an = a.anns[a.ann_base + blockIdx.y];
     const int lane = threadIdx.x & 31;
     const long long m = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (an.nb != 0 || m >= an.m_out) return;
