@@ -55,6 +55,10 @@ enum { SA_OUT_F32_DB = 0, SA_OUT_F64_DB = 1, SA_OUT_RGBA8 = 2 };
 enum { SA_PREC_AUTO = 0, SA_PREC_F32 = 1, SA_PREC_F64 = 2 };
 /* colormaps of getColorForMagnitude (MainController.java:939-956) */
 enum { SA_CMAP_GRAYSCALE = 0, SA_CMAP_HEATMAP = 1 };
+/* canvas reduction: NEAREST is renderSpectrogram's nearest-bin pick (MainController.java:1280) */
+enum { SA_REDUCE_NEAREST = 0, SA_REDUCE_MAX = 1, SA_REDUCE_MEAN = 2 };
+/* IqData.getInterleavedBinary formats (S/data/IqData.java:160-187) */
+enum { SA_PACK_F32 = 0, SA_PACK_I16 = 1 };
 
 /* Batched spectrogram request: replaces the per-frame loop MainController.java:982-999.
  * Frame t covers samples [start_sample + t*hop, +nfft) of the buffer; a frame that would
@@ -165,6 +169,49 @@ SA_API int32_t sa_downconvert_psd_batch_device(sa_engine* engine, const void* d_
                                                uint32_t psd_nfft, uint64_t psd_hop, int32_t psd_window,
                                                double* d_out_iq, const uint64_t* iq_offsets,
                                                double* d_out_psd_db, void* cuda_stream);
+
+/* ---- display canvas: MainController.renderSpectrogram, :1261-1291 ----
+ * Column t of the canvas_w x canvas_h RGBA8 image (row 0 = top = +fs/2, :1288) is built from the
+ * frames_per_column frames starting at frame t*frames_per_column of the spectrogram that `params`
+ * describes (params->n_frames and out_kind are ignored; hop is the frame stride, the reference uses
+ * nfft); pixel row f takes bin (int)(f / canvas_h * nfft) (:1280).  The reference is
+ * frames_per_column = 1 with SA_REDUCE_NEAREST; MAX / MEAN reduce the column's frames and the bins
+ * [bin(f), bin(f+1)) (MEAN averages linear power).  Colour mapping as SA_OUT_RGBA8.  Only the
+ * canvas crosses PCIe on the way back. */
+SA_API int32_t sa_render_canvas(sa_engine* engine, const void* iq, uint64_t iq_bytes,
+                                const sa_spectrogram_params* params, uint32_t canvas_w, uint32_t canvas_h,
+                                uint64_t frames_per_column, int32_t reduce, void* out_rgba);
+SA_API int32_t sa_render_canvas_device(sa_engine* engine, const void* d_iq, uint64_t iq_bytes,
+                                       const sa_spectrogram_params* params, uint32_t canvas_w,
+                                       uint32_t canvas_h, uint64_t frames_per_column, int32_t reduce,
+                                       void* d_out_rgba, void* cuda_stream);
+
+/* ---- downconverter output epilogues ----
+ * sa_iq_pack: IqData.getInterleavedBinary (S/data/IqData.java:160-187): interleaved little-endian
+ * float32 ((float) x) or int16 ((short)(32767 * x), Java narrowing: truncate, saturate to int, keep
+ * the low 16 bits; NaN -> 0).  re/im: rows of the Java double[2][n]; out: n*8 or n*4 bytes. */
+SA_API int32_t sa_iq_pack(sa_engine* engine, const double* re, const double* im, uint64_t n,
+                          int32_t format, void* out);
+/* sa_analysis_series: AnalysisDialogController.updateMagnitudeChart / updateFrequencyChart
+ * (S/controllers/AnalysisDialogController.java:219-290).  out_mag_db[i] = 20 log10(EMA_i(hypot)),
+ * i < n (non-finite values are what the Java loop skips); out_freq[i] = EMA_i(wrapped phase
+ * difference / 2 pi * fs) + center_freq for 1 <= i < n (out_freq[0] = NaN, the loop starts at 1).
+ * Either output may be NULL. */
+SA_API int32_t sa_analysis_series(sa_engine* engine, const double* re, const double* im, uint64_t n,
+                                  double sample_rate, double alpha_mag, double alpha_freq,
+                                  double center_freq, double* out_mag_db, double* out_freq);
+/* Batched device forms on the planar rows sa_downconvert_psd_batch_device wrote: signal a has its
+ * re block at d_rows + row_offsets[a], im block lengths[a] doubles later; results start at element
+ * out_offsets[a] of the output(s) (elements = IQ pairs for the packer, doubles for the series). */
+SA_API int32_t sa_iq_pack_batch_device(sa_engine* engine, const double* d_rows, const uint64_t* row_offsets,
+                                       const uint64_t* lengths, const uint64_t* out_offsets, uint32_t n_sig,
+                                       int32_t format, void* d_out, void* cuda_stream);
+SA_API int32_t sa_analysis_series_batch_device(sa_engine* engine, const double* d_rows,
+                                               const uint64_t* row_offsets, const uint64_t* lengths,
+                                               const uint64_t* out_offsets, uint32_t n_sig,
+                                               double sample_rate, double alpha_mag, double alpha_freq,
+                                               double center_freq, double* d_out_mag_db,
+                                               double* d_out_freq, void* cuda_stream);
 
 #ifdef __cplusplus
 }

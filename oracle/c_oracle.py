@@ -49,6 +49,8 @@ def lib():
         L.ora_downconvert.argtypes = [u8p, C.c_uint64, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_double,
                                       C.c_int, C.c_int, dp, dp, C.POINTER(C.c_uint64)]
         L.ora_psd_welch.argtypes = [dp, dp, C.c_uint64, C.c_double, C.c_int, C.c_uint64, C.c_int, dp, dp]
+        L.ora_iq_pack.argtypes = [dp, dp, C.c_uint64, C.c_int, u8p]
+        L.ora_analysis_series.argtypes = [dp, dp, C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_double, dp, dp]
         L.ora_window.argtypes = [C.c_int, C.c_int, dp]
         L.ora_fft.argtypes = [dp, dp, C.c_int]
         _LIB = L
@@ -142,6 +144,26 @@ def psd_welch(iq, fs, nfft, hop=None, window="hann"):
     _chk(lib().ora_psd_welch(_dp(re), _dp(im), re.size, fs, nfft, hop, WINDOWS[window], _dp(f), _dp(d)),
          "psd_welch")
     return np.stack([f, d])
+
+
+def iq_pack(iq, fmt):
+    """IqData.getInterleavedBinary (IqData.java:160-187)."""
+    re = np.ascontiguousarray(iq[0], np.float64)
+    im = np.ascontiguousarray(iq[1], np.float64)
+    code = {"float32": 0, "int16": 1}[fmt.lower()]
+    out = np.empty(re.size * (8 if code == 0 else 4), np.uint8)
+    _chk(lib().ora_iq_pack(_dp(re), _dp(im), re.size, code, out.ctypes.data_as(C.POINTER(C.c_uint8))), "iq_pack")
+    return out.tobytes()
+
+
+def analysis_series(iq, fs, alpha_mag=1.0, alpha_freq=1.0, center_freq=0.0):
+    """updateMagnitudeChart / updateFrequencyChart (AnalysisDialogController.java:219-290)."""
+    re = np.ascontiguousarray(iq[0], np.float64)
+    im = np.ascontiguousarray(iq[1], np.float64)
+    mag, frq = np.empty(re.size, np.float64), np.empty(re.size, np.float64)
+    _chk(lib().ora_analysis_series(_dp(re), _dp(im), re.size, fs, alpha_mag, alpha_freq, center_freq, _dp(mag),
+                                   _dp(frq)), "analysis_series")
+    return mag, frq
 
 
 def fft(x):

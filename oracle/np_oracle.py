@@ -129,3 +129,43 @@ def psd_welch(iq, fs, nfft, hop=None, win="hann"):
     f, p = sps.welch(x, fs=fs, window=window(win, nfft), nperseg=nfft, noverlap=nfft - hop, nfft=nfft,
                      detrend=False, return_onesided=False, scaling="density")
     return np.stack([np.fft.fftshift(f), np.fft.fftshift(10 * np.log10(p + 1e-30))])
+
+
+def iq_pack(iq, fmt):
+    """IqData.getInterleavedBinary (IqData.java:160-187), independent numpy restatement."""
+    re, im = np.asarray(iq[0], np.float64), np.asarray(iq[1], np.float64)
+    if fmt.lower() == "float32":
+        out = np.empty(2 * re.size, "<f4")
+        out[0::2], out[1::2] = re.astype(np.float32), im.astype(np.float32)
+        return out.tobytes()
+    if fmt.lower() == "int16":
+        def narrow(v):
+            v = 32767 * v
+            i = np.where(np.isnan(v), 0.0, np.clip(np.trunc(v), -2147483648.0, 2147483647.0)).astype(np.int64)
+            return (i & 0xFFFF).astype(np.uint16)
+        out = np.empty(2 * re.size, "<u2")
+        out[0::2], out[1::2] = narrow(re), narrow(im)
+        return out.tobytes()
+    raise ValueError("Unsupported binary format: " + fmt)
+
+
+def analysis_series(iq, fs, alpha_mag=1.0, alpha_freq=1.0, center_freq=0.0):
+    """updateMagnitudeChart / updateFrequencyChart (AnalysisDialogController.java:219-290); the EMA
+    is evaluated with scipy.signal.lfilter (same recurrence, different summation order)."""
+    from scipy.signal import lfilter
+    re, im = np.asarray(iq[0], np.float64), np.asarray(iq[1], np.float64)
+
+    def ema(x, alpha):
+        if x.size == 0:
+            return x
+        y, _ = lfilter([alpha], [1.0, -(1.0 - alpha)], x[1:], zi=[(1.0 - alpha) * x[0]])
+        return np.concatenate([x[:1], y])
+    with np.errstate(divide="ignore"):
+        mag = 20 * np.log10(ema(np.hypot(re, im), alpha_mag))
+    ph = np.arctan2(im, re)
+    d = ph[1:] - ph[:-1]
+    d = np.where(d > np.pi, d - 2 * np.pi, np.where(d < -np.pi, d + 2 * np.pi, d))
+    frq = np.full(re.size, np.nan)
+    frq[1:] = ema(d / (2 * np.pi) * fs, alpha_freq) + center_freq
+    return mag, frq
+

@@ -384,3 +384,66 @@ int ora_psd_welch(const double* re, const double* im, uint64_t n, double fs, int
     plan_free(&plan); free(w); free(a); free(b); free(acc);
     return 0;
 }
+
+/* ---------- rows next to the hot path ---------- */
+
+/* Java narrowing (short)(double): JLS 5.1.3 double -> int (NaN -> 0, saturate, else truncate
+ * toward zero), then int -> short keeps the low 16 bits. */
+static int16_t java_double_to_short(double v) {
+    int32_t i;
+    if (v != v) i = 0;
+    else if (v >= 2147483647.0) i = INT32_MAX;
+    else if (v <= -2147483648.0) i = INT32_MIN;
+    else i = (int32_t)v;
+    return (int16_t)(uint16_t)((uint32_t)i & 0xFFFFu);
+}
+
+/* IqData.getInterleavedBinary (IqData.java:160-187): format 0 "float32": putFloat((float) I),
+ * putFloat((float) Q), little-endian (:163-171); format 1 "int16": putShort((short)(32767 * I)), ... (:173-183). */
+int ora_iq_pack(const double* re, const double* im, uint64_t n, int format, uint8_t* out) {
+    if (format != 0 && format != 1) return -1;                  /* IllegalArgumentException :185-186 */
+    for (uint64_t i = 0; i < n; i++) {
+        if (format == 0) {
+            float a = (float)re[i], b = (float)im[i];
+            uint32_t ua, ub;
+            memcpy(&ua, &a, 4); memcpy(&ub, &b, 4);
+            for (int k = 0; k < 4; k++) { out[8 * i + k] = (uint8_t)(ua >> (8 * k)); out[8 * i + 4 + k] = (uint8_t)(ub >> (8 * k)); }
+        } else {
+            uint16_t a = (uint16_t)java_double_to_short(32767 * re[i]);
+            uint16_t b = (uint16_t)java_double_to_short(32767 * im[i]);
+            out[4 * i] = (uint8_t)a; out[4 * i + 1] = (uint8_t)(a >> 8);
+            out[4 * i + 2] = (uint8_t)b; out[4 * i + 3] = (uint8_t)(b >> 8);
+        }
+    }
+    return 0;
+}
+
+/* AnalysisDialogController.updateMagnitudeChart (:219-251) and updateFrequencyChart (:256-290).
+ * out_mag_db[i] = 20*log10(valueOld_i) (the chart skips non-finite values; they are kept here),
+ * out_freq[i] = vOld_i + center_freq for i >= 1, out_freq[0] = NaN (the loop starts at 1). */
+int ora_analysis_series(const double* re, const double* im, uint64_t n, double fs, double alpha_mag,
+                        double alpha_freq, double center_freq, double* out_mag_db, double* out_freq) {
+    double value_old = 0.0;
+    if (out_mag_db)
+        for (uint64_t i = 0; i < n; i++) {
+            double abs_value = hypot(re[i], im[i]);                                  /* :231 */
+            if (i == 0) value_old = abs_value;                                         /* :234-235 */
+            else value_old = alpha_mag * abs_value + (1 - alpha_mag) * value_old;      /* :237 */
+            out_mag_db[i] = 20 * log10(value_old);                                     /* :240 */
+        }
+    if (out_freq) {
+        double v_old = 0.0;
+        if (n > 0) out_freq[0] = NAN;
+        for (uint64_t i = 1; i < n; i++) {
+            double phase1 = atan2(im[i], re[i]);                                       /* :264 */
+            double phase2 = atan2(im[i - 1], re[i - 1]);                               /* :265 */
+            double d = phase1 - phase2;
+            if (d > M_PI) d -= 2 * M_PI; else if (d < -M_PI) d += 2 * M_PI;            /* :268-273 */
+            double inst = (d / (2 * M_PI)) * fs;                                       /* :275 */
+            if (i == 1) v_old = inst; else v_old = (alpha_freq * inst) + (1 - alpha_freq) * v_old;   /* :276-280 */
+            out_freq[i] = v_old + center_freq;                                         /* :281 */
+        }
+    }
+    return 0;
+}
+

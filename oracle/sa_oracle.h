@@ -92,6 +92,12 @@ int ora_downconvert(const uint8_t* buf, uint64_t cap_bytes, int dtype, int big_e
 int ora_psd_welch(const double* re, const double* im, uint64_t n, double fs, int nfft,
                   uint64_t hop, int window_id, double* out_freq, double* out_db);
 
+/* IqData.getInterleavedBinary (S/data/IqData.java:160-187): format 0 float32, 1 int16, little-endian. */
+int ora_iq_pack(const double* re, const double* im, uint64_t n, int format, uint8_t* out);
+/* AnalysisDialogController.updateMagnitudeChart / updateFrequencyChart (:219-290). */
+int ora_analysis_series(const double* re, const double* im, uint64_t n, double fs, double alpha_mag,
+                        double alpha_freq, double center_freq, double* out_mag_db, double* out_freq);
+
 /* in-place forward DFT, unnormalised, power-of-two n (radix-2, FP64) */
 int ora_fft(double* re, double* im, int n);
 

@@ -4,6 +4,6 @@ CUDA behind the C-ABI of include/sa_engine.h); this package is the Python mirror
 reference's service interface on top of it.
 """
 from .services import (Engine, EngineError, SpectralService, ExtractDownConvertService,  # noqa: F401
-                       AsyncExtractDownConvertService, PowerSpectralDensity)
+                       AsyncExtractDownConvertService, PowerSpectralDensity, IqData)
 
 __version__ = "0.1.0"

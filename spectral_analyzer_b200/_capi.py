@@ -18,6 +18,8 @@ DB_MAG_1E10, DB_POWER = 0, 1
 OUT_F32_DB, OUT_F64_DB, OUT_RGBA8 = 0, 1, 2
 PREC_AUTO, PREC_F32, PREC_F64 = 0, 1, 2
 CMAP = {"Grayscale": 0, "Heatmap": 1}
+REDUCE = {"nearest": 0, "max": 1, "mean": 2}
+PACK = {"float32": 0, "int16": 1}
 
 
 class SpectrogramParams(C.Structure):
@@ -77,6 +79,13 @@ def lib():
                                            dp, C.POINTER(u64), dp]
     L.sa_downconvert_psd_batch_device.argtypes = [vp, vp, u64, i32, i32, dbl, C.POINTER(Annotation), u32, u32, u64,
                                                   i32, vp, C.POINTER(u64), vp, vp]
+    L.sa_render_canvas.argtypes = [vp, vp, u64, C.POINTER(SpectrogramParams), u32, u32, u64, i32, vp]
+    L.sa_render_canvas_device.argtypes = [vp, vp, u64, C.POINTER(SpectrogramParams), u32, u32, u64, i32, vp, vp]
+    L.sa_iq_pack.argtypes = [vp, dp, dp, u64, i32, vp]
+    L.sa_analysis_series.argtypes = [vp, dp, dp, u64, dbl, dbl, dbl, dbl, dp, dp]
+    pu64 = C.POINTER(u64)
+    L.sa_iq_pack_batch_device.argtypes = [vp, vp, pu64, pu64, pu64, u32, i32, vp, vp]
+    L.sa_analysis_series_batch_device.argtypes = [vp, vp, pu64, pu64, pu64, u32, dbl, dbl, dbl, dbl, vp, vp, vp]
     _lib = L
     return L
 

@@ -266,7 +266,7 @@ static bool is_pow2(uint64_t x) { return x && !(x & (x - 1)); }
 static size_t out_elem_bytes(int out_kind) { return out_kind == SA_OUT_F64_DB ? 8 : 4; }
 
 // Validates a request and resolves precision; returns SA_OK or an error.
-static int check_spec_params(const sa_spectrogram_params* p, int* prec_out) {
+int check_spec_params(const sa_spectrogram_params* p, int* prec_out) {
     if (!p) return set_error(SA_ERR_INVALID_ARG, "params is NULL");
     if (p->struct_size != sizeof(sa_spectrogram_params))
         return set_error(SA_ERR_INVALID_ARG, "params.struct_size %u != %zu", p->struct_size, sizeof(sa_spectrogram_params));
@@ -432,7 +432,7 @@ Engine::~Engine() {
         if (slots[i].stream) cudaStreamDestroy(slots[i].stream);
     }
     for (auto& r : registered) cudaHostUnregister(const_cast<void*>(r));
-    for (int i = 0; i < 3; i++) if (scratch[i]) cudaFree(scratch[i]);
+    for (int i = 0; i < kScratch; i++) if (scratch[i]) cudaFree(scratch[i]);
 }
 
 int Engine::ensure_scratch(int which, size_t bytes) {

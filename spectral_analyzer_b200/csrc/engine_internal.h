@@ -18,9 +18,11 @@ const SpecKernelInfo* find_spec_kernel(int prec, int n, int dk, int win, int tma
 const LargeKernelInfo* find_large_kernel(int prec, int n, int dk, int win);
 void host_window(int window_id, int n, std::vector<double>& w);
 int dtype_kind(int dtype);
+int check_spec_params(const sa_spectrogram_params* p, int* prec_out);   // validates, resolves precision
 void fill_load_params(LoadParams& lp, const void* base, int dtype, int big_endian);
 
 constexpr int kSlots = 3;
+constexpr int kScratch = 5;
 
 struct Slot {
     cudaStream_t stream = nullptr;
@@ -40,8 +42,10 @@ struct Engine {
     std::map<const void*, int> occupancy;            // kernel -> resident CTAs per SM
     std::vector<const void*> registered;             // cudaHostRegister'ed ranges
     Slot slots[kSlots];
-    void* scratch[3] = {nullptr, nullptr, nullptr};  // device workspaces: [0] annotation plan + taps,
-    size_t scratch_cap[3] = {0, 0, 0};               // [1] Welch plan + partial spectra, [2] four-step FFT
+    // device workspaces: [0] annotation plan + taps, [1] Welch plan + partial spectra, [2] four-step FFT,
+    // [3] canvas / canvas dB rows, [4] signal lists of the packer / series kernels
+    void* scratch[kScratch] = {};
+    size_t scratch_cap[kScratch] = {};
 
     ~Engine();
     int twiddle_table(const SpecKernelInfo& k, const void** d_tab);

@@ -161,6 +161,46 @@ class Engine:
         return iq_list, out_psd
 
 
+    # ---- rows next to the hot path ----
+    def render_canvas(self, buffer, datatype, nfft, canvas_w, canvas_h, sample_rate, hop=None, window="rect",
+                      start_sample=0, frames_per_column=1, reduce="nearest", colormap="Grayscale", min_db=-160.0,
+                      max_db=-30.0, **kw):
+        """MainController.renderSpectrogram (:1261-1291) on the GPU: uint8 [canvas_h, canvas_w, 4], row 0 = top.
+        frames_per_column=1 / reduce='nearest' is the reference; 'max' / 'mean' pool frames x bins per pixel."""
+        _, ptr, nbytes = _host_view(buffer)
+        p = self.make_params(datatype, nfft, hop, window, 0, start_sample, colormap=colormap, sample_rate=sample_rate,
+                             min_db=min_db, max_db=max_db, **kw)
+        out = np.empty((canvas_h, canvas_w, 4), np.uint8)
+        _capi.check(_capi.lib().sa_render_canvas(self._h, ptr, nbytes, C.byref(p), canvas_w, canvas_h,
+                                                 frames_per_column, _capi.REDUCE[reduce], out.ctypes.data))
+        return out
+
+    def iq_pack(self, iq, fmt):
+        """IqData.getInterleavedBinary (IqData.java:160-187): bytes of interleaved LE float32 / int16."""
+        if fmt.lower() not in _capi.PACK:
+            raise ValueError("Unsupported binary format: " + fmt)       # IllegalArgumentException, :185-186
+        re = np.ascontiguousarray(iq[0], np.float64)
+        im = np.ascontiguousarray(iq[1], np.float64)
+        code = _capi.PACK[fmt.lower()]
+        out = np.empty(re.size * (8 if code == 0 else 4), np.uint8)
+        dp = C.POINTER(C.c_double)
+        _capi.check(_capi.lib().sa_iq_pack(self._h, re.ctypes.data_as(dp), im.ctypes.data_as(dp), re.size, code,
+                                           out.ctypes.data))
+        return out.tobytes()
+
+    def analysis_series(self, iq, sample_rate, alpha_mag=1.0, alpha_freq=1.0, center_freq=0.0):
+        """updateMagnitudeChart / updateFrequencyChart (AnalysisDialogController.java:219-290):
+        returns (mag_db[n], inst_freq[n]) with inst_freq[0] = NaN (the Java loop starts at i = 1)."""
+        re = np.ascontiguousarray(iq[0], np.float64)
+        im = np.ascontiguousarray(iq[1], np.float64)
+        mag, frq = np.empty(re.size, np.float64), np.empty(re.size, np.float64)
+        dp = C.POINTER(C.c_double)
+        _capi.check(_capi.lib().sa_analysis_series(self._h, re.ctypes.data_as(dp), im.ctypes.data_as(dp), re.size,
+                                                   sample_rate, alpha_mag, alpha_freq, center_freq,
+                                                   mag.ctypes.data_as(dp), frq.ctypes.data_as(dp)))
+        return mag, frq
+
+
 _default_engine = None
 
 
@@ -234,3 +274,19 @@ class PowerSpectralDensity:
         centred on 0 Hz, row 1 level in dB/Hz."""
         eng = cls.engine or default_engine()
         return eng.psd_welch(data, sampleRate, nfft)
+
+
+class IqData:
+    """S/data/IqData.java: container of the downconverted double[2][N]; only the binary packers
+    (getInterleavedBinary, :160-187, and getDataBuffer, :198-208) are mirrored -- they run on the GPU."""
+
+    def __init__(self, iqSamples, engine=None):
+        self.iqSamples = np.array(iqSamples, np.float64)          # defensive deep copy, IqData.java:49-52
+        self.engine = engine or default_engine()
+
+    def getInterleavedBinary(self, format):
+        return self.engine.iq_pack(self.iqSamples, format)
+
+    def getDataBuffer(self):
+        return {"IQ_BUFFER_FLOAT32": self.getInterleavedBinary("float32"),
+                "IQ_BUFFER_INT16": self.getInterleavedBinary("int16")}

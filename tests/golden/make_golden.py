@@ -42,6 +42,14 @@ def main():
     dcf = no.downconvert(raw, "cf32_le", 100, 36000, 0.125, 4, True)
     psd = no.psd_welch(dc, 1e6 / 4, 2048)
     np.savez_compressed(os.path.join(HERE, "analysis_mini.npz"), raw=raw, dc=dc, dcf=dcf, psd=psd)
+    # 5. IqData packers and analysis series on the decimated signal above, plus edge values
+    edge = np.array([[0.0, 1.0, -1.0, 0.999985, 1.00002, -1.00004, 3.2, -7.9, 1e12, -1e12, np.nan, 1e-9],
+                     [0.5, -0.5, 2.0 ** -15, -(2.0 ** -15), 0.99999, -0.99999, 65536.0, -65536.5, np.inf, -np.inf, 0.25, -0.0]])
+    mag, frq = no.analysis_series(dc, 250e3, 0.2, 0.05, 915e6)
+    np.savez_compressed(os.path.join(HERE, "iqdata_mini.npz"), edge=edge,
+                        edge_f32=np.frombuffer(no.iq_pack(edge, "float32"), np.uint8),
+                        edge_i16=np.frombuffer(no.iq_pack(edge, "int16"), np.uint8),
+                        dc_i16=np.frombuffer(no.iq_pack(dc, "int16"), np.uint8), mag=mag, frq=frq)
     print("golden fixtures written to", HERE)
 
 

@@ -162,3 +162,42 @@ def test_downconvert_tone_to_dc():
     out = co.downconvert(synth.encode(x, "cf64_le"), "cf64_le", 0, n, 0.2, 16, False)
     z = out[0] + 1j * out[1]
     assert np.abs(z[20:] - 0.5).max() < 1e-9
+
+
+# ---- rows next to the hot path: IqData packers, analysis series ----
+def test_iq_pack_known_answers_and_golden():
+    """IqData.getInterleavedBinary (IqData.java:160-187): Java narrowing (short)(32767*x)."""
+    iq = np.array([[1.0, -1.0, 0.5, 1.00002, 3.2, 1e12, np.nan], [0.0, 2.0 ** -15, -0.5, -1.00004, -7.9, -1e12, -0.0]])
+    i16 = np.frombuffer(co.iq_pack(iq, "int16"), "<i2").reshape(-1, 2)
+    # 32767*1.00002 = 32767.65 -> 32767 ; 32767*3.2 = 104854.4 -> low 16 bits of 104854 = -26218 (wraps, no clipping);
+    # 1e12 saturates the int conversion (0x7fffffff -> low 16 bits = -1); NaN -> 0
+    assert i16[:, 0].tolist() == [32767, -32767, 16383, 32767, 104854 - 131072, -1, 0]
+    assert i16[:, 1].tolist() == [0, 0, -16383, -32768, -258859 + 262144, 0, 0]
+    f32 = np.frombuffer(co.iq_pack(iq, "float32"), "<f4").reshape(-1, 2)
+    assert np.array_equal(f32[:5, 0], iq[0, :5].astype(np.float32)) and np.isnan(f32[6, 0])
+    g = np.load(os.path.join(GOLD, "iqdata_mini.npz"))
+    for fmt, key in (("float32", "edge_f32"), ("int16", "edge_i16")):
+        assert co.iq_pack(g["edge"], fmt) == no.iq_pack(g["edge"], fmt) == g[key].tobytes()
+
+
+def test_analysis_series_known_answers_and_golden():
+    """updateMagnitudeChart / updateFrequencyChart (AnalysisDialogController.java:219-290)."""
+    n, fs, f0 = 4000, 1.0e6, 12.5e3
+    z = 0.25 * np.exp(2j * np.pi * f0 / fs * np.arange(n))
+    mag, frq = co.analysis_series(np.stack([z.real, z.imag]), fs, 0.3, 0.1, 100e6)
+    assert np.abs(mag - 20 * np.log10(0.25)).max() < 1e-9            # constant envelope: the EMA is the envelope
+    assert np.isnan(frq[0]) and np.abs(frq[1:] - (100e6 + f0)).max() < 1e-3
+    # phase wrap: a tone at -0.45 fs steps the phase by -0.9 pi; +0.55 fs would alias to the same value
+    z = np.exp(-2j * np.pi * 0.45 * np.arange(64))
+    _, frq = co.analysis_series(np.stack([z.real, z.imag]), 2.0, 1.0, 1.0, 0.0)
+    assert np.abs(frq[1:] + 0.9).max() < 1e-9
+    # alpha = 1 -> no smoothing; first value initialises the average (:234-235, :276-277)
+    x = np.array([[3.0, 0.0, 0.0], [4.0, 1.0, 0.0]])
+    mag, _ = co.analysis_series(x, 1.0, 0.5, 1.0, 0.0)
+    assert np.allclose(mag[:2], 20 * np.log10([5.0, 3.0])) and np.isclose(mag[2], 20 * np.log10(1.5))
+    g = np.load(os.path.join(GOLD, "iqdata_mini.npz"))
+    a = np.load(os.path.join(GOLD, "analysis_mini.npz"))
+    cm, cf = co.analysis_series(a["dc"], 250e3, 0.2, 0.05, 915e6)
+    nm, nf = no.analysis_series(a["dc"], 250e3, 0.2, 0.05, 915e6)
+    assert np.abs(cm - g["mag"]).max() < 1e-10 and np.abs(cf[1:] - g["frq"][1:]).max() < 1e-5
+    assert np.abs(cm - nm).max() < 1e-10 and np.abs(cf[1:] - nf[1:]).max() < 1e-5
