@@ -112,4 +112,42 @@ struct PowerSpectralDensity {
     }
 };
 
+// MainController.renderSpectrogram (S/controllers/MainController.java:1261-1291) for a canvasW x canvasH view:
+// RGBA8 [canvasH][canvasW], row 0 = top.  framesPerColumn = 1 / SA_REDUCE_NEAREST is the reference.
+struct SpectrogramRenderer {
+    static std::vector<uint8_t> renderSpectrogram(Engine& e, const MappedByteBuffer& buffer, int64_t currentSampleOffset,
+                                                  int canvasW, int canvasH, int fftSize, const std::string& datatype,
+                                                  double sampleRate, double minDb, double maxDb, int colormap,
+                                                  int64_t framesPerColumn = 1, int reduce = SA_REDUCE_NEAREST) {
+        const Datatype dt(datatype);
+        sa_spectrogram_params p;
+        sa_spectrogram_params_init(&p);
+        p.dtype = dt.dtype; p.big_endian = dt.big_endian; p.nfft = (uint32_t)fftSize; p.hop = (uint64_t)fftSize;
+        p.start_sample = (uint64_t)currentSampleOffset; p.sample_rate = sampleRate; p.min_db = minDb; p.max_db = maxDb;
+        p.colormap = colormap;
+        std::vector<uint8_t> out((size_t)canvasW * canvasH * 4);
+        sa_check(sa_render_canvas(e.handle(), buffer.data, buffer.capacity, &p, (uint32_t)canvasW, (uint32_t)canvasH,
+                                  (uint64_t)framesPerColumn, reduce, out.data()));
+        return out;
+    }
+};
+
+// S/data/IqData.java: the binary packers of the downconverted double[2][N] (getInterleavedBinary :160-187)
+class IqData {
+public:
+    IqData(Engine& e, std::vector<std::vector<double>> iqSamples) : e_(e), iq_(std::move(iqSamples)) {}
+    std::vector<uint8_t> getInterleavedBinary(const std::string& format) const {
+        int code;
+        if (format == "float32" || format == "FLOAT32") code = SA_PACK_F32;
+        else if (format == "int16" || format == "INT16") code = SA_PACK_I16;
+        else throw std::invalid_argument("Unsupported binary format: " + format);
+        std::vector<uint8_t> out(iq_[0].size() * (code == SA_PACK_F32 ? 8 : 4));
+        sa_check(sa_iq_pack(e_.handle(), iq_[0].data(), iq_[1].data(), iq_[0].size(), code, out.data()));
+        return out;
+    }
+private:
+    Engine& e_;
+    std::vector<std::vector<double>> iq_;
+};
+
 }  // namespace spectral_analyzer

@@ -57,6 +57,17 @@ public final class NativeSpectralEngine implements AutoCloseable {
             FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, JAVA_DOUBLE, JAVA_INT, JAVA_LONG,
                     JAVA_INT, ADDRESS, ADDRESS));
 
+    // int32 sa_render_canvas(engine, iq, iq_bytes, params, canvas_w, canvas_h, frames_per_column, reduce, out_rgba)
+    private static final MethodHandle RENDER_CANVAS = fn("sa_render_canvas",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS, JAVA_INT, JAVA_INT, JAVA_LONG, JAVA_INT, ADDRESS));
+    // int32 sa_iq_pack(engine, re, im, n, format, out)
+    private static final MethodHandle IQ_PACK = fn("sa_iq_pack",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, JAVA_INT, ADDRESS));
+    // int32 sa_analysis_series(engine, re, im, n, fs, alpha_mag, alpha_freq, center_freq, out_mag_db, out_freq)
+    private static final MethodHandle ANALYSIS_SERIES = fn("sa_analysis_series",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, JAVA_DOUBLE, JAVA_DOUBLE, JAVA_DOUBLE,
+                    JAVA_DOUBLE, ADDRESS, ADDRESS));
+
     /** struct sa_spectrogram_params (include/sa_engine.h), natural alignment, 96 bytes. */
     static final StructLayout PARAMS = MemoryLayout.structLayout(
             JAVA_INT.withName("struct_size"), JAVA_INT.withName("dtype"), JAVA_INT.withName("big_endian"),
@@ -154,6 +165,63 @@ public final class NativeSpectralEngine implements AutoCloseable {
             MemorySegment f = a.allocate(JAVA_DOUBLE, nfft), db = a.allocate(JAVA_DOUBLE, nfft);
             check((int) PSD_WELCH.invoke(engine, re, im, (long) data[0].length, fs, nfft, 0L, 1 /* SA_WIN_HANN */, f, db));
             return new double[][] { f.toArray(JAVA_DOUBLE), db.toArray(JAVA_DOUBLE) };
+        }
+    }
+
+    /**
+     * MainController.renderSpectrogram (MainController.java:1261-1291) on the GPU: ARGB-ready RGBA8 bytes,
+     * canvasH rows of canvasW pixels, row 0 = top.  The caller blits them with PixelWriter.setPixels.
+     */
+    public byte[] renderSpectrogram(MappedByteBuffer buffer, long currentSampleOffset, int canvasW, int canvasH,
+                                    int fftSize, String datatype, double sampleRate, double minDb, double maxDb,
+                                    int colormap) throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            int[] dt = parse(a, datatype);
+            MemorySegment p = a.allocate(PARAMS);
+            PARAMS_INIT.invoke(p);
+            p.set(JAVA_INT, PARAMS.byteOffset(MemoryLayout.PathElement.groupElement("dtype")), dt[0]);
+            p.set(JAVA_INT, PARAMS.byteOffset(MemoryLayout.PathElement.groupElement("big_endian")), dt[1]);
+            p.set(JAVA_INT, PARAMS.byteOffset(MemoryLayout.PathElement.groupElement("nfft")), fftSize);
+            p.set(JAVA_LONG, PARAMS.byteOffset(MemoryLayout.PathElement.groupElement("start_sample")), currentSampleOffset);
+            p.set(JAVA_LONG, PARAMS.byteOffset(MemoryLayout.PathElement.groupElement("hop")), (long) fftSize);
+            p.set(JAVA_INT, PARAMS.byteOffset(MemoryLayout.PathElement.groupElement("colormap")), colormap);
+            p.set(JAVA_DOUBLE, PARAMS.byteOffset(MemoryLayout.PathElement.groupElement("sample_rate")), sampleRate);
+            p.set(JAVA_DOUBLE, PARAMS.byteOffset(MemoryLayout.PathElement.groupElement("min_db")), minDb);
+            p.set(JAVA_DOUBLE, PARAMS.byteOffset(MemoryLayout.PathElement.groupElement("max_db")), maxDb);
+            MemorySegment out = a.allocate((long) canvasW * canvasH * 4);
+            MemorySegment seg = MemorySegment.ofBuffer(buffer);
+            check((int) RENDER_CANVAS.invoke(engine, seg, seg.byteSize(), p, canvasW, canvasH, 1L, 0 /* SA_REDUCE_NEAREST */, out));
+            return out.toArray(ValueLayout.JAVA_BYTE);
+        }
+    }
+
+    /** Drop-in body of IqData.getInterleavedBinary (IqData.java:160-187). */
+    public byte[] getInterleavedBinary(double[][] iqSamples, String format) throws Throwable {
+        int code;
+        if ("float32".equalsIgnoreCase(format)) code = 0;
+        else if ("int16".equalsIgnoreCase(format)) code = 1;
+        else throw new IllegalArgumentException("Unsupported binary format: " + format);
+        try (Arena a = Arena.ofConfined()) {
+            int n = iqSamples[0].length;
+            MemorySegment re = a.allocateFrom(JAVA_DOUBLE, iqSamples[0]), im = a.allocateFrom(JAVA_DOUBLE, iqSamples[1]);
+            MemorySegment out = a.allocate((long) n * (code == 0 ? 8 : 4));
+            check((int) IQ_PACK.invoke(engine, re, im, (long) n, code, out));
+            return out.toArray(ValueLayout.JAVA_BYTE);
+        }
+    }
+
+    /**
+     * The two O(N) loops of AnalysisDialogController.updateMagnitudeChart / updateFrequencyChart (:219-290):
+     * returns {magnitude dB[n], smoothed instantaneous frequency + centre[n]} (element 0 of row 1 is NaN).
+     */
+    public double[][] analysisSeries(double[][] data, double sampleRate, double alphaMagn, double alphaFreq,
+                                     double centerFreq) throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            int n = data[0].length;
+            MemorySegment re = a.allocateFrom(JAVA_DOUBLE, data[0]), im = a.allocateFrom(JAVA_DOUBLE, data[1]);
+            MemorySegment mag = a.allocate(JAVA_DOUBLE, n), frq = a.allocate(JAVA_DOUBLE, n);
+            check((int) ANALYSIS_SERIES.invoke(engine, re, im, (long) n, sampleRate, alphaMagn, alphaFreq, centerFreq, mag, frq));
+            return new double[][] { mag.toArray(JAVA_DOUBLE), frq.toArray(JAVA_DOUBLE) };
         }
     }
 

@@ -46,6 +46,23 @@ int main() {
     int pk = 0;
     for (int i = 1; i < 256; i++) if (psd[1][i] > psd[1][pk]) pk = i;
     EXPECT(std::fabs(psd[0][pk]) < 1.0e6 / 4 / 256 * 1.5);
+    // IqData.getInterleavedBinary: DC tone 1.0 -> int16 32767 / 0 (truncation), float32 little-endian
+    IqData iqd(eng, z);
+    std::vector<uint8_t> i16 = iqd.getInterleavedBinary("int16");
+    EXPECT(i16.size() == 4 * (size_t)n);
+    const int16_t last_i = (int16_t)(i16[4 * (n - 1)] | (i16[4 * (n - 1) + 1] << 8));
+    EXPECT(last_i >= 32763 && last_i <= 32767);
+    threw = false;
+    try { iqd.getInterleavedBinary("int8"); } catch (const std::invalid_argument&) { threw = true; }
+    EXPECT(threw);
+    // renderSpectrogram: 4 columns x 64 rows; the tone's row is the brightest of column 0
+    std::vector<uint8_t> px = SpectrogramRenderer::renderSpectrogram(eng, buf, 0, 4, 64, n, "cf32_le", 1.0e6, -160.0, -30.0,
+                                                                    SA_CMAP_GRAYSCALE, 1, SA_REDUCE_MAX);
+    EXPECT(px.size() == 4u * 64u * 4u);
+    int best = 0;
+    for (int y = 1; y < 64; y++) if (px[(size_t)(y * 4) * 4] > px[(size_t)(best * 4) * 4]) best = y;
+    const int f_row = 63 - best;                                   // y flipped, MainController.java:1288
+    EXPECT((int)((double)f_row / 64 * n) <= arg && arg < (int)((double)(f_row + 1) / 64 * n));
     std::printf("cpp services ok\n");
     return 0;
 }
