@@ -208,7 +208,8 @@ int Engine::launch_spectrogram_large(const void* d_iq, uint64_t n_samples, const
     if (win) { rc = window_table(p.window, (int)p.nfft, prec, &a.s.window); if (rc) return rc; }
     const size_t elem = (prec == SA_PREC_F64) ? 16 : 8;
     const uint64_t per_frame = (uint64_t)p.nfft * elem;
-    const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(p.n_frames, (64ull << 20) / per_frame));
+    static const uint64_t ws_mb = getenv("SA_LARGE_WS_MB") ? (uint64_t)atoi(getenv("SA_LARGE_WS_MB")) : 512;
+    const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(p.n_frames, (ws_mb << 20) / per_frame));
     rc = ensure_scratch(2, chunk * per_frame);
     if (rc) return rc;
     a.ws = scratch[2];

@@ -17,6 +17,15 @@ namespace sa {
 
 constexpr int kLargeC = 16;      // columns / rows per CTA
 
+// Exchange-buffer stride between the columns of large_cols_kernel: the column is the fast thread index, so
+// consecutive lanes hit the same offset of consecutive buffers; a stride of 16 bytes (mod 128) spreads them
+// over the banks and keeps the 128-bit stores of pass 0 aligned (without it all 16 columns share a bank:
+// 16-way conflicts).
+template <typename T, int N1> struct ColStride {
+    static constexpr int E = (int)sizeof(cpx<T>), M = 128 / E, STEP = 16 / E, BASE = Geo<T, N1>::SM_ELEMS;
+    static constexpr int value = BASE + ((STEP - BASE % M) + M) % M;
+};
+
 struct LargeArgs {
     SpecArgs s;                  // s.twiddle: pair table of the N1-point plan; s.window: T[N]
     long long frame0;            // first frame of this chunk
@@ -32,7 +41,7 @@ large_cols_kernel(const LargeArgs a) {
     constexpr int P = G::P, TPF = G::TPF, N = N1 * N2, C = kLargeC;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int fl = threadIdx.x % C, t = threadIdx.x / C;          // column is the fast index
-    cpx<T>* sm = reinterpret_cast<cpx<T>*>(smem_raw) + (size_t)fl * G::SM_ELEMS;
+    cpx<T>* sm = reinterpret_cast<cpx<T>*>(smem_raw) + (size_t)fl * ColStride<T, N1>::value;
     const long long frame = a.frame0 + blockIdx.y;
     const long long s0 = a.s.start_sample + frame * a.s.hop;
     if (s0 + N > a.s.n_samples) return;                           // EOF frame: large_rows_kernel writes the fill row
@@ -123,7 +132,7 @@ LargeKernelInfo make_large_info(int prec) {
     k.prec = prec; k.n = N1 * N2; k.n1 = N1; k.n2 = N2; k.dk = DK; k.win = WIN ? 1 : 0;
     k.cta_cols = kLargeC * Geo<T, N1>::TPF;
     k.cta_rows = kLargeC * Geo<T, N2>::TPF;
-    k.smem_cols = (size_t)kLargeC * Geo<T, N1>::SM_ELEMS * sizeof(cpx<T>);
+    k.smem_cols = (size_t)kLargeC * ColStride<T, N1>::value * sizeof(cpx<T>);
     const size_t ex = (size_t)kLargeC * Geo<T, N2>::SM_ELEMS * sizeof(cpx<T>);
     const size_t tile = (size_t)N2 * (kLargeC + 1) * sizeof(T);
     k.smem_rows = ex > tile ? ex : tile;

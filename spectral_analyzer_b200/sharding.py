@@ -55,6 +55,35 @@ def gather_rows(rows, n_frames, group=None, dst=0):
     return torch.cat(parts, dim=0)
 
 
+def canvas_columns(canvas_w, frames_per_column, world, rank):
+    """Canvas columns [c0, c1) of `rank` and the frame block they are made of: a rank renders whole
+    columns (Engine.render_canvas on its own samples), so only canvas-sized tiles are gathered."""
+    c0, c1 = frame_block(canvas_w, world, rank)
+    return c0, c1, c0 * frames_per_column, c1 * frames_per_column
+
+
+def gather_canvas(tile, canvas_w, group=None, dst=0):
+    """Display assembly of the decimated image (gather the display-sized image, not the
+    full-resolution rows): per-rank tiles [canvas_h, c1 - c0, 4] uint8 -> [canvas_h, canvas_w, 4] on `dst`."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    per = (canvas_w + world - 1) // world
+    h = tile.shape[0]
+    block = torch.zeros((per, h) + tuple(tile.shape[2:]), dtype=tile.dtype, device=tile.device)
+    block[: tile.shape[1]] = tile.transpose(0, 1)              # column-major blocks concatenate along columns
+    out = [torch.empty_like(block) for _ in range(world)] if rank == dst else None
+    dist.gather(block, out, dst=dst, group=group)
+    if rank != dst:
+        return None
+    parts = []
+    for r in range(world):
+        c0, c1 = frame_block(canvas_w, world, r)
+        parts.append(out[r][: c1 - c0])
+    return torch.cat(parts, dim=0).transpose(0, 1).contiguous()
+
+
 def annotation_shares(counts, world):
     """Size-balanced assignment of annotations to ranks (longest-processing-time first).
     Returns a list of index lists, one per rank."""

@@ -86,3 +86,40 @@ def test_sharded_image_equals_unsharded(world, n_frames):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert ok and shape == (n_frames, 256)
+
+
+def _canvas_worker(rank, world, port, W, H, fpc, q):
+    """Each rank renders its own canvas columns from its own samples (the checker stands in for
+    Engine.render_canvas), then only canvas-sized tiles are gathered."""
+    from oracle import c_oracle as co
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    nfft, fs = 128, 1.0e6
+    raw = synth.recording(W * fpc * nfft, "cu8", seed=13)
+    c0, c1, f0, f1 = sharding.canvas_columns(W, fpc, world, rank)
+    s0, s1 = sharding.sample_span(0, f0, f1, nfft, nfft)
+    db = co.spectrogram(raw[s0 * 2: s1 * 2], "cu8", 0, nfft, nfft, "rect", f1 - f0, nthreads=1)
+    tile = co.render_canvas(db[::fpc], H, fs, -120.0, -20.0, "Heatmap")            # [H, c1 - c0, 4], nearest frame
+    full = sharding.gather_canvas(torch.from_numpy(tile), W, dst=0)
+    if rank == 0:
+        db_all = co.spectrogram(raw, "cu8", 0, nfft, nfft, "rect", W * fpc, nthreads=1)
+        ref = co.render_canvas(db_all[::fpc], H, fs, -120.0, -20.0, "Heatmap")
+        q.put((bool(np.array_equal(full.numpy(), ref)), tuple(full.shape)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,W", [(2, 9), (3, 4)])
+def test_sharded_canvas_equals_unsharded(world, W):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_canvas_worker, args=(r, world, port, W, 40, 3, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    ok, shape = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok and shape == (40, W, 4)
