@@ -90,6 +90,43 @@ def annotation_case(eng, n_samples, n_ann, count, down, steps):
             "GBps": round(alg / ms / 1e6, 1), "roofline_frac": round(alg / ms / 1e6 / peak, 4), "peak_kind": kind_p}
 
 
+def canvas_case(eng, n_samples, nfft, hop, W, H, reduce, steps):
+    """N2: whole-recording view, canvas W x H from 2^28 cf32 samples: device-resident time of the spectrogram +
+    canvas kernels, and the host call (H2D of the samples, D2H of the canvas only)."""
+    dev = torch.device("cuda", 0)
+    raw = torch.randn(2 * n_samples, device=dev, dtype=torch.float32).mul_(0.1)
+    frames = (n_samples - nfft) // hop + 1
+    fpc = frames // W
+    out = torch.empty(W * H, device=dev, dtype=torch.int32)
+    p = eng.make_params("cf32_le", nfft, hop, "hann", colormap="Heatmap", sample_rate=2.4e6)
+    stream = torch.cuda.current_stream().cuda_stream
+    L = _capi.lib()
+    red = _capi.REDUCE[reduce]
+
+    def run():
+        _capi.check(L.sa_render_canvas_device(eng.handle, raw.data_ptr(), n_samples * 8, C.byref(p), W, H, fpc, red,
+                                              out.data_ptr(), stream))
+    ms = timed(run, steps)
+    h_raw = torch.empty(2 * n_samples, dtype=torch.float32, pin_memory=True)
+    h_raw.copy_(raw)
+    h_np = h_raw.numpy()
+    import time
+    eng.render_canvas(h_np, "cf32_le", nfft, W, H, 2.4e6, hop=hop, window="hann", frames_per_column=fpc, reduce=reduce,
+                      colormap="Heatmap")
+    t0 = time.perf_counter()
+    for _ in range(3):
+        eng.render_canvas(h_np, "cf32_le", nfft, W, H, 2.4e6, hop=hop, window="hann", frames_per_column=fpc,
+                          reduce=reduce, colormap="Heatmap")
+    host_ms = (time.perf_counter() - t0) / 3 * 1e3
+    alg = n_samples * 8 + W * H * 4
+    peak, kind_p = hbm_peak()
+    return {"config": "N2 canvas %dx%d (%s) from cf32 %d-pt hop %d" % (W, H, reduce, nfft, hop), "samples": n_samples,
+            "frames_per_column": fpc, "ms": round(ms, 4), "Msamples_per_s": round(W * fpc * hop / ms / 1e3, 1),
+            "alg_bytes": alg, "GBps": round(alg / ms / 1e6, 1), "roofline_frac": round(alg / ms / 1e6 / peak, 4),
+            "host_call_ms": round(host_ms, 2), "host_Msamples_per_s": round(W * fpc * hop / host_ms / 1e3, 1),
+            "d2h_bytes": W * H * 4, "peak_kind": kind_p}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0)
@@ -116,6 +153,8 @@ def main():
     cases.append(('cf32 65536 Hann (four-step FP32)', lambda: spectrogram_case(eng, "cf32 65536 Hann (four-step FP32)", "cf32_le", sc(1 << 27), 65536, 65536, "hann", "f32", args.steps)))
     cases.append(('cf32 256 rect', lambda: spectrogram_case(eng, "cf32 256 rect", "cf32_le", sc(1 << 28), 256, 256, "rect", "f32", args.steps)))
     cases.append(('cf32 16384 Hann', lambda: spectrogram_case(eng, "cf32 16384 Hann", "cf32_le", sc(1 << 28), 16384, 16384, "hann", "f32", args.steps)))
+    cases.append(("N2 canvas max", lambda: canvas_case(eng, sc(1 << 28), 1024, 512, 2048, 1024, "max", args.steps)))
+    cases.append(("N2 canvas nearest", lambda: canvas_case(eng, sc(1 << 28), 1024, 512, 2048, 1024, "nearest", args.steps)))
     for name, fn in cases:
         if args.only in name:
             res.append(fn())

@@ -50,15 +50,15 @@ void fill_canvas_args(CanvasArgs& ca, const sa_spectrogram_params& p, uint32_t w
 int launch_canvas(Engine* eng, CanvasArgs& ca, const float* d_db, int col0, int ncols, cudaStream_t stream) {
     ca.db = d_db; ca.col0 = col0; ca.ncols = ncols;
     void* args[] = { &ca };
-    cudaError_t e = cudaLaunchKernel((const void*)&canvas_kernel, dim3((ca.canvas_h + 255) / 256, ncols), dim3(256), args, 0, stream);
+    cudaError_t e = cudaLaunchKernel((const void*)&canvas_kernel, dim3((ca.canvas_h + kCanvasRows - 1) / kCanvasRows, ncols), dim3(kCanvasRows * kCanvasGroups), args, 0, stream);
     if (e != cudaSuccess) return cuda_fail(e, "launch canvas_kernel");
     eng->launches++;
     return SA_OK;
 }
 
-uint64_t canvas_cols_per_chunk(const sa_spectrogram_params& p, uint64_t fpc, uint32_t w) {
+uint64_t canvas_cols_per_chunk(const sa_spectrogram_params& p, uint64_t fpc, uint32_t w, uint64_t chunk_bytes) {
     const uint64_t col_bytes = fpc * (uint64_t)p.nfft * 4;
-    return std::max<uint64_t>(1, std::min<uint64_t>(w, kCanvasChunkBytes / col_bytes));
+    return std::max<uint64_t>(1, std::min<uint64_t>(w, chunk_bytes / col_bytes));
 }
 
 }  // namespace
@@ -81,7 +81,7 @@ int32_t sa_render_canvas_device(sa_engine* engine, const void* d_iq, uint64_t iq
     const uint64_t bps = (uint64_t)sa_bytes_per_iq(q.dtype);
     if ((uintptr_t)d_iq % bps) return set_error(SA_ERR_INVALID_ARG, "d_iq must be aligned to %llu bytes", (unsigned long long)bps);
     cudaStream_t stream = (cudaStream_t)cuda_stream;
-    const uint64_t cpc = canvas_cols_per_chunk(q, frames_per_column, canvas_w);
+    const uint64_t cpc = canvas_cols_per_chunk(q, frames_per_column, canvas_w, 4 * kCanvasChunkBytes);
     rc = engine->ensure_scratch(3, cpc * frames_per_column * q.nfft * 4);
     if (rc) return rc;
     CanvasArgs ca;
@@ -113,7 +113,7 @@ int32_t sa_render_canvas(sa_engine* engine, const void* iq, uint64_t iq_bytes, c
     if (rc) return rc;
     const uint64_t bps = (uint64_t)sa_bytes_per_iq(q.dtype);
     const uint64_t n_samples = iq_bytes / bps;
-    const uint64_t cpc = canvas_cols_per_chunk(q, frames_per_column, canvas_w);
+    const uint64_t cpc = canvas_cols_per_chunk(q, frames_per_column, canvas_w, kCanvasChunkBytes);
     const uint64_t fpchunk = cpc * frames_per_column;
     const uint64_t in_cap = ((fpchunk - 1) * q.hop + q.nfft) * bps;
     const uint64_t out_cap = fpchunk * q.nfft * 4;

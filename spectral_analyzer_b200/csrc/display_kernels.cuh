@@ -27,31 +27,57 @@ struct CanvasArgs {
     float inv_range, cmap_bias;
 };
 
-// one thread per pixel; threads of a warp take consecutive rows f, i.e. consecutive bin ranges
-__global__ void __launch_bounds__(256)
+// CTA = 32 pixel rows x 8 frame groups: lane = row f (consecutive rows -> consecutive bin ranges, coalesced),
+// warp g takes the column's frames g, g + 8, ... with four independent partial results in flight; the eight
+// partials of a pixel are combined through shared memory.
+constexpr int kCanvasRows = 32, kCanvasGroups = 8;
+
+__global__ void __launch_bounds__(kCanvasRows * kCanvasGroups)
 canvas_kernel(const CanvasArgs a) {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float part[kCanvasGroups][kCanvasRows];
+    const int lane = threadIdx.x % kCanvasRows, g = threadIdx.x / kCanvasRows;
+    const int f = blockIdx.x * kCanvasRows + lane;
     const int col = blockIdx.y;
-    if (f >= a.canvas_h) return;
+    const bool live = f < a.canvas_h;
     // MainController.java:1280  bin = (int)((double) f / canvasH * nfft)
-    const int b0 = (int)((double)f / (double)a.canvas_h * (double)a.nfft);
-    int b1 = (int)((double)(f + 1) / (double)a.canvas_h * (double)a.nfft);
+    const int b0 = live ? (int)((double)f / (double)a.canvas_h * (double)a.nfft) : 0;
+    int b1 = live ? (int)((double)(f + 1) / (double)a.canvas_h * (double)a.nfft) : 1;
     if (b1 <= b0) b1 = b0 + 1;
     if (b1 > a.nfft) b1 = a.nfft;
     const float* rows = a.db + (size_t)col * a.fpc * a.nfft;
-    float v;
+    float v = 0.f;
     if (a.reduce == REDUCE_NEAREST) {
-        v = rows[b0];                                   // first frame of the column, nearest bin (:1283)
-    } else if (a.reduce == REDUCE_MAX) {
-        v = -3.0e38f;
-        for (int fr = 0; fr < a.fpc; fr++)
-            for (int b = b0; b < b1; b++) v = fmaxf(v, rows[(size_t)fr * a.nfft + b]);
+        if (live && g == 0) v = rows[b0];               // first frame of the column, nearest bin (:1283)
     } else {
-        float acc = 0.f;                                // mean of linear power, back to dB
-        for (int fr = 0; fr < a.fpc; fr++)
-            for (int b = b0; b < b1; b++) acc += exp2f(rows[(size_t)fr * a.nfft + b] * 0.33219280948873623f);
-        v = 3.01029995663981f * log2f(acc / (float)(a.fpc * (b1 - b0)));
+        const bool is_max = a.reduce == REDUCE_MAX;
+        float acc[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) acc[u] = is_max ? -3.0e38f : 0.f;
+        if (live) {
+            for (int fr = g; fr < a.fpc; fr += 4 * kCanvasGroups) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int fu = fr + u * kCanvasGroups;
+                    if (fu < a.fpc) {
+                        const float* r = rows + (size_t)fu * a.nfft;
+                        for (int b = b0; b < b1; b++) {
+                            const float x = r[b];
+                            acc[u] = is_max ? fmaxf(acc[u], x) : acc[u] + exp2f(x * 0.33219280948873623f);
+                        }
+                    }
+                }
+            }
+        }
+        v = is_max ? fmaxf(fmaxf(acc[0], acc[1]), fmaxf(acc[2], acc[3])) : (acc[0] + acc[1]) + (acc[2] + acc[3]);
+        part[g][lane] = v;
+        __syncthreads();
+        if (g == 0) {
+#pragma unroll
+            for (int k = 1; k < kCanvasGroups; k++) v = is_max ? fmaxf(v, part[k][lane]) : v + part[k][lane];
+            if (!is_max) v = 3.01029995663981f * log2f(v / (float)(a.fpc * (b1 - b0)));   // mean of linear power, back to dB
+        }
     }
+    if (!live || g != 0) return;
     const uint32_t px = a.cmap == 1 ? colormap_px<1>(v, a.inv_range, a.cmap_bias) : colormap_px<0>(v, a.inv_range, a.cmap_bias);
     a.out[(size_t)(a.canvas_h - 1 - f) * a.canvas_w + a.col0 + col] = px;      // :1288 y flipped
 }
