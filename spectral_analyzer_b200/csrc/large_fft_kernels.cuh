@@ -61,12 +61,19 @@ large_cols_kernel(const LargeArgs a) {
     }
     TwSeed<T> seed; seed.om = mk2<T>((T)1, (T)0); seed.oh = seed.om;
     fft_frame<T, N1, false, false, true>(v, t, sm, reinterpret_cast<const cpx<T>*>(a.s.twiddle), nullptr, seed);
+    // four-step twiddle W_N^(n2 k1), k1 = t + TPF q: W_N^(n2 t) advanced by W_N^(n2 TPF) per q (two table reads
+    // per thread instead of P scattered ones; re-seeded from the table every 8 steps)
     const cpx<T>* twn = reinterpret_cast<const cpx<T>*>(a.tw_n);
     cpx<T>* ws = reinterpret_cast<cpx<T>*>(a.ws) + (size_t)blockIdx.y * N;
+    const cpx<T> step = __ldg(&twn[(n2 * TPF) & (N - 1)]);
+    cpx<T> w = __ldg(&twn[(n2 * t) & (N - 1)]);
 #pragma unroll
     for (int q = 0; q < P; q++) {
         const int k1 = t + TPF * q;
-        const cpx<T> w = __ldg(&twn[(n2 * k1) & (N - 1)]);
+        if (q > 0) {
+            if ((q & 7) == 0) w = __ldg(&twn[(n2 * k1) & (N - 1)]);
+            else w = mk2<T>(fma_t(-w.y, step.y, w.x * step.x), fma_t(w.y, step.x, w.x * step.y));
+        }
         ws[(size_t)k1 * N2 + n2] = mk2<T>(fma_t(-w.y, v[q].y, w.x * v[q].x), fma_t(w.y, v[q].x, w.x * v[q].y));
     }
 }
