@@ -1,0 +1,60 @@
+"""Small invocation of every kernel family, for compute-sanitizer (memcheck / racecheck) runs:
+    compute-sanitizer --tool memcheck python tools/sanitize_smoke.py
+Sizes are tiny (the tools slow kernels down 10-100x); results are still compared with the CPU checker."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import spectral_analyzer_b200 as sa                      # noqa: E402
+from spectral_analyzer_b200 import synth                 # noqa: E402
+from oracle import c_oracle as co                        # noqa: E402
+
+only = sys.argv[1] if len(sys.argv) > 1 else ""
+eng = sa.Engine(0)
+n_checked = 0
+for nfft in (64, 256, 1024, 2048, 4096, 16384, 65536):
+    for dt, win, hop in (("cf32_le", "hann", nfft // 2), ("ci16_le", "rect", nfft), ("cu8", "hann", nfft // 2 + 1)):
+        if only and only not in ("spec%d" % nfft):
+            continue
+        frames = 5
+        raw = synth.recording((frames - 2) * hop + nfft + 9, dt, seed=nfft)            # last frame(s) past EOF
+        got = eng.spectrogram(raw, dt, nfft, frames, hop=hop, window=win, start_sample=0)
+        ref = co.spectrogram(raw, dt, 0, nfft, hop, win, frames)
+        strong = ref > ref.max(axis=1, keepdims=True) - 40
+        assert np.abs(got - ref)[strong].max() < 1e-3, (nfft, dt)
+        n_checked += 1
+if not only or only == "f64":
+    raw = synth.recording(16384 * 3, "cf64_le", seed=2)
+    for nfft in (1024, 16384):
+        got = eng.spectrogram(raw, "cf64_le", nfft, 3, window="hann", out_kind="f64")
+        ref = co.spectrogram(raw, "cf64_le", 0, nfft, nfft, "hann", 3)
+        assert np.abs(got - ref).max() < 1e-6
+        n_checked += 1
+if not only or only == "analysis":
+    raw = synth.recording(40000, "ci16_le", seed=3)
+    for down, fast in ((16, False), (5, False), (16, True), (600, False)):
+        got = eng.downconvert(raw, "ci16_le", 100, 36000, 0.125, down, fast)
+        ref = co.downconvert(raw, "ci16_le", 100, 36000, 0.125, down, fast)
+        assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-5, (down, fast)
+        n_checked += 1
+    iq = co.downconvert(raw, "ci16_le", 100, 36000, 0.125, 4, False)
+    psd = eng.psd_welch(iq, 250e3, 2048)
+    ref = co.psd_welch(iq, 250e3, 2048)
+    top = ref[1] > ref[1].max() - 60
+    assert np.abs(psd[1] - ref[1])[top].max() < 2e-3
+    assert eng.iq_pack(iq, "int16") == co.iq_pack(iq, "int16")
+    gm, gf = eng.analysis_series(iq, 250e3, 0.2, 0.05, 1e6)
+    rm, rf = co.analysis_series(iq, 250e3, 0.2, 0.05, 1e6)
+    assert np.abs(gm - rm).max() < 1e-9 and np.abs(gf[1:] - rf[1:]).max() < 1e-3
+    n_checked += 3
+if not only or only == "canvas":
+    raw = synth.recording(1024 * 40, "cf32_le", seed=5)
+    for red in ("nearest", "max", "mean"):
+        px = eng.render_canvas(raw, "cf32_le", 1024, 13, 200, 2.4e6, frames_per_column=3, reduce=red, colormap="Heatmap")
+        assert px.shape == (200, 13, 4) and (px[..., 3] == 255).all()
+        n_checked += 1
+eng.close()
+print("sanitize smoke ok: %d checks" % n_checked)
