@@ -208,15 +208,54 @@ int Engine::launch_spectrogram_large(const void* d_iq, uint64_t n_samples, const
     if (win) { rc = window_table(p.window, (int)p.nfft, prec, &a.s.window); if (rc) return rc; }
     const size_t elem = (prec == SA_PREC_F64) ? 16 : 8;
     const uint64_t per_frame = (uint64_t)p.nfft * elem;
+    void* args[] = { &a };
+    cudaError_t e;
+    // opt-in (SA_LARGE_CLUSTER=1): measured slower than the two-kernel path on B200 (DESIGN.md K6 ablation)
+    static const bool use_cluster = getenv("SA_LARGE_CLUSTER") != nullptr;
+    if (k->fn_cluster && use_cluster) {
+        // cluster path: one 8-CTA cluster per frame, per-cluster workspace slice that stays in L2
+        auto it = occupancy.find(k->fn_cluster);
+        int n_clusters = 0;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = kLargeCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.blockDim = dim3(k->cta_cols);
+        cfg.dynamicSmemBytes = k->smem_cluster;
+        cfg.stream = stream;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        if (it == occupancy.end()) {
+            e = cudaFuncSetAttribute(k->fn_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->smem_cluster);
+            if (e != cudaSuccess) return cuda_fail(e, "large FFT cluster smem attribute");
+            cfg.gridDim = dim3(kLargeCluster * num_sms);
+            e = cudaOccupancyMaxActiveClusters(&n_clusters, k->fn_cluster, &cfg);
+            if (e != cudaSuccess || n_clusters < 1) { cudaGetLastError(); n_clusters = 0; }
+            occupancy[k->fn_cluster] = n_clusters;
+        } else {
+            n_clusters = it->second;
+        }
+        if (n_clusters > 0) {
+            const uint64_t use = std::min<uint64_t>((uint64_t)n_clusters, p.n_frames);
+            rc = ensure_scratch(2, 2 * use * per_frame);
+            if (rc) return rc;
+            a.ws = scratch[2];
+            a.frame0 = 0;
+            cfg.gridDim = dim3((unsigned)(use * kLargeCluster));
+            e = cudaLaunchKernelExC(&cfg, k->fn_cluster, args);
+            if (e != cudaSuccess) return cuda_fail(e, "launch large_cluster_kernel");
+            launches++;
+            return SA_OK;
+        }
+    }
     static const uint64_t ws_mb = getenv("SA_LARGE_WS_MB") ? (uint64_t)atoi(getenv("SA_LARGE_WS_MB")) : 512;
     const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(p.n_frames, (ws_mb << 20) / per_frame));
     rc = ensure_scratch(2, chunk * per_frame);
     if (rc) return rc;
     a.ws = scratch[2];
-    cudaError_t e = cudaFuncSetAttribute(k->fn_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->smem_cols);
+    e = cudaFuncSetAttribute(k->fn_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->smem_cols);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k->fn_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->smem_rows);
     if (e != cudaSuccess) return cuda_fail(e, "large FFT smem attribute");
-    void* args[] = { &a };
     for (uint64_t f0 = 0; f0 < p.n_frames; f0 += chunk) {
         const unsigned nf = (unsigned)std::min<uint64_t>(chunk, p.n_frames - f0);
         a.frame0 = (long long)f0;

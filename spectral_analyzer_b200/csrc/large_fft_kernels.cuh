@@ -34,18 +34,17 @@ struct LargeArgs {
     void* ws;                    // cpx<T>[chunk frames][N1][N2]
 };
 
+// column group `cg` (C columns n2) of `frame`: writes A[k1][n2] of that frame to ws_frame
 template <typename T, int N1, int N2, int DK, bool WIN>
-__global__ void __launch_bounds__(kLargeC * Geo<T, N1>::TPF)
-large_cols_kernel(const LargeArgs a) {
+__device__ __forceinline__ void large_cols_body(const LargeArgs& a, const long long frame, cpx<T>* __restrict__ ws,
+                                                const int cg, unsigned char* smem_raw) {
     using G = Geo<T, N1>;
     constexpr int P = G::P, TPF = G::TPF, N = N1 * N2, C = kLargeC;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int fl = threadIdx.x % C, t = threadIdx.x / C;          // column is the fast index
     cpx<T>* sm = reinterpret_cast<cpx<T>*>(smem_raw) + (size_t)fl * ColStride<T, N1>::value;
-    const long long frame = a.frame0 + blockIdx.y;
     const long long s0 = a.s.start_sample + frame * a.s.hop;
-    if (s0 + N > a.s.n_samples) return;                           // EOF frame: large_rows_kernel writes the fill row
-    const int n2 = blockIdx.x * C + fl;
+    if (s0 + N > a.s.n_samples) return;                           // EOF frame (uniform): the rows step writes the fill row
+    const int n2 = cg * C + fl;
     cpx<T> v[P];
     if (a.s.lp.swap) {
 #pragma unroll
@@ -64,7 +63,6 @@ large_cols_kernel(const LargeArgs a) {
     // four-step twiddle W_N^(n2 k1), k1 = t + TPF q: W_N^(n2 t) advanced by W_N^(n2 TPF) per q (two table reads
     // per thread instead of P scattered ones; re-seeded from the table every 8 steps)
     const cpx<T>* twn = reinterpret_cast<const cpx<T>*>(a.tw_n);
-    cpx<T>* ws = reinterpret_cast<cpx<T>*>(a.ws) + (size_t)blockIdx.y * N;
     const cpx<T> step = __ldg(&twn[(n2 * TPF) & (N - 1)]);
     cpx<T> w = __ldg(&twn[(n2 * t) & (N - 1)]);
 #pragma unroll
@@ -78,24 +76,35 @@ large_cols_kernel(const LargeArgs a) {
     }
 }
 
+template <typename T, int N1, int N2, int DK, bool WIN>
+__global__ void __launch_bounds__(kLargeC * Geo<T, N1>::TPF)
+large_cols_kernel(const LargeArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    large_cols_body<T, N1, N2, DK, WIN>(a, a.frame0 + blockIdx.y, reinterpret_cast<cpx<T>*>(a.ws) + (size_t)blockIdx.y * (N1 * N2),
+                                        blockIdx.x, smem_raw);
+}
+
+// 16-byte / 8-byte loads that bypass L1 (the workspace is written by other SMs of the same launch in the cluster kernel)
+__device__ __forceinline__ float2  ld_cg(const float2* p)  { return __ldcg(p); }
+__device__ __forceinline__ double2 ld_cg(const double2* p) { return __ldcg(p); }
+
+// row group `rg` (C rows k1) of `frame`: N2-point FFTs of A[k1][.] from ws_frame, dB, fft-shifted store
 template <typename T, int N1, int N2>
-__global__ void __launch_bounds__(kLargeC * Geo<T, N2>::TPF)
-large_rows_kernel(const LargeArgs a) {
+__device__ __forceinline__ void large_rows_body(const LargeArgs& a, const long long frame, const cpx<T>* __restrict__ ws_frame,
+                                                const int rg, unsigned char* smem_raw) {
     using G = Geo<T, N2>;
     constexpr int P = G::P, TPF = G::TPF, N = N1 * N2, C = kLargeC, THREADS = C * TPF;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int t = threadIdx.x % TPF, fl = threadIdx.x / TPF;      // element is the fast index
     cpx<T>* sm = reinterpret_cast<cpx<T>*>(smem_raw) + (size_t)fl * G::SM_ELEMS;
-    const long long frame = a.frame0 + blockIdx.y;
     const long long s0 = a.s.start_sample + frame * a.s.hop;
     const bool readable = s0 + N <= a.s.n_samples;                // CTA-uniform, MainController.java:987
-    const int k1 = blockIdx.x * C + fl;
+    const int k1 = rg * C + fl;
     T db[P];
     if (readable) {
-        const cpx<T>* ws = reinterpret_cast<const cpx<T>*>(a.ws) + (size_t)blockIdx.y * N + (size_t)k1 * N2;
+        const cpx<T>* ws = ws_frame + (size_t)k1 * N2;
         cpx<T> v[P];
 #pragma unroll
-        for (int q = 0; q < P; q++) v[q] = ws[t + TPF * q];
+        for (int q = 0; q < P; q++) v[q] = ld_cg(&ws[t + TPF * q]);
         TwSeed<T> seed; seed.om = mk2<T>((T)1, (T)0); seed.oh = seed.om;
         fft_frame<T, N2, false, false, true>(v, t, sm, reinterpret_cast<const cpx<T>*>(a.tw2), nullptr, seed);
         if (a.s.db_mode == DBM_MAG_1E10) bins_to_db<T, P, DBM_MAG_1E10>(v, db);
@@ -112,7 +121,7 @@ large_rows_kernel(const LargeArgs a) {
     __syncthreads();
     const int c = threadIdx.x % C, j0 = threadIdx.x / C;
     const size_t row = (size_t)frame * N;
-    const int kbase = blockIdx.x * C + c;
+    const int kbase = rg * C + c;
     for (int k2 = j0; k2 < N2; k2 += THREADS / C) {
         const T val = tile[k2 * (C + 1) + c];
         const size_t o = row + (size_t)((kbase + N1 * k2 + N / 2) & (N - 1));     // SpectralService.java:78
@@ -122,8 +131,64 @@ large_rows_kernel(const LargeArgs a) {
     }
 }
 
+template <typename T, int N1, int N2>
+__global__ void __launch_bounds__(kLargeC * Geo<T, N2>::TPF)
+large_rows_kernel(const LargeArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    large_rows_body<T, N1, N2>(a, a.frame0 + blockIdx.y, reinterpret_cast<const cpx<T>*>(a.ws) + (size_t)blockIdx.y * (N1 * N2),
+                               blockIdx.x, smem_raw);
+}
+
+// ---- cluster variant (N1 == N2): one thread-block cluster of kLargeCluster CTAs per frame ----
+// The A[k1][n2] matrix of a frame lives in a per-cluster slice of the workspace that is rewritten every frame,
+// so only (resident clusters) x N elements are ever in flight: it stays in L2 instead of making a DRAM round trip
+// (the two-kernel path writes and re-reads the whole chunk).  The column step and the row step of a frame are
+// separated by the hardware cluster barrier (release / acquire), no host-side launch boundary and no spin-wait.
+constexpr int kLargeCluster = 8;
+
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_id_x()    { unsigned r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_count_x() { unsigned r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <typename T, int N1, int N2, int DK, bool WIN>
+__global__ void __launch_bounds__(kLargeC * Geo<T, N1>::TPF, 2)
+large_cluster_kernel(const LargeArgs a) {
+    static_assert(Geo<T, N1>::TPF == Geo<T, N2>::TPF, "both steps use the same CTA size");
+    constexpr int N = N1 * N2, C = kLargeC;
+    constexpr int COL_GROUPS = N2 / C / kLargeCluster, ROW_GROUPS = N1 / C / kLargeCluster;
+    static_assert(COL_GROUPS >= 1 && ROW_GROUPS >= 1, "every CTA of the cluster owns whole groups");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const unsigned rank = cluster_ctarank();
+    // two slices per cluster: the column step of the next frame fills one while slower CTAs still read the other
+    cpx<T>* ws = reinterpret_cast<cpx<T>*>(a.ws) + (size_t)cluster_id_x() * (2 * N);
+    const long long stride = cluster_count_x();
+    long long f = cluster_id_x();
+    int buf = 0;
+    auto cols = [&](long long fr, int b) {
+#pragma unroll 1
+        for (int g = 0; g < COL_GROUPS; g++) {
+            large_cols_body<T, N1, N2, DK, WIN>(a, a.frame0 + fr, ws + (size_t)b * N, (int)rank * COL_GROUPS + g, smem_raw);
+            __syncthreads();
+        }
+    };
+    if (f < a.s.n_frames) cols(f, buf);
+    for (; f < a.s.n_frames; f += stride, buf ^= 1) {
+        cluster_sync_all();                     // every column of frame f is in the workspace; frame f - stride fully read
+#pragma unroll 1
+        for (int g = 0; g < ROW_GROUPS; g++) {
+            large_rows_body<T, N1, N2>(a, a.frame0 + f, ws + (size_t)buf * N, (int)rank * ROW_GROUPS + g, smem_raw);
+            __syncthreads();
+        }
+        if (f + stride < a.s.n_frames) cols(f + stride, buf ^ 1);
+    }
+}
+
 struct LargeKernelInfo {
-    const void* fn_cols; const void* fn_rows;
+    const void* fn_cols; const void* fn_rows; const void* fn_cluster;
+    size_t smem_cluster;
     int prec, n, n1, n2, dk, win;
     int cta_cols, cta_rows;
     size_t smem_cols, smem_rows;
@@ -143,6 +208,11 @@ LargeKernelInfo make_large_info(int prec) {
     const size_t ex = (size_t)kLargeC * Geo<T, N2>::SM_ELEMS * sizeof(cpx<T>);
     const size_t tile = (size_t)N2 * (kLargeC + 1) * sizeof(T);
     k.smem_rows = ex > tile ? ex : tile;
+    k.fn_cluster = nullptr; k.smem_cluster = 0;
+    if constexpr (N1 == N2) {
+        k.fn_cluster = (const void*)&large_cluster_kernel<T, N1, N2, DK, WIN>;
+        k.smem_cluster = k.smem_cols > k.smem_rows ? k.smem_cols : k.smem_rows;
+    }
     return k;
 }
 
