@@ -33,6 +33,9 @@
 #ifndef SA_TW_SMEM_MAX_TPF
 #define SA_TW_SMEM_MAX_TPF 32
 #endif
+#ifndef SA_PACKED_SMALL_RADIX
+#define SA_PACKED_SMALL_RADIX 0
+#endif
 #ifndef SA_TW_RECURRENCE
 #define SA_TW_RECURRENCE 1
 #endif
@@ -205,6 +208,41 @@ __device__ __forceinline__ void radix_fft(cpx<T> (&v)[P], const T* __restrict__ 
                                           const TwPair<T>* __restrict__ tw, const int tw_stride,
                                           const TwSeed<T>& seed) {
     static_assert(R == 2 || R == 4 || R == 8 || R == 16 || R == 32, "radix");
+    if constexpr (SA_PACKED_SMALL_RADIX && sizeof(T) == 4 && R <= 4 && (MUL == MUL_REAL || MUL == MUL_NONE)) {
+        // ablation, off by default (C2 2.55 -> 2.68 ms: the re-pairing costs more than the packed ops save):
+        // small first-pass radices (spectrogram_mid_kernel): a complex value is already a packed (re, im) register
+        // pair, so the window multiply and the W = 1 butterflies run as FMUL2 / FFMA2 / FADD2 with the real factor
+        // as the scalar-broadcast operand -- 3 instead of 6 (2 instead of 4) instructions per butterfly
+        pk2 o[R];
+#pragma unroll
+        for (int m = 0; m < R / 2; m++) {
+            const cpx<T> x = v[OFF + STR * m], y = v[OFF + STR * (m + R / 2)];
+            const pk2 X = pack2((float)x.x, (float)x.y), Y = pack2((float)y.x, (float)y.y);
+            if constexpr (MUL == MUL_REAL) {
+                const cpx<T> wp = *reinterpret_cast<const cpx<T>*>(wr + 2 * (OFF + STR * m));
+                const pk2 t = mul2(X, bcast2((float)wp.x));
+                o[2 * m] = fma2(Y, bcast2((float)wp.y), t);
+                o[2 * m + 1] = fma2(Y, bcast2(-(float)wp.y), t);
+            } else {
+                o[2 * m] = add2(X, Y);
+                o[2 * m + 1] = sub2(X, Y);
+            }
+        }
+        if constexpr (R == 2) {
+            float re, im;
+            unpack2(o[0], re, im); v[OFF] = mk2<T>((T)re, (T)im);
+            unpack2(o[1], re, im); v[OFF + STR] = mk2<T>((T)re, (T)im);
+        } else {
+            // o = (x0+x2, x0-x2, x1+x3, x1-x3); X0 = o0+o2, X2 = o0-o2, X1 = o1 - i o3, X3 = o1 + i o3
+            float ar, ai, br, bi, re, im;
+            unpack2(add2(o[0], o[2]), re, im); v[OFF] = mk2<T>((T)re, (T)im);
+            unpack2(sub2(o[0], o[2]), re, im); v[OFF + 2 * STR] = mk2<T>((T)re, (T)im);
+            unpack2(o[1], ar, ai); unpack2(o[3], br, bi);
+            v[OFF + STR] = mk2<T>((T)(ar + bi), (T)(ai - br));
+            v[OFF + 3 * STR] = mk2<T>((T)(ar - bi), (T)(ai + br));
+        }
+        return;
+    }
     cpx<T> a[R];
     pk2 rec_re = 0, rec_im = 0;                 // (om^m, om^(m+R/2)) as packed re / im (MUL_REC)
     if constexpr (MUL == MUL_REC) { rec_re = pack2(1.0f, (float)seed.oh.x); rec_im = pack2(0.0f, (float)seed.oh.y); }

@@ -90,12 +90,13 @@ __device__ __forceinline__ uint32_t colormap_px(const float db, const float scal
     if constexpr (HEAT) {
         const float r = __saturatef(__fmaf_rn(n, 1.0f / 0.3f, -0.2f / 0.3f));
         const float g = __saturatef(__fmaf_rn(n, 2.0f, -1.0f));
-        const float b = n >= 0.2f ? 1.0f - r : 0.0f;
         const uint32_t R = __float_as_uint(__fmaf_rn(r, 255.0f, MAGIC));
         const uint32_t G = __float_as_uint(__fmaf_rn(g, 255.0f, MAGIC));
-        const uint32_t B = __float_as_uint(__fmaf_rn(b, 255.0f, MAGIC));
+        // b = n >= 0.2 ? 1 - r : 0, scaled: 255 (1 - r) + magic; the blue magic carries alpha in mantissa bits 8..15
+        constexpr float MAGIC_A = MAGIC + 65280.0f;
+        const uint32_t B = __float_as_uint(n >= 0.2f ? __fmaf_rn(r, -255.0f, MAGIC_A + 255.0f) : MAGIC_A);
         const uint32_t rg = __byte_perm(R, G, 0x0040);          // byte0 = R, byte1 = G
-        return __byte_perm(rg, B, 0x0410) | 0xFF000000u;        // byte2 = B (byte 3 overwritten by alpha)
+        return __byte_perm(rg, B, 0x5410);                      // byte2 = B, byte3 = alpha (byte 1 of B's magic)
     } else {
         const uint32_t V = __float_as_uint(__fmaf_rn(n, 255.0f, MAGIC));
         return __byte_perm(V, 0xFF000000u, 0x7000);             // R = G = B = V, A = 255
