@@ -350,11 +350,39 @@ int32_t sa_downconvert_psd_batch(sa_engine* engine, const void* iq, uint64_t iq_
     if (rc) return rc;
     cudaError_t e = cudaSuccess;
     uint64_t pos = 0;
-    for (uint32_t i = 0; i < n_ann && e == cudaSuccess; i++) {
-        if (anns[i].count)
-            e = cudaMemcpyAsync((char*)s.d_in + pos * bps, (const char*)iq + anns[i].start_sample * bps,
-                                anns[i].count * bps, cudaMemcpyHostToDevice, s.stream);
-        pos += anns[i].count;
+    if (host_ptr_is_pinned(iq)) {
+        for (uint32_t i = 0; i < n_ann && e == cudaSuccess; i++) {
+            if (anns[i].count)
+                e = cudaMemcpyAsync((char*)s.d_in + pos * bps, (const char*)iq + anns[i].start_sample * bps,
+                                    anns[i].count * bps, cudaMemcpyHostToDevice, s.stream);
+            pos += anns[i].count;
+        }
+    } else {
+        // pageable capture (mmapped file): pieces of <= 32 MiB alternate between the pinned staging buffers of
+        // slots 1 and 2; an event per buffer says when its previous H2D has drained
+        const size_t piece = 32u << 20;
+        Slot* st[2] = { &engine->slots[1], &engine->slots[2] };
+        cudaEvent_t ev[2] = { nullptr, nullptr };
+        for (int k = 0; k < 2 && e == cudaSuccess; k++) {
+            rc = engine->ensure_staging(*st[k], piece, 0);
+            if (rc) return rc;
+            e = cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming);
+        }
+        int k = 0;
+        for (uint32_t i = 0; i < n_ann && e == cudaSuccess; i++) {
+            const uint64_t total = anns[i].count * bps;
+            for (uint64_t off = 0; off < total && e == cudaSuccess; off += piece, k ^= 1) {
+                const size_t nb = (size_t)std::min<uint64_t>(piece, total - off);
+                e = cudaEventSynchronize(ev[k]);                 // a never-recorded event is complete
+                if (e != cudaSuccess) break;
+                engine->host_copy(st[k]->h_in, (const char*)iq + anns[i].start_sample * bps + off, nb);
+                e = cudaMemcpyAsync((char*)s.d_in + pos * bps + off, st[k]->h_in, nb, cudaMemcpyHostToDevice, s.stream);
+                if (e == cudaSuccess) e = cudaEventRecord(ev[k], s.stream);
+            }
+            pos += anns[i].count;
+        }
+        for (int j = 0; j < 2; j++)
+            if (ev[j]) { cudaEventSynchronize(ev[j]); cudaEventDestroy(ev[j]); }
     }
     if (e != cudaSuccess) return cuda_fail(e, "H2D annotation spans");
     double* d_iq_out = (double*)s.d_out;

@@ -123,11 +123,14 @@ int32_t sa_render_canvas(sa_engine* engine, const void* iq, uint64_t iq_bytes, c
     CanvasArgs ca;
     fill_canvas_args(ca, q, canvas_w, canvas_h, frames_per_column, reduce, (uint32_t*)engine->scratch[3]);
     // chunk c: H2D of its samples -> spectrogram -> canvas columns, on slot c % kSlots; only the canvas comes back
+    const bool in_pinned = host_ptr_is_pinned(iq);
     uint64_t c = 0;
     cudaError_t e = cudaSuccess;
     for (uint64_t c0 = 0; c0 < canvas_w; c0 += cpc, c++) {
         Slot& s = engine->slots[c % kSlots];
         rc = engine->ensure_slot(s, in_cap, out_cap);
+        if (rc) return rc;
+        rc = engine->ensure_staging(s, in_pinned ? 0 : in_cap, 0);
         if (rc) return rc;
         e = cudaStreamSynchronize(s.stream);
         if (e != cudaSuccess) return cuda_fail(e, "slot sync");
@@ -138,7 +141,9 @@ int32_t sa_render_canvas(sa_engine* engine, const void* iq, uint64_t iq_bytes, c
         if (s_end > n_samples) s_end = n_samples;
         const uint64_t ns = s_end > s_begin ? s_end - s_begin : 0;
         if (ns) {
-            e = cudaMemcpyAsync(s.d_in, (const char*)iq + s_begin * bps, ns * bps, cudaMemcpyHostToDevice, s.stream);
+            const void* src = (const char*)iq + s_begin * bps;
+            if (!in_pinned) { engine->host_copy(s.h_in, src, ns * bps); src = s.h_in; }
+            e = cudaMemcpyAsync(s.d_in, src, ns * bps, cudaMemcpyHostToDevice, s.stream);
             if (e != cudaSuccess) return cuda_fail(e, "H2D");
         }
         sa_spectrogram_params r = q;

@@ -12,6 +12,54 @@
 
 namespace sa {
 
+// ---------------- parallel host copies ----------------
+CopyPool::CopyPool(int workers) {
+    for (int i = 0; i < workers; i++) threads_.emplace_back([this] { worker(); });
+}
+CopyPool::~CopyPool() {
+    { std::lock_guard<std::mutex> l(mu_); stop_ = true; }
+    cv_.notify_all();
+    for (auto& t : threads_) t.join();
+}
+void CopyPool::worker() {
+    for (;;) {
+        Job j;
+        {
+            std::unique_lock<std::mutex> l(mu_);
+            cv_.wait(l, [this] { return stop_ || !queue_.empty(); });
+            if (queue_.empty()) return;
+            j = queue_.back();
+            queue_.pop_back();
+        }
+        memcpy(j.dst, j.src, j.bytes);
+        {
+            std::lock_guard<std::mutex> l(mu_);
+            if (--outstanding_ == 0) done_cv_.notify_all();
+        }
+    }
+}
+void CopyPool::copy(void* dst, const void* src, size_t bytes) {
+    const size_t part = std::max<size_t>(1 << 20, (bytes / (threads_.size() + 1) + 4095) & ~(size_t)4095);
+    size_t own_off = 0, own_bytes = std::min(part, bytes);
+    {
+        std::lock_guard<std::mutex> l(mu_);
+        for (size_t off = own_bytes; off < bytes; off += part) {
+            queue_.push_back({(char*)dst + off, (const char*)src + off, std::min(part, bytes - off)});
+            outstanding_++;
+        }
+    }
+    cv_.notify_all();
+    memcpy((char*)dst + own_off, (const char*)src + own_off, own_bytes);      // the caller copies the first part
+    std::unique_lock<std::mutex> l(mu_);
+    done_cv_.wait(l, [this] { return outstanding_ == 0; });
+}
+
+bool host_ptr_is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
 // ---------------- error reporting ----------------
 static thread_local char g_err[512] = "";
 
@@ -392,6 +440,43 @@ int Engine::launch_spectrogram(const void* d_iq, uint64_t n_samples, const sa_sp
     return SA_OK;
 }
 
+void Engine::host_copy(void* dst, const void* src, size_t bytes) {
+    if (bytes < (4u << 20)) { memcpy(dst, src, bytes); return; }
+    if (!copy_pool) {
+        const char* ev = getenv("SA_COPY_THREADS");
+        const unsigned hw = std::thread::hardware_concurrency();
+        int n = ev ? atoi(ev) : (int)std::min(16u, std::max(2u, hw - hw / 3));
+        copy_pool = new CopyPool(std::max(1, n - 1));
+    }
+    copy_pool->copy(dst, src, bytes);
+}
+
+int Engine::ensure_staging(Slot& s, size_t in_bytes, size_t out_bytes) {
+    cudaError_t e;
+    if (s.h_in_cap < in_bytes) {
+        if (s.h_in) cudaFreeHost(s.h_in);
+        s.h_in = nullptr; s.h_in_cap = 0;
+        e = cudaHostAlloc(&s.h_in, in_bytes, cudaHostAllocPortable);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaHostAlloc(staging in)");
+        s.h_in_cap = in_bytes;
+    }
+    if (s.h_out_cap < out_bytes) {
+        if (s.h_out) cudaFreeHost(s.h_out);
+        s.h_out = nullptr; s.h_out_cap = 0;
+        e = cudaHostAlloc(&s.h_out, out_bytes, cudaHostAllocPortable);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaHostAlloc(staging out)");
+        s.h_out_cap = out_bytes;
+    }
+    return SA_OK;
+}
+
+int Engine::flush_pending(Slot& s) {
+    if (!s.pending_dst) return SA_OK;
+    host_copy(s.pending_dst, s.h_out, s.pending_bytes);
+    s.pending_dst = nullptr; s.pending_bytes = 0;
+    return SA_OK;
+}
+
 int Engine::ensure_slot(Slot& s, size_t in_bytes, size_t out_bytes) {
     cudaError_t e;
     if (!s.stream) {
@@ -428,21 +513,29 @@ int Engine::spectrogram_host(const void* iq, uint64_t iq_bytes, const sa_spectro
     fpc = std::min<uint64_t>(fpc, p.n_frames);
     const uint64_t in_cap = ((fpc - 1) * p.hop + p.nfft) * bps;
     const uint64_t out_cap = fpc * row_bytes;
+    // pageable buffers (an mmapped file, a Java heap array) go through pinned staging with parallel host copies;
+    // pinned / registered buffers are the DMA source and target themselves
+    const bool in_pinned = host_ptr_is_pinned(iq), out_pinned = host_ptr_is_pinned(out);
     int rc = SA_OK;
     uint64_t c = 0;
     for (uint64_t f0 = 0; f0 < p.n_frames && rc == SA_OK; f0 += fpc, c++) {
         Slot& s = slots[c % kSlots];
         rc = ensure_slot(s, in_cap, out_cap);
         if (rc) break;
+        rc = ensure_staging(s, in_pinned ? 0 : in_cap, out_pinned ? 0 : out_cap);
+        if (rc) break;
         cudaError_t e = cudaStreamSynchronize(s.stream);     // slot buffers free again
         if (e != cudaSuccess) { rc = cuda_fail(e, "slot sync"); break; }
+        flush_pending(s);
         const uint64_t nf = std::min<uint64_t>(fpc, p.n_frames - f0);
         const uint64_t s_begin = p.start_sample + f0 * p.hop;
         uint64_t s_end = s_begin + (nf - 1) * p.hop + p.nfft;
         if (s_end > n_samples) s_end = n_samples;             // frames past EOF become fill rows
         const uint64_t ns = s_end > s_begin ? s_end - s_begin : 0;
         if (ns) {
-            e = cudaMemcpyAsync(s.d_in, (const char*)iq + s_begin * bps, ns * bps, cudaMemcpyHostToDevice, s.stream);
+            const void* src = (const char*)iq + s_begin * bps;
+            if (!in_pinned) { host_copy(s.h_in, src, ns * bps); src = s.h_in; }
+            e = cudaMemcpyAsync(s.d_in, src, ns * bps, cudaMemcpyHostToDevice, s.stream);
             if (e != cudaSuccess) { rc = cuda_fail(e, "H2D"); break; }
         }
         sa_spectrogram_params q = p;
@@ -450,13 +543,17 @@ int Engine::spectrogram_host(const void* iq, uint64_t iq_bytes, const sa_spectro
         q.n_frames = nf;
         rc = launch_spectrogram(s.d_in, ns, q, prec, s.d_out, s.stream);
         if (rc) break;
-        e = cudaMemcpyAsync((char*)out + f0 * row_bytes, s.d_out, nf * row_bytes, cudaMemcpyDeviceToHost, s.stream);
+        void* dst = (char*)out + f0 * row_bytes;
+        if (!out_pinned) { s.pending_dst = dst; s.pending_bytes = nf * row_bytes; dst = s.h_out; }
+        e = cudaMemcpyAsync(dst, s.d_out, nf * row_bytes, cudaMemcpyDeviceToHost, s.stream);
         if (e != cudaSuccess) { rc = cuda_fail(e, "D2H"); break; }
     }
     for (int i = 0; i < kSlots; i++)
         if (slots[i].stream) {
             cudaError_t e = cudaStreamSynchronize(slots[i].stream);
             if (e != cudaSuccess && rc == SA_OK) rc = cuda_fail(e, "pipeline drain");
+            if (rc == SA_OK) flush_pending(slots[i]);
+            slots[i].pending_dst = nullptr;
         }
     return rc;
 }
@@ -470,7 +567,10 @@ Engine::~Engine() {
         if (slots[i].d_in) cudaFree(slots[i].d_in);
         if (slots[i].d_out) cudaFree(slots[i].d_out);
         if (slots[i].stream) cudaStreamDestroy(slots[i].stream);
+        if (slots[i].h_in) cudaFreeHost(slots[i].h_in);
+        if (slots[i].h_out) cudaFreeHost(slots[i].h_out);
     }
+    delete copy_pool;
     for (auto& r : registered) cudaHostUnregister(const_cast<void*>(r));
     for (int i = 0; i < kScratch; i++) if (scratch[i]) cudaFree(scratch[i]);
 }
@@ -590,7 +690,11 @@ int32_t sa_register_host(sa_engine* engine, const void* ptr, uint64_t bytes, int
         cudaGetLastError();
         e = cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterPortable);
     }
-    if (e != cudaSuccess) { cudaGetLastError(); return cuda_fail(e, "cudaHostRegister"); }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(SA_ERR_CUDA, "cudaHostRegister: %s (file-backed mappings cannot be page-locked; unregistered "
+                         "buffers are staged through pinned memory by the engine)", cudaGetErrorString(e));
+    }
     engine->registered.push_back(ptr);
     return SA_OK;
 }

@@ -1,8 +1,11 @@
 // engine_internal.h -- host-side state behind the opaque sa_engine handle.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
+#include <condition_variable>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "../../include/sa_engine.h"
@@ -18,6 +21,7 @@ const SpecKernelInfo* find_spec_kernel(int prec, int n, int dk, int win, int tma
 const LargeKernelInfo* find_large_kernel(int prec, int n, int dk, int win);
 void host_window(int window_id, int n, std::vector<double>& w);
 int dtype_kind(int dtype);
+bool host_ptr_is_pinned(const void* p);     // pinned / registered host memory (DMA-able as is)
 int check_spec_params(const sa_spectrogram_params* p, int* prec_out);   // validates, resolves precision
 void fill_load_params(LoadParams& lp, const void* base, int dtype, int big_endian);
 
@@ -28,6 +32,28 @@ struct Slot {
     cudaStream_t stream = nullptr;
     void* d_in = nullptr;  size_t in_cap = 0;
     void* d_out = nullptr; size_t out_cap = 0;
+    // pinned staging for PAGEABLE host buffers (an mmapped .sigmf-data file cannot be cudaHostRegister'ed)
+    void* h_in = nullptr;  size_t h_in_cap = 0;
+    void* h_out = nullptr; size_t h_out_cap = 0;
+    void* pending_dst = nullptr; size_t pending_bytes = 0;       // result still sitting in h_out
+};
+
+// Worker threads that move bytes between pageable memory and the pinned staging buffers in parallel
+// (one memcpy thread moves 5-10 GB/s; PCIe 5 x16 needs ~50 GB/s per direction).
+class CopyPool {
+public:
+    explicit CopyPool(int workers);
+    ~CopyPool();
+    void copy(void* dst, const void* src, size_t bytes);         // returns when every part has been copied
+private:
+    void worker();
+    struct Job { char* dst; const char* src; size_t bytes; };
+    std::vector<std::thread> threads_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_cv_;
+    std::vector<Job> queue_;
+    size_t outstanding_ = 0;
+    bool stop_ = false;
 };
 
 struct Engine {
@@ -42,6 +68,7 @@ struct Engine {
     std::map<const void*, int> occupancy;            // kernel -> resident CTAs per SM
     std::vector<const void*> registered;             // cudaHostRegister'ed ranges
     Slot slots[kSlots];
+    CopyPool* copy_pool = nullptr;                   // created on first use
     // device workspaces: [0] annotation plan + taps, [1] Welch plan + partial spectra, [2] four-step FFT,
     // [3] canvas / canvas dB rows, [4] signal lists of the packer / series kernels
     void* scratch[kScratch] = {};
@@ -52,6 +79,9 @@ struct Engine {
     int window_table(int window_id, int n, int prec, const void** d_tab);
     int kernel_grid(const void* fn, int cta, size_t smem, int* blocks_per_sm);
     int ensure_slot(Slot& s, size_t in_bytes, size_t out_bytes);
+    int ensure_staging(Slot& s, size_t in_bytes, size_t out_bytes);      // pinned h_in / h_out (0 = not needed)
+    void host_copy(void* dst, const void* src, size_t bytes);            // parallel memcpy (CopyPool)
+    int flush_pending(Slot& s);                                          // h_out -> the caller's pageable buffer
     int ensure_scratch(int which, size_t bytes);
     int root_table(int n, int prec, const void** d_tab);      // W_n^j, j = 0..n-1
     int mid_t1_table(int n, const void** d_tab);              // pass-1 twiddle pairs of spectrogram_mid_kernel

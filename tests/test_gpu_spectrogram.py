@@ -246,3 +246,33 @@ def test_config5_cf64_65536_hann(engine):
     wav = np.concatenate([np.zeros(44, np.uint8), body])
     got = engine.spectrogram(wav[44:], "ci16_le", 1024, 9)
     check_db_parity(got, co.spectrogram(body, "ci16_le", 0, 1024, 1024, "rect", 9))
+
+
+def test_pinned_and_pageable_host_paths_agree(engine, tmp_path):
+    """Pinned / registered buffers are DMA'd directly; pageable ones (numpy arrays, an mmapped .sigmf-data file --
+    cudaHostRegister refuses file-backed mappings) go through the engine's pinned staging ring."""
+    import torch
+    n, nfft, hop = 1 << 21, 1024, 512
+    raw = synth.recording(n, "ci16_le", seed=44)
+    frames = (n - nfft) // hop + 3                                   # two EOF rows
+    a = engine.spectrogram(raw, "ci16_le", nfft, frames, hop=hop, window="hann")            # pageable in / out
+    pin = torch.empty(raw.size, dtype=torch.uint8, pin_memory=True)
+    pin.numpy()[:] = raw
+    out = torch.empty((frames, nfft), dtype=torch.float32, pin_memory=True)
+    b = engine.spectrogram(pin.numpy(), "ci16_le", nfft, frames, hop=hop, window="hann", out=out.numpy())
+    assert np.array_equal(a, b)
+    path = tmp_path / "rec.sigmf-data"
+    path.write_bytes(raw.tobytes())
+    mm = np.memmap(path, dtype=np.uint8, mode="r")
+    c = engine.spectrogram(mm, "ci16_le", nfft, frames, hop=hop, window="hann")
+    assert np.array_equal(a, c)
+    with pytest.raises(EngineError):
+        engine.register_host(mm, read_only=True)                    # file-backed: cannot be page-locked
+    engine.register_host(raw, read_only=False)                      # anonymous memory can
+    d = engine.spectrogram(raw, "ci16_le", nfft, frames, hop=hop, window="hann")
+    engine.unregister_host(raw)
+    assert np.array_equal(a, d)
+    # annotation batch from the mapped file (staged spans)
+    iq_m, psd_m = engine.downconvert_psd_batch(mm, "ci16_le", 1e6, [(1000, 600000, 0.1, 16, False), (5, 40000, -0.2, 4, True)], psd_nfft=1024)
+    iq_p, psd_p = engine.downconvert_psd_batch(pin.numpy(), "ci16_le", 1e6, [(1000, 600000, 0.1, 16, False), (5, 40000, -0.2, 4, True)], psd_nfft=1024)
+    assert all(np.array_equal(x, y) for x, y in zip(iq_m, iq_p)) and np.array_equal(psd_m, psd_p)
