@@ -225,7 +225,8 @@ static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, i
     da.anns = d_anns;
     da.taps = d_taps;
     da.out = d_out_iq;
-    static DcTapParams tp;               // guarded by the engine mutex; copied into the launch by cudaLaunchKernel
+    DcTapParams tp;                      // copied into the launch by cudaLaunchKernel (kernel-parameter bank)
+    tp.h_last = 0.f; tp.down = 0;
     void* args[] = { &da, &tp };
     for (uint32_t g0 = 0; g0 < n_ann;) {
         uint32_t g1 = g0 + 1;
