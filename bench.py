@@ -53,6 +53,9 @@ class ClockSampler(threading.Thread):
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            # warm the two queries of the sampling loop (the first call of each is tens of ms)
+            pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
         except Exception:
             self.nv = None
 
@@ -73,7 +76,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.001)
 
     def summary(self):
         s = sorted(self.samples)
@@ -207,10 +210,10 @@ def main():
         step()
     barrier()
     sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = eng.kernel_launches
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
+    sampler.start()
     ev[0].record()
     for i in range(args.steps):
         step()

@@ -16,10 +16,6 @@
 #pragma once
 #include "spectrogram_kernel.cuh"
 
-#ifndef SA_MID_REC1
-#define SA_MID_REC1 0
-#endif
-
 namespace sa {
 
 template <int N> struct MidGeo {
@@ -103,26 +99,57 @@ __device__ __forceinline__ void mid_load_frame(const LoadParams& lp, const char*
     if constexpr (M + 1 < G::R0) mid_load_frame<DK, N, SWAP, M + 1>(lp, frame_base, t, v);
 }
 
-template <int N, int DK, bool WIN>
-__global__ void __launch_bounds__(MidGeo<N>::CTA, MidGeo<N>::MINB)
-spectrogram_mid_kernel(const SpecArgs a) {
+// The three passes of the small-radix-first plan on the registers of one frame.  In: v[i + S*m] = sample
+// m*(N/R0) + S*t + i (already decoded); out: v[q] = X[t + TPF*q].  `sm` is the frame's exchange buffer, `win` the
+// thread's window row (pair order), `t1_row` = pass-1 twiddle pairs + (t mod R0), seed = (W_N^t, W_N^(16 t)).
+template <int N, bool WIN>
+__device__ __forceinline__ void mid_fft(float2 (&v)[32], const int t, const int fl, float2* __restrict__ sm,
+                                        const float* __restrict__ win, const TwPair<float>* __restrict__ t1_row,
+                                        const TwSeed<float>& seed) {
     using G = MidGeo<N>;
     constexpr int P = 32, R0 = G::R0, S = G::S, TPF = G::TPF, FPC = G::FPC;
-    constexpr int bps = bytes_per_iq_kind<DK>();
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int fl = threadIdx.x / TPF, t = threadIdx.x % TPF;
-    float2* sm = reinterpret_cast<float2*>(smem_raw) + (size_t)fl * G::SM_ELEMS;
-    TwPair<float>* t1 = reinterpret_cast<TwPair<float>*>(smem_raw + G::EX_BYTES);
-    float* wsm = reinterpret_cast<float*>(smem_raw + G::EX_BYTES + G::T1_BYTES);
-
-    // tables: pass-1 twiddle pairs [m' < 16][r < R0]; window rows in first-stage pair order
+    // pass 0: S radix-R0 butterflies on v[i + S*m]
+    RadixAll<float, R0, S, P, WIN ? MUL_REAL : MUL_NONE, false, 0>::run(v, win, nullptr, 0, seed);
+    mid_sync<TPF, FPC>(fl);                  // the previous frame's exchange has been read back
     {
-        const float4* src = reinterpret_cast<const float4*>(a.twiddle);
-        float4* dst = reinterpret_cast<float4*>(t1);
-        for (int i = threadIdx.x; i < 16 * R0; i += G::CTA) dst[i] = __ldg(&src[i]);
+        float2* dst = sm + 33 * t;           // outputs j*R0 + m, j = S*t + i: the block [32 t, 32 t + 32)
+#pragma unroll
+        for (int i = 0; i < S; i++)
+#pragma unroll
+            for (int m = 0; m < R0; m++) dst[i * R0 + m] = v[i + S * m];
     }
+    mid_sync<TPF, FPC>(fl);
+#pragma unroll
+    for (int q = 0; q < P; q++) v[q] = sm[mid_pad(t) + q * (TPF + TPF / 32)];
+
+    // pass 1: radix 32, Ns = R0
+    radix_fft<float, 32, 1, 0, P, MUL_CPX, true>(v, nullptr, t1_row, R0, seed);
+    mid_sync<TPF, FPC>(fl);
+    {
+        float2* dst = sm + (t / R0) * (33 * R0) + (t % R0);
+#pragma unroll
+        for (int m = 0; m < 32; m++) dst[m * R0 + ((m * R0) >> 5)] = v[m];
+    }
+    mid_sync<TPF, FPC>(fl);
+#pragma unroll
+    for (int q = 0; q < P; q++) v[q] = sm[mid_pad(t) + q * (TPF + TPF / 32)];
+
+    // pass 2: radix 32, Ns = 32 R0 = TPF, twiddle W_N^(t m) by recurrence
+    radix_fft<float, 32, 1, 0, P, MUL_REC, false>(v, nullptr, nullptr, 0, seed);
+}
+
+// Copies the pass-1 twiddle pairs and (WIN) the window rows in first-stage pair order into shared memory;
+// the caller synchronises the CTA afterwards.
+template <int N, bool WIN>
+__device__ __forceinline__ void mid_setup_tables(const void* __restrict__ t1_global, const void* __restrict__ window,
+                                                 TwPair<float>* __restrict__ t1, float* __restrict__ wsm) {
+    using G = MidGeo<N>;
+    constexpr int P = 32, R0 = G::R0, S = G::S;
+    const float4* src = reinterpret_cast<const float4*>(t1_global);
+    float4* dst = reinterpret_cast<float4*>(t1);
+    for (int i = threadIdx.x; i < 16 * R0; i += G::CTA) dst[i] = __ldg(&src[i]);
     if constexpr (WIN) {
-        const float* w = reinterpret_cast<const float*>(a.window);
+        const float* w = reinterpret_cast<const float*>(window);
         for (int i = threadIdx.x; i < N; i += G::CTA) {
             // sample i = m*(N/R0) + S*tt + ii  ->  register e = ii + S*m of thread tt
             const int m = i / (N / R0), rem = i % (N / R0), tt = rem / S, ii = rem % S;
@@ -131,6 +158,22 @@ spectrogram_mid_kernel(const SpecArgs a) {
             wsm[tt * G::WROW + slot] = __ldg(&w[i]);
         }
     }
+}
+
+template <int N, int DK, bool WIN>
+__global__ void __launch_bounds__(MidGeo<N>::CTA, MidGeo<N>::MINB)
+spectrogram_mid_kernel(const SpecArgs a) {
+    using G = MidGeo<N>;
+    constexpr int P = 32, R0 = G::R0, TPF = G::TPF, FPC = G::FPC;
+    constexpr int bps = bytes_per_iq_kind<DK>();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int fl = threadIdx.x / TPF, t = threadIdx.x % TPF;
+    float2* sm = reinterpret_cast<float2*>(smem_raw) + (size_t)fl * G::SM_ELEMS;
+    TwPair<float>* t1 = reinterpret_cast<TwPair<float>*>(smem_raw + G::EX_BYTES);
+    float* wsm = reinterpret_cast<float*>(smem_raw + G::EX_BYTES + G::T1_BYTES);
+
+    // tables: pass-1 twiddle pairs [m' < 16][r < R0]; window rows in first-stage pair order
+    mid_setup_tables<N, WIN>(a.twiddle, a.window, t1, wsm);
     __syncthreads();
     const float* win = wsm + t * G::WROW;
     TwSeed<float> seed;
@@ -139,17 +182,7 @@ spectrogram_mid_kernel(const SpecArgs a) {
         seed.om = __ldg(&root[t]);
         seed.oh = __ldg(&root[(16 * t) & (N - 1)]);
     }
-#if !SA_MID_REC1
     const TwPair<float>* t1_row = t1 + (t % R0);
-#else
-    TwSeed<float> seed1;                         // pass-1 twiddles W_{32 R0}^{(t mod R0) m} by recurrence as well
-    {
-        const float2* root = reinterpret_cast<const float2*>(a.aux);
-        seed1.om = __ldg(&root[32 * (t % R0)]);
-        seed1.oh = __ldg(&root[(512 * (t % R0)) & (N - 1)]);
-    }
-    (void)t1;
-#endif
 
     const long long n_blocks = (a.n_frames + FPC - 1) / FPC;
     const int new_bytes = (int)(a.hop < N ? a.hop : N) * bps;
@@ -173,38 +206,7 @@ spectrogram_mid_kernel(const SpecArgs a) {
         if (a.lp.swap) mid_load_frame<DK, N, true>(a.lp, base + s0 * bps, t, v);
         else           mid_load_frame<DK, N, false>(a.lp, base + s0 * bps, t, v);
 
-        // pass 0: S radix-R0 butterflies on v[i + S*m]
-        RadixAll<float, R0, S, P, WIN ? MUL_REAL : MUL_NONE, false, 0>::run(v, win, nullptr, 0, seed);
-        mid_sync<TPF, FPC>(fl);                  // the previous frame's exchange has been read back
-        {
-            float2* dst = sm + 33 * t;           // outputs j*R0 + m, j = S*t + i: the block [32 t, 32 t + 32)
-#pragma unroll
-            for (int i = 0; i < S; i++)
-#pragma unroll
-                for (int m = 0; m < R0; m++) dst[i * R0 + m] = v[i + S * m];
-        }
-        mid_sync<TPF, FPC>(fl);
-#pragma unroll
-        for (int q = 0; q < P; q++) v[q] = sm[mid_pad(t) + q * (TPF + TPF / 32)];
-
-        // pass 1: radix 32, Ns = R0
-#if SA_MID_REC1
-        radix_fft<float, 32, 1, 0, P, MUL_REC, false>(v, nullptr, nullptr, 0, seed1);
-#else
-        radix_fft<float, 32, 1, 0, P, MUL_CPX, true>(v, nullptr, t1_row, R0, seed);
-#endif
-        mid_sync<TPF, FPC>(fl);
-        {
-            float2* dst = sm + (t / R0) * (33 * R0) + (t % R0);
-#pragma unroll
-            for (int m = 0; m < 32; m++) dst[m * R0 + ((m * R0) >> 5)] = v[m];
-        }
-        mid_sync<TPF, FPC>(fl);
-#pragma unroll
-        for (int q = 0; q < P; q++) v[q] = sm[mid_pad(t) + q * (TPF + TPF / 32)];
-
-        // pass 2: radix 32, Ns = 32 R0 = TPF, twiddle W_N^(t m) by recurrence
-        radix_fft<float, 32, 1, 0, P, MUL_REC, false>(v, nullptr, nullptr, 0, seed);
+        mid_fft<N, WIN>(v, t, fl, sm, win, t1_row, seed);
         store_row<float, N>(a, frame, t, v);
     }
 }
