@@ -317,7 +317,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic, "peak_kind": peak_kind,
                          "alg_bytes_per_launch": int(alg_bytes), "kernel_ms": round(kern_ms, 4),
-                         "kernel": "spectrogram_kernel<float,1024,cf32,window>"},
+                         "kernel": "spectrogram_tma_kernel<float,1024,cf32,window>"},
             "clocks": sampler.summary(),
             "gpu_launches": int(launches),
         }
