@@ -13,6 +13,10 @@
 #pragma once
 #include "spectrogram_kernel.cuh"
 
+#ifndef SA_TMA_BLOCKS_PER_STEP
+#define SA_TMA_BLOCKS_PER_STEP 1
+#endif
+
 namespace sa {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -79,13 +83,17 @@ spectrogram_tma_kernel(const SpecArgs a) {
         tma_load_1d(dst, base + (a.start_sample + frame * a.hop) * (long long)sizeof(raw_t), FRAME_BYTES, bar);
     };
 
-    long long fb = blockIdx.x;
+    // a CTA takes SA_TMA_BLOCKS_PER_STEP adjacent frame blocks before it strides by the grid
+    constexpr long long K = SA_TMA_BLOCKS_PER_STEP;
+    auto adv = [&](long long b) { return ((b + 1) % K != 0) ? b + 1 : b + 1 + ((long long)gridDim.x - 1) * K; };
+    long long fb = (long long)blockIdx.x * K;
     if (fb < n_blocks && readable_f(frame_of(fb)) && t == 0) issue(frame_of(fb));
     uint32_t parity = 0;
-    for (; fb < n_blocks; fb += gridDim.x) {
+    for (; fb < n_blocks; fb = adv(fb)) {
         const long long frame = frame_of(fb);
-        const long long next = frame_of(fb + gridDim.x);
-        const bool next_readable = (fb + gridDim.x < n_blocks) && readable_f(next);
+        const long long nfb = adv(fb);
+        const long long next = frame_of(nfb);
+        const bool next_readable = (nfb < n_blocks) && readable_f(next);
         if (frame >= a.n_frames) continue;            // warp-uniform; a later block cannot be in range either
         if (!readable_f(frame)) {                     // EOF row, no copy was issued for it
             store_fill<T, N>(a, frame, t);
