@@ -9,6 +9,10 @@
 #pragma once
 #include "decode.cuh"
 
+#ifndef SA_STORE_STREAMING
+#define SA_STORE_STREAMING 0
+#endif
+
 namespace sa {
 
 enum { OUT_F32_DB = 0, OUT_F64_DB = 1, OUT_RGBA8 = 2 };
@@ -189,7 +193,13 @@ __device__ __forceinline__ void store_row(const SpecArgs& a, const long long fra
     if (a.out_kind == OUT_F32_DB) {
         float* o = reinterpret_cast<float*>(a.out) + row;
 #pragma unroll
-        for (int q = 0; q < P; q++) o[(k0 + TPF * q) & (N - 1)] = (float)db[q];
+        for (int q = 0; q < P; q++) {
+#if SA_STORE_STREAMING
+            __stcs(&o[(k0 + TPF * q) & (N - 1)], (float)db[q]);      // rows are never re-read: evict-first in L2
+#else
+            o[(k0 + TPF * q) & (N - 1)] = (float)db[q];
+#endif
+        }
     } else if (a.out_kind == OUT_F64_DB) {
         double* o = reinterpret_cast<double*>(a.out) + row;
 #pragma unroll

@@ -13,6 +13,9 @@
 #pragma once
 #include "spectrogram_kernel.cuh"
 
+#ifndef SA_TMA_EVICT_LAST
+#define SA_TMA_EVICT_LAST 0
+#endif
 #ifndef SA_TMA_BLOCKS_PER_STEP
 #define SA_TMA_BLOCKS_PER_STEP 1
 #endif
@@ -37,8 +40,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+#if SA_TMA_EVICT_LAST
+    // overlapping frames read every sample twice: ask L2 to keep the lines until the second read
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+#else
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+#endif
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
