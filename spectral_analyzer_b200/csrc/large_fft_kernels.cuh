@@ -13,6 +13,10 @@
 #pragma once
 #include "spectrogram_kernel.cuh"
 
+#ifndef SA_LARGE_COLS_MINB
+#define SA_LARGE_COLS_MINB 3
+#endif
+
 namespace sa {
 
 constexpr int kLargeC = 16;      // columns / rows per CTA
@@ -77,7 +81,7 @@ __device__ __forceinline__ void large_cols_body(const LargeArgs& a, const long l
 }
 
 template <typename T, int N1, int N2, int DK, bool WIN>
-__global__ void __launch_bounds__(kLargeC * Geo<T, N1>::TPF)
+__global__ void __launch_bounds__(kLargeC * Geo<T, N1>::TPF, sizeof(T) == 4 ? SA_LARGE_COLS_MINB : 2)
 large_cols_kernel(const LargeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     large_cols_body<T, N1, N2, DK, WIN>(a, a.frame0 + blockIdx.y, reinterpret_cast<cpx<T>*>(a.ws) + (size_t)blockIdx.y * (N1 * N2),
