@@ -413,12 +413,19 @@ int Engine::launch_spectrogram(const void* d_iq, uint64_t n_samples, const sa_sp
     static const bool no_tma = getenv("SA_NO_TMA") != nullptr;      // A/B switches for the ablations in DESIGN.md
     static const bool no_mid = getenv("SA_NO_MID") != nullptr;
     const SpecKernelInfo* k = (aligned && !no_tma) ? find_spec_kernel(prec, (int)p.nfft, dk, win, 1) : nullptr;
-    if (!k && aligned && !no_mid) k = find_spec_kernel(prec, (int)p.nfft, dk, win, 2);     // small-radix-first plan
+    if (!k && aligned && !no_mid) {                                                        // small-radix-first plan
+        // the asynchronously staged variant where it measured faster on B200 (tools/mid_pf_matrix.py): 2048 (8 frames
+        // per CTA) and 16384 (one frame owns the SM) gain 6-19 %, 4096 / 8192 lose up to 19 %.  SA_MID_PF=all|none overrides.
+        static const char* pf_env = getenv("SA_MID_PF");
+        const bool pf = pf_env ? (strcmp(pf_env, "all") == 0) : (p.nfft == 2048 || p.nfft == 16384);
+        if (pf) k = find_spec_kernel(prec, (int)p.nfft, dk, win, 3);
+        if (!k) k = find_spec_kernel(prec, (int)p.nfft, dk, win, 2);
+    }
     if (!k) k = find_spec_kernel(prec, (int)p.nfft, dk, win, 0);
     if (!k) return set_error(SA_ERR_UNSUPPORTED, "no kernel for nfft %u precision %s dtype %d", p.nfft,
                              prec == SA_PREC_F64 ? "f64" : "f32", p.dtype);
     int rc;
-    if (k->tma == 2) {
+    if (k->tma >= 2) {
         rc = mid_t1_table(k->n, &a.twiddle);
         if (rc) return rc;
         rc = root_table(k->n, prec, &a.aux);

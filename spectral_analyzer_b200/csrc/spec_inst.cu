@@ -30,12 +30,19 @@ struct Registrar {
 #endif
 #if SA_INST_N >= 2048
         // small-radix-first plan with 128-bit loads, taken when the frames are 16-byte aligned
-        register_spec_kernel(make_spec_mid_info<SA_INST_N, DK_CF32, false>());
-        register_spec_kernel(make_spec_mid_info<SA_INST_N, DK_CF32, true>());
-        register_spec_kernel(make_spec_mid_info<SA_INST_N, DK_CI16, false>());
-        register_spec_kernel(make_spec_mid_info<SA_INST_N, DK_CI16, true>());
-        register_spec_kernel(make_spec_mid_info<SA_INST_N, DK_C8, false>());
-        register_spec_kernel(make_spec_mid_info<SA_INST_N, DK_C8, true>());
+        register_spec_kernel(make_spec_mid_info<SA_INST_N, DK_CF32, false, false>());
+        register_spec_kernel(make_spec_mid_info<SA_INST_N, DK_CF32, true, false>());
+        register_spec_kernel(make_spec_mid_info<SA_INST_N, DK_CI16, false, false>());
+        register_spec_kernel(make_spec_mid_info<SA_INST_N, DK_CI16, true, false>());
+        register_spec_kernel(make_spec_mid_info<SA_INST_N, DK_C8, false, false>());
+        register_spec_kernel(make_spec_mid_info<SA_INST_N, DK_C8, true, false>());
+        // ... and with the next frame staged asynchronously (cp.async) under pass 2 and the epilogue
+        register_spec_kernel(make_spec_mid_info<SA_INST_N, DK_CF32, false, true>());
+        register_spec_kernel(make_spec_mid_info<SA_INST_N, DK_CF32, true, true>());
+        register_spec_kernel(make_spec_mid_info<SA_INST_N, DK_CI16, false, true>());
+        register_spec_kernel(make_spec_mid_info<SA_INST_N, DK_CI16, true, true>());
+        register_spec_kernel(make_spec_mid_info<SA_INST_N, DK_C8, false, true>());
+        register_spec_kernel(make_spec_mid_info<SA_INST_N, DK_C8, true, true>());
 #endif
 #else
         // FP64 arithmetic (cf64 input, or any input when the caller asks for SA_PREC_F64);

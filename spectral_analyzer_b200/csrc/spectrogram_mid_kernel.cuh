@@ -62,24 +62,10 @@ __device__ __forceinline__ uint32_t ldg_stream4(const void* p) {
     return r;
 }
 
-// S consecutive samples starting at p -> v[OFF + i], i < S (decode of decode.cuh, same values bit for bit)
+// decode of S consecutive samples held as raw words -> v[OFF + i], i < S (decode.cuh, same values bit for bit)
 template <int DK, int S, bool SWAP, int OFF>
-__device__ __forceinline__ void mid_load_slice(const LoadParams& lp, const char* __restrict__ p, float2 (&v)[32]) {
-    constexpr int BYTES = S * bytes_per_iq_kind<DK>();
-    static_assert(BYTES >= 4 && BYTES % 4 == 0, "slice must be whole words");
-    uint32_t w[BYTES / 4];
-    if constexpr (BYTES >= 16) {
-#pragma unroll
-        for (int i = 0; i < BYTES / 16; i++) {
-            const uint4 x = ldg_stream16(p + 16 * i);
-            w[4 * i] = x.x; w[4 * i + 1] = x.y; w[4 * i + 2] = x.z; w[4 * i + 3] = x.w;
-        }
-    } else if constexpr (BYTES == 8) {
-        const uint2 x = ldg_stream8(p);
-        w[0] = x.x; w[1] = x.y;
-    } else {
-        w[0] = ldg_stream4(p);
-    }
+__device__ __forceinline__ void mid_decode_words(const LoadParams& lp, const uint32_t (&w)[S * bytes_per_iq_kind<DK>() / 4],
+                                                 float2 (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < S; i++) {
         if constexpr (DK == DK_CF32) {
@@ -98,6 +84,27 @@ __device__ __forceinline__ void mid_load_slice(const LoadParams& lp, const char*
     }
 }
 
+// S consecutive samples starting at p (global memory, streaming loads) -> v[OFF + i]
+template <int DK, int S, bool SWAP, int OFF>
+__device__ __forceinline__ void mid_load_slice(const LoadParams& lp, const char* __restrict__ p, float2 (&v)[32]) {
+    constexpr int BYTES = S * bytes_per_iq_kind<DK>();
+    static_assert(BYTES >= 4 && BYTES % 4 == 0, "slice must be whole words");
+    uint32_t w[BYTES / 4];
+    if constexpr (BYTES >= 16) {
+#pragma unroll
+        for (int i = 0; i < BYTES / 16; i++) {
+            const uint4 x = ldg_stream16(p + 16 * i);
+            w[4 * i] = x.x; w[4 * i + 1] = x.y; w[4 * i + 2] = x.z; w[4 * i + 3] = x.w;
+        }
+    } else if constexpr (BYTES == 8) {
+        const uint2 x = ldg_stream8(p);
+        w[0] = x.x; w[1] = x.y;
+    } else {
+        w[0] = ldg_stream4(p);
+    }
+    mid_decode_words<DK, S, SWAP, OFF>(lp, w, v);
+}
+
 template <int DK, int N, bool SWAP, int M = 0>
 __device__ __forceinline__ void mid_load_frame(const LoadParams& lp, const char* __restrict__ frame_base, const int t,
                                                float2 (&v)[32]) {
@@ -107,13 +114,68 @@ __device__ __forceinline__ void mid_load_frame(const LoadParams& lp, const char*
     if constexpr (M + 1 < G::R0) mid_load_frame<DK, N, SWAP, M + 1>(lp, frame_base, t, v);
 }
 
+// ---- asynchronous staging of the NEXT frame (cp.async, one 16/8/4-byte chunk per thread and step) ----
+// Chunk c = m*CH + i of thread t lands at byte ((c*TPF) + t)*CHB of the frame's exchange buffer: consecutive threads,
+// consecutive chunks -> conflict-free both for the asynchronous writes and for the 128-bit reads of the same
+// thread one frame later (a thread only ever reads back what it staged itself: no barrier on that side).
+template <int DK, int N> struct MidStage {
+    using G = MidGeo<N>;
+    static constexpr int bps = bytes_per_iq_kind<DK>();
+    static constexpr int BYTES = G::S * bps;                 // bytes of one slice per thread
+    static constexpr int CHB = BYTES >= 16 ? 16 : BYTES;     // chunk bytes
+    static constexpr int CH = BYTES / CHB;                   // chunks per slice
+    static_assert((size_t)N * bps <= (size_t)G::SM_ELEMS * sizeof(float2), "raw frame fits the exchange buffer");
+};
+
+template <int CHB> __device__ __forceinline__ void cp_async_chunk(uint32_t dst, const void* src) {
+    if constexpr (CHB == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    else if constexpr (CHB == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+
+template <int DK, int N>
+__device__ __forceinline__ void mid_stage_frame(const char* __restrict__ frame_base, const int t, const uint32_t sm_addr) {
+    using G = MidGeo<N>;
+    using ST = MidStage<DK, N>;
+#pragma unroll
+    for (int m = 0; m < G::R0; m++)
+#pragma unroll
+        for (int i = 0; i < ST::CH; i++)
+            cp_async_chunk<ST::CHB>(sm_addr + (uint32_t)(((m * ST::CH + i) * G::TPF + t) * ST::CHB),
+                                    frame_base + ((size_t)m * (N / G::R0) + (size_t)G::S * t) * ST::bps + i * ST::CHB);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+template <int DK, int N, bool SWAP, int M = 0>
+__device__ __forceinline__ void mid_decode_staged(const LoadParams& lp, const unsigned char* __restrict__ stage, const int t,
+                                                  float2 (&v)[32]) {
+    using G = MidGeo<N>;
+    using ST = MidStage<DK, N>;
+    uint32_t w[ST::BYTES / 4];
+#pragma unroll
+    for (int i = 0; i < ST::CH; i++) {
+        const unsigned char* p = stage + (size_t)((M * ST::CH + i) * G::TPF + t) * ST::CHB;
+        if constexpr (ST::CHB == 16) {
+            const uint4 x = *reinterpret_cast<const uint4*>(p);
+            w[4 * i] = x.x; w[4 * i + 1] = x.y; w[4 * i + 2] = x.z; w[4 * i + 3] = x.w;
+        } else if constexpr (ST::CHB == 8) {
+            const uint2 x = *reinterpret_cast<const uint2*>(p);
+            w[0] = x.x; w[1] = x.y;
+        } else {
+            w[0] = *reinterpret_cast<const uint32_t*>(p);
+        }
+    }
+    mid_decode_words<DK, G::S, SWAP, G::S * M>(lp, w, v);
+    if constexpr (M + 1 < G::R0) mid_decode_staged<DK, N, SWAP, M + 1>(lp, stage, t, v);
+}
+
 // The three passes of the small-radix-first plan on the registers of one frame.  In: v[i + S*m] = sample
 // m*(N/R0) + S*t + i (already decoded); out: v[q] = X[t + TPF*q].  `sm` is the frame's exchange buffer, `win` the
 // thread's window row (pair order), `t1_row` = pass-1 twiddle pairs + (t mod R0), seed = (W_N^t, W_N^(16 t)).
 template <int N, bool WIN>
-__device__ __forceinline__ void mid_fft(float2 (&v)[32], const int t, const int fl, float2* __restrict__ sm,
-                                        const float* __restrict__ win, const TwPair<float>* __restrict__ t1_row,
-                                        const TwSeed<float>& seed) {
+__device__ __forceinline__ void mid_fft_front(float2 (&v)[32], const int t, const int fl, float2* __restrict__ sm,
+                                              const float* __restrict__ win, const TwPair<float>* __restrict__ t1_row,
+                                              const TwSeed<float>& seed) {
     using G = MidGeo<N>;
     constexpr int P = 32, R0 = G::R0, S = G::S, TPF = G::TPF, FPC = G::FPC;
     // pass 0: S radix-R0 butterflies on v[i + S*m]
@@ -141,9 +203,19 @@ __device__ __forceinline__ void mid_fft(float2 (&v)[32], const int t, const int 
     mid_sync<TPF, FPC>(fl);
 #pragma unroll
     for (int q = 0; q < P; q++) v[q] = sm[mid_pad(t) + q * (TPF + TPF / 32)];
+}
 
-    // pass 2: radix 32, Ns = 32 R0 = TPF, twiddle W_N^(t m) by recurrence
-    radix_fft<float, 32, 1, 0, P, MUL_REC, false>(v, nullptr, nullptr, 0, seed);
+// pass 2 (no shared memory): radix 32, Ns = 32 R0 = TPF, twiddle W_N^(t m) by recurrence
+__device__ __forceinline__ void mid_fft_back(float2 (&v)[32], const TwSeed<float>& seed) {
+    radix_fft<float, 32, 1, 0, 32, MUL_REC, false>(v, nullptr, nullptr, 0, seed);
+}
+
+template <int N, bool WIN>
+__device__ __forceinline__ void mid_fft(float2 (&v)[32], const int t, const int fl, float2* __restrict__ sm,
+                                        const float* __restrict__ win, const TwPair<float>* __restrict__ t1_row,
+                                        const TwSeed<float>& seed) {
+    mid_fft_front<N, WIN>(v, t, fl, sm, win, t1_row, seed);
+    mid_fft_back(v, seed);
 }
 
 // Copies the pass-1 twiddle pairs and (WIN) the window rows in first-stage pair order into shared memory;
@@ -168,7 +240,10 @@ __device__ __forceinline__ void mid_setup_tables(const void* __restrict__ t1_glo
     }
 }
 
-template <int N, int DK, bool WIN>
+// PF: the raw bytes of a slot's NEXT frame are staged asynchronously into the (then idle) exchange buffer while
+// pass 2 and the epilogue of the current frame run, so no global-load latency sits on the per-frame critical
+// path (it matters most where one or two frames occupy a whole SM: nfft 8192 / 16384).
+template <int N, int DK, bool WIN, bool PF>
 __global__ void __launch_bounds__(MidGeo<N>::CTA, MidGeo<N>::MINB)
 spectrogram_mid_kernel(const SpecArgs a) {
     using G = MidGeo<N>;
@@ -195,11 +270,17 @@ spectrogram_mid_kernel(const SpecArgs a) {
     const long long n_blocks = (a.n_frames + FPC - 1) / FPC;
     const int new_bytes = (int)(a.hop < N ? a.hop : N) * bps;
     const char* base = reinterpret_cast<const char*>(a.lp.base);
+    const uint32_t sm_addr = (uint32_t)__cvta_generic_to_shared(sm);
+    auto readable_f = [&](long long fr) { return fr < a.n_frames && a.start_sample + fr * a.hop + N <= a.n_samples; };
+    if constexpr (PF) {       // prologue: stage this slot's first frame
+        const long long f0 = (long long)blockIdx.x * FPC + fl;
+        if (readable_f(f0)) mid_stage_frame<DK, N>(base + (a.start_sample + f0 * a.hop) * bps, t, sm_addr);
+    }
     for (long long fb = blockIdx.x; fb < n_blocks; fb += gridDim.x) {
         const long long frame = fb * FPC + fl;
         const long long s0 = a.start_sample + frame * a.hop;              // MainController.java:984
-        {   // pull the new samples of this slot's NEXT frame into L2 while the current one is transformed
-            const long long nf = frame + (long long)gridDim.x * FPC;
+        const long long nf = frame + (long long)gridDim.x * FPC;          // this slot's next frame
+        if constexpr (!PF) {   // pull the new samples of the NEXT frame into L2 while the current one is transformed
             const long long ns_end = a.start_sample + nf * a.hop + N;
             if (nf < a.n_frames && ns_end <= a.n_samples) {
                 const char* pf = base + ns_end * bps - new_bytes;
@@ -208,26 +289,44 @@ spectrogram_mid_kernel(const SpecArgs a) {
             }
         }
         if (frame >= a.n_frames) continue;                                // uniform over the frame's threads
-        if (s0 + N > a.n_samples) { store_fill<float, N>(a, frame, t); continue; }   // :987, :994-998
+        if (s0 + N > a.n_samples) {                                       // :987, :994-998
+            store_fill<float, N>(a, frame, t);
+            if constexpr (PF) {   // nothing of this slot is in flight and every reader of the buffer is past its reads
+                if (readable_f(nf)) mid_stage_frame<DK, N>(base + (a.start_sample + nf * a.hop) * bps, t, sm_addr);
+            }
+            continue;
+        }
 
         float2 v[P];
-        if (a.lp.swap) mid_load_frame<DK, N, true>(a.lp, base + s0 * bps, t, v);
-        else           mid_load_frame<DK, N, false>(a.lp, base + s0 * bps, t, v);
+        if constexpr (PF) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");           // this thread's own chunks have landed
+            const unsigned char* stage = reinterpret_cast<const unsigned char*>(sm);
+            if (a.lp.swap) mid_decode_staged<DK, N, true>(a.lp, stage, t, v);
+            else           mid_decode_staged<DK, N, false>(a.lp, stage, t, v);
+        } else {
+            if (a.lp.swap) mid_load_frame<DK, N, true>(a.lp, base + s0 * bps, t, v);
+            else           mid_load_frame<DK, N, false>(a.lp, base + s0 * bps, t, v);
+        }
 
-        mid_fft<N, WIN>(v, t, fl, sm, win, t1_row, seed);
+        mid_fft_front<N, WIN>(v, t, fl, sm, win, t1_row, seed);
+        if constexpr (PF) {
+            mid_sync<TPF, FPC>(fl);                                        // the exchange buffer has been read back by everyone
+            if (readable_f(nf)) mid_stage_frame<DK, N>(base + (a.start_sample + nf * a.hop) * bps, t, sm_addr);
+        }
+        mid_fft_back(v, seed);
         store_row<float, N>(a, frame, t, v);
     }
 }
 
-template <int N, int DK, bool WIN>
+template <int N, int DK, bool WIN, bool PF>
 SpecKernelInfo make_spec_mid_info() {
     using G = MidGeo<N>;
     SpecKernelInfo k;
-    k.fn = (const void*)&spectrogram_mid_kernel<N, DK, WIN>;
+    k.fn = (const void*)&spectrogram_mid_kernel<N, DK, WIN, PF>;
     k.prec = 1; k.n = N; k.dk = DK; k.win = WIN ? 1 : 0;
     k.cta = G::CTA; k.fpc = G::FPC; k.minb = G::MINB;
     k.smem = G::EX_BYTES + G::T1_BYTES + (WIN ? G::WIN_BYTES : 0);
-    k.p = 32; k.np = 3; k.tma = 2;
+    k.p = 32; k.np = 3; k.tma = PF ? 3 : 2;
     k.radix[0] = G::R0; k.radix[1] = 32; k.radix[2] = 32; k.radix[3] = 1;
     return k;
 }
