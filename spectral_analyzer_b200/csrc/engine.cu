@@ -415,9 +415,10 @@ int Engine::launch_spectrogram(const void* d_iq, uint64_t n_samples, const sa_sp
     const SpecKernelInfo* k = (aligned && !no_tma) ? find_spec_kernel(prec, (int)p.nfft, dk, win, 1) : nullptr;
     if (!k && aligned && !no_mid) {                                                        // small-radix-first plan
         // the asynchronously staged variant where it measured faster on B200 (tools/mid_pf_matrix.py): 2048 (8 frames
-        // per CTA) and 16384 (one frame owns the SM) gain 6-19 %, 4096 / 8192 lose up to 19 %.  SA_MID_PF=all|none overrides.
+        // per CTA) and 16384 (one frame owns the SM) gain 6-19 %, 4096 (4 frames per CTA) 0-10 %, 8192 loses up to 19 %.
+        // SA_MID_PF=all|none overrides.
         static const char* pf_env = getenv("SA_MID_PF");
-        const bool pf = pf_env ? (strcmp(pf_env, "all") == 0) : (p.nfft == 2048 || p.nfft == 16384);
+        const bool pf = pf_env ? (strcmp(pf_env, "all") == 0) : (p.nfft != 8192);
         if (pf) k = find_spec_kernel(prec, (int)p.nfft, dk, win, 3);
         if (!k) k = find_spec_kernel(prec, (int)p.nfft, dk, win, 2);
     }

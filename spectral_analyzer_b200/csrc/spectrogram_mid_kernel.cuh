@@ -20,14 +20,15 @@
 #define SA_CTA_MID 512
 #endif
 #ifndef SA_CTA_MID_4096
-#define SA_CTA_MID_4096 128
+#define SA_CTA_MID_4096 512
 #endif
 
 namespace sa {
 
 template <int N> struct MidGeo {
     static constexpr int P = 32, R0 = N / 1024, S = P / R0, TPF = N / P;
-    // FPC consecutive frames per CTA step (16 warps; measured per size: 2048 -> 512 threads (C4 4.85 -> 4.76 ms); 4096 -> 128 threads (C2 2.53 ms; 256: 2.60, 512: 2.63))
+    // FPC consecutive frames per CTA step (16 warps; measured per size: 2048 -> 512 threads (C4 4.85 -> 4.76 ms); 4096 -> 512 threads together with the
+    // staged variant (C2 417 -> 420, 50 % overlap 189 -> 210 Gsamples/s; without staging 128 threads were best))
     static constexpr int CTA = (N == 4096) ? SA_CTA_MID_4096 : (TPF > SA_CTA_MID ? TPF : SA_CTA_MID);
     static constexpr int FPC = CTA / TPF;
     static constexpr int MINB = 512 / CTA;

@@ -9,7 +9,7 @@ import spectral_analyzer_b200 as sa                      # noqa: E402
 from bench_configs import spectrogram_case               # noqa: E402
 
 eng = sa.Engine(0)
-for nfft in (2048, 4096, 8192, 16384):
+for nfft in [int(x) for x in os.environ.get("SA_MATRIX_N", "2048,4096,8192,16384").split(",")]:
     for dt, log2n in (("cf32_le", 28), ("ci16_le", 29), ("cu8", 30)):
         for win in ("hann", "rect"):
             r = spectrogram_case(eng, "m", dt, 1 << log2n, nfft, nfft, win, "f32", 8)
