@@ -154,6 +154,7 @@ def main():
     cases.append(('cf32 256 rect', lambda: spectrogram_case(eng, "cf32 256 rect", "cf32_le", sc(1 << 28), 256, 256, "rect", "f32", args.steps)))
     cases.append(('cf32 16384 Hann', lambda: spectrogram_case(eng, "cf32 16384 Hann", "cf32_le", sc(1 << 28), 16384, 16384, "hann", "f32", args.steps)))
     cases.append(("cf64 1024 Hann FP64", lambda: spectrogram_case(eng, "cf64 1024 Hann FP64", "cf64_le", sc(1 << 27), 1024, 1024, "hann", "f64", args.steps)))
+    cases.append(("cf64 256 Hann FP64", lambda: spectrogram_case(eng, "cf64 256 Hann FP64", "cf64_le", sc(1 << 27), 256, 256, "hann", "f64", args.steps)))
     cases.append(("cf64 8192 Hann FP64", lambda: spectrogram_case(eng, "cf64 8192 Hann FP64", "cf64_le", sc(1 << 27), 8192, 8192, "hann", "f64", args.steps)))
     cases.append(("ci16 1024 Hann 50% overlap", lambda: spectrogram_case(eng, "ci16 1024 Hann 50% overlap", "ci16_le", sc(1 << 29), 1024, 512, "hann", "f32", args.steps)))
     cases.append(("cf32 8192 Hann", lambda: spectrogram_case(eng, "cf32 8192 Hann", "cf32_le", sc(1 << 28), 8192, 8192, "hann", "f32", args.steps)))

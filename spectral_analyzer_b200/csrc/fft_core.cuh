@@ -27,6 +27,9 @@
 #ifndef SA_CTA_1WPF
 #define SA_CTA_1WPF 512
 #endif
+#ifndef SA_CTA_F64
+#define SA_CTA_F64 512      // FP64 plans whose frames fit a warp (nfft <= 512); cf64 256: 139 -> 147 Gsamples/s
+#endif
 #ifndef SA_WIN_SMEM_MAX_TPF
 #define SA_WIN_SMEM_MAX_TPF 128
 #endif
@@ -335,7 +338,8 @@ template <typename T, int N> struct Geo {
     // twiddle/window tables per SM, and the 16+ consecutive frames a CTA takes per step are one contiguous
     // stretch of the capture (DRAM page locality; the overlapping halves of neighbouring frames are fetched
     // together).  Measured on the 1024-point kernel: 128 -> 256 -> 512 threads = 0.865 -> 0.850 -> 0.801 ms
-    static constexpr int CTA = (sizeof(T) == 4 && TPF <= 32) ? SA_CTA_1WPF : (TPF > 128 ? TPF : 128);
+    static constexpr int CTA = (sizeof(T) == 4 && TPF <= 32) ? SA_CTA_1WPF
+                             : (sizeof(T) == 8 && TPF <= 32) ? SA_CTA_F64 : (TPF > 128 ? TPF : 128);
     static constexpr int FPC = CTA / TPF;                    // frames per CTA pass
     // resident CTAs per SM the register cap is set for: one-warp-per-frame FP32 kernels run 5 warps per
     // scheduler (96 registers), everything else 4 (128 registers)
