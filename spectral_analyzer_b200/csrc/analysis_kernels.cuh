@@ -83,7 +83,7 @@ __device__ __forceinline__ float2 cmul(float2 x, float2 p) {
 // One sample per thread and step (coalesced), kDcUnroll independent loads in flight per thread before the
 // first is consumed; the NCO phase of every sample comes from the exact 64-bit accumulator.  Samples before
 // the annotation start (n < 0) are the zero history of the causal filter.
-constexpr int kDcUnroll = 8;
+constexpr int kDcUnrollMax = 16;      // loads in flight per thread (16-byte cf64 pairs: 8, register budget); C3: 8 -> 16 = +4 %
 
 __device__ __forceinline__ void sts64(uint32_t addr, float x, float y) {
     asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(x), "f"(y) : "memory");
@@ -94,6 +94,7 @@ __device__ __forceinline__ void dc_stage_tile_impl(const DcArgs& a, const DcAnn&
                                                    const long long nlo, const int n_stage, const int pad) {
     using LD = Loader<float, DK>;
     using raw_t = typename LD::raw_t;
+    constexpr int kDcUnroll = sizeof(raw_t) <= 8 ? kDcUnrollMax : kDcUnrollMax / 2;
     const raw_t* src = reinterpret_cast<const raw_t*>(a.lp.base) + (an.start_sample + nlo) + threadIdx.x;
     // the phasor advances kDcThreads samples per step: one complex multiply by wstep (packed: P = (c, -s),
     // Q = i P, P' = P.x W + P.y (i W)), re-seeded from the exact 64-bit phase at every batch of kDcUnroll samples
