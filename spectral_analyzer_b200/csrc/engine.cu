@@ -151,6 +151,9 @@ static int upload_pairs(const std::vector<double>& re, const std::vector<double>
     cudaError_t e = cudaMalloc(d_out, h.size() * sizeof(T));
     if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(twiddle)");
     e = cudaMemcpy(*d_out, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+    // a pageable H2D cudaMemcpy may return once the data is STAGED; the kernels that read the table run on
+    // non-blocking streams, which do not order against the legacy stream: wait for the DMA itself
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(twiddle)");
     return SA_OK;
 }
@@ -185,6 +188,7 @@ int Engine::window_table(int window_id, int n, int prec, const void** d_tab) {
         e = cudaMalloc(&d, n * sizeof(float));
         if (e == cudaSuccess) e = cudaMemcpy(d, wf.data(), n * sizeof(float), cudaMemcpyHostToDevice);
     }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();      // see upload_pairs
     if (e != cudaSuccess) return cuda_fail(e, "window table");
     windows[key] = d;
     *d_tab = d;
