@@ -18,6 +18,9 @@
  * sa_last_error() returns a thread-local message.  All entry points are re-entrant: calls
  * on one engine serialise on an internal lock, different engines run concurrently.
  * There is NO CPU fallback: without a CUDA device sa_engine_create fails with SA_ERR_NO_DEVICE.
+ * The *_device entry points are asynchronous on the caller's stream and use per-engine workspaces:
+ * successive device calls on ONE engine must be issued on one stream (or be ordered by the caller);
+ * use one engine per stream for concurrent device work.
  */
 #ifndef SA_ENGINE_H
 #define SA_ENGINE_H

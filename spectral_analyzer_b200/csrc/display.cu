@@ -149,7 +149,7 @@ int32_t sa_render_canvas(sa_engine* engine, const void* iq, uint64_t iq_bytes, c
         sa_spectrogram_params r = q;
         r.start_sample = 0;
         r.n_frames = nf;
-        rc = engine->launch_spectrogram(s.d_in, ns, r, prec, s.d_out, s.stream);
+        rc = engine->launch_spectrogram(s.d_in, ns, r, prec, s.d_out, s.stream, 5 + (int)(c % kSlots));
         if (rc) return rc;
         rc = launch_canvas(engine, ca, (const float*)s.d_out, (int)c0, (int)nc, s.stream);
         if (rc) return rc;

@@ -237,7 +237,7 @@ int Engine::mid_t1_table(int n, const void** d_tab) {
 
 // Four-step path (large_fft_kernels.cuh): frames are processed in chunks whose workspace stays L2-sized.
 int Engine::launch_spectrogram_large(const void* d_iq, uint64_t n_samples, const sa_spectrogram_params& p, int prec,
-                                     const SpecArgs& base, void* d_out, cudaStream_t stream) {
+                                     const SpecArgs& base, void* d_out, cudaStream_t stream, int ws) {
     (void)d_iq; (void)n_samples; (void)d_out;
     const int dk = dtype_kind(p.dtype);
     const int win = (prec == SA_PREC_F64) ? 1 : (p.window != SA_WIN_RECT ? 1 : 0);
@@ -289,9 +289,9 @@ int Engine::launch_spectrogram_large(const void* d_iq, uint64_t n_samples, const
         }
         if (n_clusters > 0) {
             const uint64_t use = std::min<uint64_t>((uint64_t)n_clusters, p.n_frames);
-            rc = ensure_scratch(2, 2 * use * per_frame);
+            rc = ensure_scratch(ws, 2 * use * per_frame);
             if (rc) return rc;
-            a.ws = scratch[2];
+            a.ws = scratch[ws];
             a.frame0 = 0;
             cfg.gridDim = dim3((unsigned)(use * kLargeCluster));
             e = cudaLaunchKernelExC(&cfg, k->fn_cluster, args);
@@ -302,9 +302,9 @@ int Engine::launch_spectrogram_large(const void* d_iq, uint64_t n_samples, const
     }
     static const uint64_t ws_mb = getenv("SA_LARGE_WS_MB") ? (uint64_t)atoi(getenv("SA_LARGE_WS_MB")) : 512;
     const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(p.n_frames, (ws_mb << 20) / per_frame));
-    rc = ensure_scratch(2, chunk * per_frame);
+    rc = ensure_scratch(ws, chunk * per_frame);
     if (rc) return rc;
-    a.ws = scratch[2];
+    a.ws = scratch[ws];
     e = cudaFuncSetAttribute(k->fn_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->smem_cols);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k->fn_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->smem_rows);
     if (e != cudaSuccess) return cuda_fail(e, "large FFT smem attribute");
@@ -387,7 +387,7 @@ int check_spec_params(const sa_spectrogram_params* p, int* prec_out) {
 
 // Launches the fused spectrogram kernel on device-resident samples.
 int Engine::launch_spectrogram(const void* d_iq, uint64_t n_samples, const sa_spectrogram_params& p, int prec,
-                               void* d_out, cudaStream_t stream) {
+                               void* d_out, cudaStream_t stream, int ws) {
     if (p.n_frames == 0) return SA_OK;
     const int dk = dtype_kind(p.dtype);
     const int win = (prec == SA_PREC_F64) ? 1 : (p.window != SA_WIN_RECT ? 1 : 0);
@@ -410,7 +410,7 @@ int Engine::launch_spectrogram(const void* d_iq, uint64_t n_samples, const sa_sp
     }
     // transforms too large for one SM's shared memory take the four-step path
     if (p.nfft > 16384 || (prec == SA_PREC_F64 && p.nfft > 8192))
-        return launch_spectrogram_large(d_iq, n_samples, p, prec, a, d_out, stream);
+        return launch_spectrogram_large(d_iq, n_samples, p, prec, a, d_out, stream, ws);
     // TMA-staged variant (needs every frame start 16-byte aligned), else the LDG kernel
     const uint64_t iq_b = (uint64_t)sa_bytes_per_iq(p.dtype);
     const bool aligned = ((uintptr_t)d_iq % 16 == 0) && ((p.start_sample * iq_b) % 16 == 0) && ((p.hop * iq_b) % 16 == 0);
@@ -553,7 +553,7 @@ int Engine::spectrogram_host(const void* iq, uint64_t iq_bytes, const sa_spectro
         sa_spectrogram_params q = p;
         q.start_sample = 0;
         q.n_frames = nf;
-        rc = launch_spectrogram(s.d_in, ns, q, prec, s.d_out, s.stream);
+        rc = launch_spectrogram(s.d_in, ns, q, prec, s.d_out, s.stream, 5 + (int)(c % kSlots));
         if (rc) break;
         void* dst = (char*)out + f0 * row_bytes;
         if (!out_pinned) { s.pending_dst = dst; s.pending_bytes = nf * row_bytes; dst = s.h_out; }

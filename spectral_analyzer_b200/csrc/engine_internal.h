@@ -26,7 +26,7 @@ int check_spec_params(const sa_spectrogram_params* p, int* prec_out);   // valid
 void fill_load_params(LoadParams& lp, const void* base, int dtype, int big_endian);
 
 constexpr int kSlots = 3;
-constexpr int kScratch = 5;
+constexpr int kScratch = 8;
 
 struct Slot {
     cudaStream_t stream = nullptr;
@@ -70,7 +70,8 @@ struct Engine {
     Slot slots[kSlots];
     CopyPool* copy_pool = nullptr;                   // created on first use
     // device workspaces: [0] annotation plan + taps, [1] Welch plan + partial spectra, [2] four-step FFT,
-    // [3] canvas / canvas dB rows, [4] signal lists of the packer / series kernels
+    // [3] canvas / canvas dB rows, [4] signal lists of the packer / series kernels,
+    // [5..7] four-step FFT workspaces of the host pipeline's slots (their chunks run concurrently on three streams)
     void* scratch[kScratch] = {};
     size_t scratch_cap[kScratch] = {};
 
@@ -85,10 +86,12 @@ struct Engine {
     int ensure_scratch(int which, size_t bytes);
     int root_table(int n, int prec, const void** d_tab);      // W_n^j, j = 0..n-1
     int mid_t1_table(int n, const void** d_tab);              // pass-1 twiddle pairs of spectrogram_mid_kernel
+    // ws: index of the scratch buffer the four-step path may use as its workspace (2 for device-API calls; the
+    // host pipeline passes 5 + slot so that chunks in flight on different streams never share a workspace)
     int launch_spectrogram_large(const void* d_iq, uint64_t n_samples, const sa_spectrogram_params& p, int prec,
-                                 const SpecArgs& base, void* d_out, cudaStream_t stream);
+                                 const SpecArgs& base, void* d_out, cudaStream_t stream, int ws);
     int launch_spectrogram(const void* d_iq, uint64_t n_samples, const sa_spectrogram_params& p, int prec,
-                           void* d_out, cudaStream_t stream);
+                           void* d_out, cudaStream_t stream, int ws = 2);
     int spectrogram_host(const void* iq, uint64_t iq_bytes, const sa_spectrogram_params& p, int prec, void* out);
 };
 

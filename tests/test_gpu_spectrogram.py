@@ -276,3 +276,23 @@ def test_pinned_and_pageable_host_paths_agree(engine, tmp_path):
     iq_m, psd_m = engine.downconvert_psd_batch(mm, "ci16_le", 1e6, [(1000, 600000, 0.1, 16, False), (5, 40000, -0.2, 4, True)], psd_nfft=1024)
     iq_p, psd_p = engine.downconvert_psd_batch(pin.numpy(), "ci16_le", 1e6, [(1000, 600000, 0.1, 16, False), (5, 40000, -0.2, 4, True)], psd_nfft=1024)
     assert all(np.array_equal(x, y) for x, y in zip(iq_m, iq_p)) and np.array_equal(psd_m, psd_p)
+
+
+@pytest.mark.parametrize("nfft,dt,prec", [(32768, "ci16_le", "f32"), (65536, "cf32_le", "f32"), (16384, "cf64_le", "f64")])
+def test_four_step_through_the_chunked_host_pipeline(monkeypatch, nfft, dt, prec):
+    """Several host chunks of a four-step size are in flight on different streams: every slot has its own
+    workspace (a shared one would be overwritten by the next chunk's column step)."""
+    import spectral_analyzer_b200 as sa
+    frames, hop = 41, nfft // 2
+    raw = synth.recording((frames - 1) * hop + nfft, dt, seed=77)
+    ref = co.spectrogram(raw, dt, 0, nfft, hop, "hann", frames)
+    monkeypatch.setenv("SA_CHUNK_MB", "1")
+    eng = sa.Engine(0)
+    kind = "f64" if prec == "f64" else "f32"
+    for _ in range(3):          # repeated: a workspace race would be timing dependent
+        got = eng.spectrogram(raw, dt, nfft, frames, hop=hop, window="hann", precision=prec, out_kind=kind)
+        if prec == "f64":
+            check_db_parity(got, ref, strong_tol=1e-9, floor_tol=1e-6)
+        else:
+            check_db_parity(got, ref)
+    eng.close()
