@@ -74,6 +74,10 @@ int32_t sa_render_canvas_device(sa_engine* engine, const void* d_iq, uint64_t iq
     if (!d_out_rgba || (!d_iq && iq_bytes)) return set_error(SA_ERR_INVALID_ARG, "NULL buffer");
     sa_spectrogram_params q = *params;
     q.out_kind = SA_OUT_F32_DB;
+    if (reduce == SA_REDUCE_NEAREST) {          // only the first frame of every column is shown: transform only those
+        q.hop = params->hop * frames_per_column;
+        frames_per_column = 1;
+    }
     q.n_frames = (uint64_t)canvas_w * frames_per_column;
     int prec = 0;
     rc = check_spec_params(&q, &prec);
@@ -107,6 +111,10 @@ int32_t sa_render_canvas(sa_engine* engine, const void* iq, uint64_t iq_bytes, c
     if (!out_rgba || (!iq && iq_bytes)) return set_error(SA_ERR_INVALID_ARG, "NULL buffer");
     sa_spectrogram_params q = *params;
     q.out_kind = SA_OUT_F32_DB;
+    if (reduce == SA_REDUCE_NEAREST) {          // only the first frame of every column is shown: transform only those
+        q.hop = params->hop * frames_per_column;
+        frames_per_column = 1;
+    }
     q.n_frames = (uint64_t)canvas_w * frames_per_column;
     int prec = 0;
     rc = check_spec_params(&q, &prec);
@@ -122,6 +130,34 @@ int32_t sa_render_canvas(sa_engine* engine, const void* iq, uint64_t iq_bytes, c
     if (rc) return rc;
     CanvasArgs ca;
     fill_canvas_args(ca, q, canvas_w, canvas_h, frames_per_column, reduce, (uint32_t*)engine->scratch[3]);
+    // sparse frames (hop >= 2 nfft, e.g. the nearest-frame quick look of a long recording): only the frames'
+    // own samples are packed into pinned memory and cross PCIe, not the gaps between them
+    const uint64_t total_frames = (uint64_t)canvas_w * frames_per_column;
+    const uint64_t frame_bytes = (uint64_t)q.nfft * bps;
+    if (q.hop >= 2ull * q.nfft && total_frames * frame_bytes <= (256ull << 20)) {
+        uint64_t nr = 0;                                    // readable frames are a prefix (MainController.java:987)
+        while (nr < total_frames && q.start_sample + nr * q.hop + q.nfft <= n_samples) nr++;
+        Slot& s = engine->slots[0];
+        rc = engine->ensure_slot(s, std::max<uint64_t>(nr * frame_bytes, 16), total_frames * q.nfft * 4);
+        if (rc) return rc;
+        rc = engine->ensure_staging(s, std::max<uint64_t>(nr * frame_bytes, 16), 0);
+        if (rc) return rc;
+        for (uint64_t t = 0; t < nr; t++)
+            memcpy((char*)s.h_in + t * frame_bytes, (const char*)iq + (q.start_sample + t * q.hop) * bps, frame_bytes);
+        cudaError_t e2 = cudaSuccess;
+        if (nr) e2 = cudaMemcpyAsync(s.d_in, s.h_in, nr * frame_bytes, cudaMemcpyHostToDevice, s.stream);
+        if (e2 != cudaSuccess) return cuda_fail(e2, "H2D packed frames");
+        sa_spectrogram_params r = q;
+        r.start_sample = 0; r.hop = q.nfft; r.n_frames = total_frames;
+        rc = engine->launch_spectrogram(s.d_in, nr * q.nfft, r, prec, s.d_out, s.stream, 5);
+        if (rc) return rc;
+        rc = launch_canvas(engine, ca, (const float*)s.d_out, 0, (int)canvas_w, s.stream);
+        if (rc) return rc;
+        e2 = cudaMemcpyAsync(out_rgba, engine->scratch[3], canvas_bytes, cudaMemcpyDeviceToHost, s.stream);
+        if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(s.stream);
+        if (e2 != cudaSuccess) return cuda_fail(e2, "sparse canvas");
+        return SA_OK;
+    }
     // chunk c: H2D of its samples -> spectrogram -> canvas columns, on slot c % kSlots; only the canvas comes back
     const bool in_pinned = host_ptr_is_pinned(iq);
     uint64_t c = 0;

@@ -114,3 +114,31 @@ def test_analysis_series_golden_and_silence(engine):
     assert np.abs(gm - g["mag"]).max() < 1e-9 and np.abs(gf[1:] - g["frq"][1:]).max() < 1e-3
     zm, _ = engine.analysis_series(np.zeros((2, 100)), 1e6, 0.5, 0.5, 0.0)
     assert np.isneginf(zm).all()                                         # 20 log10(0): the values the Java chart skips
+
+
+@pytest.mark.parametrize("dt,nfft", [("cf32_le", 1024), ("cu8", 2048)])
+def test_canvas_nearest_with_frame_stride_and_sparse_frames(engine, dt, nfft):
+    """frames_per_column > 1 with the nearest pick shows frame t*fpc of every column: only those frames are
+    transformed and (host path) only their samples are packed and sent.  Also a sparse max-pooled view, and
+    columns past the end of the recording (-150 dB rows)."""
+    fs, W, H, fpc = 2.4e6, 23, 160, 7
+    n = nfft * (fpc * (W - 3)) + 5                                        # the last columns run past EOF
+    raw = synth.recording(n, dt, seed=61)
+    db = co.spectrogram(raw, dt, 0, nfft, nfft, "rect", W * fpc)
+    ref = co.render_canvas(db[::fpc], H, fs, -140.0, -20.0, "Grayscale")
+    got = engine.render_canvas(raw, dt, nfft, W, H, fs, frames_per_column=fpc, reduce="nearest", colormap="Grayscale",
+                               min_db=-140.0, max_db=-20.0)
+    assert np.abs(got.astype(np.int32) - ref.astype(np.int32)).max() <= 1
+    assert (got[:, -1, :3] == got[0, -1, :3]).all()                        # EOF column: one colour (-150 dB)
+    # sparse hop (3 nfft) with max pooling over 2 frames per column
+    hop, fpc2, W2 = 3 * nfft, 2, 11
+    raw2 = synth.recording((W2 * fpc2 - 1) * hop + nfft, dt, seed=62)
+    db2 = co.spectrogram(raw2, dt, 0, nfft, hop, "hann", W2 * fpc2).reshape(W2, fpc2, nfft)
+    edges = (np.arange(H + 1, dtype=np.float64) / H * nfft).astype(np.int64)
+    pooled = np.stack([db2[:, :, edges[f]:max(edges[f + 1], edges[f] + 1)].max(axis=(1, 2)) for f in range(H)], axis=1)
+    conv = 10 * np.log10(fs / nfft) + 20 * np.log10(nfft)
+    n_lvl = np.clip((pooled.T[::-1] - conv + 140.0) / 120.0, 0, 1)
+    ref2 = np.floor(n_lvl * 255 + 0.5).astype(np.int32)
+    got2 = engine.render_canvas(raw2, dt, nfft, W2, H, fs, hop=hop, window="hann", frames_per_column=fpc2, reduce="max",
+                                colormap="Grayscale", min_db=-140.0, max_db=-20.0)
+    assert np.abs(got2[..., 0].astype(np.int32) - ref2).max() <= 1
