@@ -58,7 +58,8 @@ int launch_canvas(Engine* eng, CanvasArgs& ca, const float* d_db, int col0, int 
 
 uint64_t canvas_cols_per_chunk(const sa_spectrogram_params& p, uint64_t fpc, uint32_t w, uint64_t chunk_bytes) {
     const uint64_t col_bytes = fpc * (uint64_t)p.nfft * 4;
-    return std::max<uint64_t>(1, std::min<uint64_t>(w, chunk_bytes / col_bytes));
+    // at most 65535 columns per launch (grid.y)
+    return std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>(w, 65535), chunk_bytes / col_bytes));
 }
 
 }  // namespace
@@ -134,7 +135,7 @@ int32_t sa_render_canvas(sa_engine* engine, const void* iq, uint64_t iq_bytes, c
     // own samples are packed into pinned memory and cross PCIe, not the gaps between them
     const uint64_t total_frames = (uint64_t)canvas_w * frames_per_column;
     const uint64_t frame_bytes = (uint64_t)q.nfft * bps;
-    if (q.hop >= 2ull * q.nfft && total_frames * frame_bytes <= (256ull << 20)) {
+    if (q.hop >= 2ull * q.nfft && total_frames * frame_bytes <= (256ull << 20) && canvas_w <= 65535) {
         uint64_t nr = 0;                                    // readable frames are a prefix (MainController.java:987)
         while (nr < total_frames && q.start_sample + nr * q.hop + q.nfft <= n_samples) nr++;
         Slot& s = engine->slots[0];
