@@ -152,6 +152,9 @@ def main():
     cases.append(('C5 cf64 65536 Hann f64', lambda: spectrogram_case(eng, "C5 cf64 65536 Hann f64", "cf64_le", sc(1 << 26), 65536, 65536, "hann", "f64", args.steps)))
     cases.append(('cf32 65536 Hann (four-step FP32)', lambda: spectrogram_case(eng, "cf32 65536 Hann (four-step FP32)", "cf32_le", sc(1 << 27), 65536, 65536, "hann", "f32", args.steps)))
     cases.append(('cf32 256 rect', lambda: spectrogram_case(eng, "cf32 256 rect", "cf32_le", sc(1 << 28), 256, 256, "rect", "f32", args.steps)))
+    cases.append(('cf32 64 rect', lambda: spectrogram_case(eng, "cf32 64 rect", "cf32_le", sc(1 << 28), 64, 64, "rect", "f32", args.steps)))
+    cases.append(('cf32 128 Hann', lambda: spectrogram_case(eng, "cf32 128 Hann", "cf32_le", sc(1 << 28), 128, 128, "hann", "f32", args.steps)))
+    cases.append(('cf32 512 Hann 50% overlap', lambda: spectrogram_case(eng, "cf32 512 Hann 50% overlap", "cf32_le", sc(1 << 28), 512, 256, "hann", "f32", args.steps)))
     cases.append(('cf32 16384 Hann', lambda: spectrogram_case(eng, "cf32 16384 Hann", "cf32_le", sc(1 << 28), 16384, 16384, "hann", "f32", args.steps)))
     cases.append(("cf64 1024 Hann FP64", lambda: spectrogram_case(eng, "cf64 1024 Hann FP64", "cf64_le", sc(1 << 27), 1024, 1024, "hann", "f64", args.steps)))
     cases.append(("cf64 256 Hann FP64", lambda: spectrogram_case(eng, "cf64 256 Hann FP64", "cf64_le", sc(1 << 27), 256, 256, "hann", "f64", args.steps)))
