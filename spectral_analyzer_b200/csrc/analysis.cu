@@ -363,7 +363,11 @@ int32_t sa_downconvert_psd_batch(sa_engine* engine, const void* iq, uint64_t iq_
         // slots 1 and 2; an event per buffer says when its previous H2D has drained
         const size_t piece = 32u << 20;
         Slot* st[2] = { &engine->slots[1], &engine->slots[2] };
-        cudaEvent_t ev[2] = { nullptr, nullptr };
+        struct Events {                                      // destroyed on every exit path
+            cudaEvent_t ev[2] = { nullptr, nullptr };
+            ~Events() { for (auto x : ev) if (x) { cudaEventSynchronize(x); cudaEventDestroy(x); } }
+        } evs;
+        cudaEvent_t* ev = evs.ev;
         for (int k = 0; k < 2 && e == cudaSuccess; k++) {
             rc = engine->ensure_staging(*st[k], piece, 0);
             if (rc) return rc;
@@ -382,8 +386,6 @@ int32_t sa_downconvert_psd_batch(sa_engine* engine, const void* iq, uint64_t iq_
             }
             pos += anns[i].count;
         }
-        for (int j = 0; j < 2; j++)
-            if (ev[j]) { cudaEventSynchronize(ev[j]); cudaEventDestroy(ev[j]); }
     }
     if (e != cudaSuccess) return cuda_fail(e, "H2D annotation spans");
     double* d_iq_out = (double*)s.d_out;
