@@ -13,6 +13,9 @@
 #pragma once
 #include "spectrogram_kernel.cuh"
 
+#ifndef SA_LARGE_ROWS_MINB
+#define SA_LARGE_ROWS_MINB 3
+#endif
 #ifndef SA_LARGE_COLS_MINB
 #define SA_LARGE_COLS_MINB 3
 #endif
@@ -136,7 +139,7 @@ __device__ __forceinline__ void large_rows_body(const LargeArgs& a, const long l
 }
 
 template <typename T, int N1, int N2>
-__global__ void __launch_bounds__(kLargeC * Geo<T, N2>::TPF)
+__global__ void __launch_bounds__(kLargeC * Geo<T, N2>::TPF, SA_LARGE_ROWS_MINB)
 large_rows_kernel(const LargeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     large_rows_body<T, N1, N2>(a, a.frame0 + blockIdx.y, reinterpret_cast<const cpx<T>*>(a.ws) + (size_t)blockIdx.y * (N1 * N2),
