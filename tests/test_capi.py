@@ -66,3 +66,23 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.lower(), f + " mentions the oracle"
+
+
+def test_python_binding_covers_the_header():
+    """_capi.py is the 1:1 mirror of the Panama binding: every function the header declares has its argument
+    types spelled out there (no implicit int marshalling of 64-bit sizes or pointers)."""
+    L = _capi.lib()
+    no_args = {"sa_last_error", "sa_version"}
+    for n in declared_symbols():
+        if n in no_args:
+            continue
+        assert getattr(L, n).argtypes is not None, n + " has no argtypes in _capi.py"
+
+
+def test_new_entry_points_validate_arguments_without_a_gpu():
+    """Argument errors of the canvas / packer / series calls are reported before any device work."""
+    L = _capi.lib()
+    assert L.sa_iq_pack(None, None, None, 0, 0, None) == 1            # engine is NULL
+    assert b"engine is NULL" in L.sa_last_error()
+    p = _capi.default_params()
+    assert L.sa_render_canvas(None, None, 0, C.byref(p), 4, 4, 1, 0, None) == 1
