@@ -11,8 +11,14 @@
 //   pass 2  radix 32; twiddles W_N^{t m} by the packed register recurrence seeded with W_N^t.
 // Against the general plan (32 * 32 * R0: twiddle pairs for two passes from global memory) this removes
 // every per-frame twiddle LDG and the scalar radix-R0 tail with its 8 distinct twiddle sets per thread.
-// Exchange buffer: one pad element per 32 (index i + i/32) keeps all three access patterns at the
-// two-wavefront minimum of 64-bit accesses.
+// Exchange buffer: one pad element per 32 (physical index i + i/32) keeps all three access patterns at the
+// two-wavefront minimum of 64-bit accesses (a warp moves 256 bytes; bank of an 8-byte element = physical index
+// mod 16, so a pattern is conflict-free when the 32 lanes cover every residue exactly twice):
+//   pass-0 write   lane t, fixed (i, m): logical 32 t + c  -> physical 33 t + c        : residues t + c      (each twice)
+//   read-back      lane t, fixed q     : logical t + TPF q -> physical t + t/32 + const : consecutive         (each twice)
+//   pass-1 write   lane t, fixed m     : logical (t/R0) 32 R0 + (t mod R0) + m R0
+//                                        -> physical (t/R0) 33 R0 + (t mod R0) + const  : residues R0 (t/R0) + (t mod R0) = t
+// (33 R0 = R0 mod 16 for every R0 in {2, 4, 8, 16}); the pass-2 input is the same read-back pattern.
 #pragma once
 #include "spectrogram_kernel.cuh"
 
