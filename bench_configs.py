@@ -118,7 +118,8 @@ def canvas_case(eng, n_samples, nfft, hop, W, H, reduce, steps):
         eng.render_canvas(h_np, "cf32_le", nfft, W, H, 2.4e6, hop=hop, window="hann", frames_per_column=fpc,
                           reduce=reduce, colormap="Heatmap")
     host_ms = (time.perf_counter() - t0) / 3 * 1e3
-    alg = n_samples * 8 + W * H * 4
+    # nearest pick: only the W displayed frames are read
+    alg = (W * nfft if reduce == "nearest" else n_samples) * 8 + W * H * 4
     peak, kind_p = hbm_peak()
     return {"config": "N2 canvas %dx%d (%s) from cf32 %d-pt hop %d" % (W, H, reduce, nfft, hop), "samples": n_samples,
             "frames_per_column": fpc, "ms": round(ms, 4), "Msamples_per_s": round(W * fpc * hop / ms / 1e3, 1),

@@ -417,6 +417,10 @@ int Engine::launch_spectrogram(const void* d_iq, uint64_t n_samples, const sa_sp
     static const bool no_tma = getenv("SA_NO_TMA") != nullptr;      // A/B switches for the ablations in DESIGN.md
     static const bool no_mid = getenv("SA_NO_MID") != nullptr;
     const SpecKernelInfo* k = (aligned && !no_tma) ? find_spec_kernel(prec, (int)p.nfft, dk, win, 1) : nullptr;
+    // 4096: two radix-64 passes (one exchange) for cf32 / ci16 input; cu8 / ci8 keep the 3-pass kernel (measured)
+    static const char* r64_env = getenv("SA_R64");
+    const bool use_r64 = r64_env ? (strcmp(r64_env, "all") == 0) : (dk == DK_CF32 || dk == DK_CI16);
+    if (!k && aligned && use_r64 && prec == SA_PREC_F32 && p.nfft == 4096) k = find_spec_kernel(prec, 4096, dk, win, 4);
     if (!k && aligned && !no_mid) {                                                        // small-radix-first plan
         // the asynchronously staged variant where it measured faster on B200 (tools/mid_pf_matrix.py): 2048 (8 frames
         // per CTA) and 16384 (one frame owns the SM) gain 6-19 %, 4096 (4 frames per CTA) 0-10 %, 8192 loses up to 19 %.

@@ -71,19 +71,46 @@ __host__ __device__ constexpr double cos32_tab(int q) {
 __host__ __device__ constexpr double w32_re(int q) { return q <= 8 ? cos32_tab(q) : -cos32_tab(16 - q); }
 __host__ __device__ constexpr double w32_im(int q) { return q <= 8 ? -cos32_tab(8 - q) : -cos32_tab(q - 8); }
 
-// DIT butterfly: (a, b) <- (a + W b, a - W b), W = W32^q, q compile-time after unrolling.
-template <typename T>
+// cos(2*pi*q/64), q = 0..16 (radix-64 passes)
+__host__ __device__ constexpr double cos64_tab(int q) {
+    return q == 0 ? 1.0
+         : q == 1 ? 0.9951847266721968862448369531094799
+         : q == 2 ? 0.980785280403230449126182236134239
+         : q == 3 ? 0.95694033573220886493579788698027
+         : q == 4 ? 0.9238795325112867561281831893967883
+         : q == 5 ? 0.8819212643483550297127568636603884
+         : q == 6 ? 0.8314696123025452370787883776179058
+         : q == 7 ? 0.7730104533627369608109066097584698
+         : q == 8 ? 0.707106781186547524400844362104849
+         : q == 9 ? 0.6343932841636454982151716132254934
+         : q == 10 ? 0.5555702330196022247428308139485329
+         : q == 11 ? 0.4713967368259976485563876259052544
+         : q == 12 ? 0.3826834323650897717284599840303989
+         : q == 13 ? 0.2902846772544623676361923758173953
+         : q == 14 ? 0.1950903220161282678482848684770222
+         : q == 15 ? 0.09801714032956060199419556388864184
+         : 0.0;
+}
+// W64^q = exp(-2*pi*i*q/64) for q = 0..32
+__host__ __device__ constexpr double w64_re(int q) { return q <= 16 ? cos64_tab(q) : -cos64_tab(32 - q); }
+__host__ __device__ constexpr double w64_im(int q) { return q <= 16 ? -cos64_tab(16 - q) : -cos64_tab(q - 16); }
+// twiddle of base B (32 or 64): exponent q in units of 2*pi/B, q = 0..B/2
+template <int B> __host__ __device__ constexpr double wB_re(int q) { return B == 64 ? w64_re(q) : w32_re(q); }
+template <int B> __host__ __device__ constexpr double wB_im(int q) { return B == 64 ? w64_im(q) : w32_im(q); }
+
+// DIT butterfly: (a, b) <- (a + W b, a - W b), W = W_B^q, q compile-time after unrolling.
+template <typename T, int B = 32>
 __device__ __forceinline__ void bfly(cpx<T>& a, cpx<T>& b, const int q) {
     if (q == 0) {
         T bx = b.x, by = b.y;
         b.x = a.x - bx; b.y = a.y - by;
         a.x = a.x + bx; a.y = a.y + by;
-    } else if (q == 8) {            // W = -i : W b = (b.y, -b.x)
+    } else if (q == B / 4) {        // W = -i : W b = (b.y, -b.x)
         T bx = b.x, by = b.y;
         b.x = a.x - by; b.y = a.y + bx;
         a.x = a.x + by; a.y = a.y - bx;
     } else {
-        const T wr = (T)w32_re(q), wi = (T)w32_im(q);
+        const T wr = (T)wB_re<B>(q), wi = (T)wB_im<B>(q);
         T ox = fma_t(-wi, b.y, fma_t(wr, b.x, a.x));
         T oy = fma_t( wi, b.x, fma_t(wr, b.y, a.y));
         b.x = fma_t((T)2, a.x, -ox);
@@ -95,6 +122,7 @@ __device__ __forceinline__ void bfly(cpx<T>& a, cpx<T>& b, const int q) {
 // bit reversal of x within log2(n) bits, n <= 32; loop-free so it folds after unrolling
 __host__ __device__ constexpr int bitrev_c(int x, int n) {
     const int r5 = ((x & 1) << 4) | ((x & 2) << 2) | (x & 4) | ((x & 8) >> 2) | ((x & 16) >> 4);
+    if (n == 64) return ((x & 1) << 5) | ((x & 2) << 3) | ((x & 4) << 1) | ((x & 8) >> 1) | ((x & 16) >> 3) | ((x & 32) >> 5);
     return n == 32 ? r5 : n == 16 ? (r5 >> 1) : n == 8 ? (r5 >> 2) : n == 4 ? (r5 >> 3) : (r5 >> 4);
 }
 
@@ -102,10 +130,11 @@ __host__ __device__ constexpr int bitrev_c(int x, int n) {
 // unroll a loop whose induction variable is shifted)
 template <typename T, int R, int LEN>
 __device__ __forceinline__ void dit_stages(cpx<T> (&a)[R]) {
+    constexpr int B = R > 32 ? 64 : 32;
 #pragma unroll
     for (int b = 0; b < R; b += LEN) {
 #pragma unroll
-        for (int k = 0; k < LEN / 2; k++) bfly<T>(a[b + k], a[b + k + LEN / 2], k * (32 / LEN));
+        for (int k = 0; k < LEN / 2; k++) bfly<T, B>(a[b + k], a[b + k + LEN / 2], k * (B / LEN));
     }
     if constexpr (LEN < R) dit_stages<T, R, LEN * 2>(a);
 }
@@ -128,17 +157,18 @@ __device__ __forceinline__ pk2 mul2(pk2 a, pk2 b) { pk2 r; asm("mul.rn.f32x2 %0,
 __device__ __forceinline__ pk2 neg2(pk2 a) { float lo, hi; unpack2(a, lo, hi); return pack2(-lo, -hi); }
 
 // two DIT butterflies at once: (a, b) <- (a + W b, a - W b), W = W32^q in both lanes
+template <int B = 32>
 __device__ __forceinline__ void bfly2(pk2& ar, pk2& ai, pk2& br, pk2& bi, const int q) {
     if (q == 0) {
         const pk2 xr = br, xi = bi;
         br = sub2(ar, xr); bi = sub2(ai, xi);
         ar = add2(ar, xr); ai = add2(ai, xi);
-    } else if (q == 8) {            // W = -i : W b = (b.im, -b.re)
+    } else if (q == B / 4) {        // W = -i : W b = (b.im, -b.re)
         const pk2 xr = br, xi = bi;
         br = sub2(ar, xi); bi = add2(ai, xr);
         ar = add2(ar, xi); ai = sub2(ai, xr);
     } else {
-        const float wr = (float)w32_re(q), wi = (float)w32_im(q);
+        const float wr = (float)wB_re<B>(q), wi = (float)wB_im<B>(q);
         const pk2 o_r = fma2(bcast2(-wi), bi, fma2(bcast2(wr), br, ar));
         const pk2 o_i = fma2(bcast2(wi), br, fma2(bcast2(wr), bi, ai));
         br = fma2(bcast2(2.0f), ar, neg2(o_r));
@@ -150,10 +180,11 @@ __device__ __forceinline__ void bfly2(pk2& ar, pk2& ai, pk2& br, pk2& bi, const 
 // packed stages of span LEN .. H on H = R/2 packed positions
 template <int H, int LEN>
 __device__ __forceinline__ void dit_stages_packed(pk2 (&pr)[H], pk2 (&pi)[H]) {
+    constexpr int B = H > 16 ? 64 : 32;          // H = R/2 packed positions
 #pragma unroll
     for (int b = 0; b < H; b += LEN) {
 #pragma unroll
-        for (int k = 0; k < LEN / 2; k++) bfly2(pr[b + k], pi[b + k], pr[b + k + LEN / 2], pi[b + k + LEN / 2], k * (32 / LEN));
+        for (int k = 0; k < LEN / 2; k++) bfly2<B>(pr[b + k], pi[b + k], pr[b + k + LEN / 2], pi[b + k + LEN / 2], k * (B / LEN));
     }
     if constexpr (LEN < H) dit_stages_packed<H, LEN * 2>(pr, pi);
 }
@@ -170,7 +201,7 @@ __device__ __forceinline__ void dit_tail(cpx<T> (&a)[R]) {
 #pragma unroll
         for (int i = 0; i < H; i++) { unpack2(pr[i], a[i].x, a[i + H].x); unpack2(pi[i], a[i].y, a[i + H].y); }
 #pragma unroll
-        for (int k = 0; k < H; k++) bfly<T>(a[k], a[k + H], k * (32 / R));     // last stage: lanes interact
+        for (int k = 0; k < H; k++) bfly<T, (R > 32 ? 64 : 32)>(a[k], a[k + H], k * ((R > 32 ? 64 : 32) / R));     // last stage: lanes interact
     } else {
         if constexpr (R > 2) dit_stages<T, R, 4>(a);
     }
@@ -185,7 +216,7 @@ __device__ __forceinline__ void dit_tail(cpx<T> (&a)[R]) {
 enum { MUL_NONE = 0, MUL_REAL = 1, MUL_CPX = 2, MUL_REC = 3 };
 
 // per-lane seeds of the twiddle recurrence: om = W_N^t, oh = om^(R/2)
-template <typename T> struct TwSeed { cpx<T> om, oh; };
+template <typename T> struct TwSeed { cpx<T> om, oh; cpx<T> q_lo, q_hi; };   // q_*: om^(R/4), om^(3R/4) (radix-64 re-seed)
 
 template <typename T> struct TwPair { cpx<T> lo, hi; };     // twiddles of elements m and m + R/2
 // TW_SMEM: the table was copied to shared memory (plain loads); otherwise read-only global loads
@@ -210,7 +241,7 @@ template <typename T, int R, int STR, int OFF, int P, int MUL, bool TW_SMEM>
 __device__ __forceinline__ void radix_fft(cpx<T> (&v)[P], const T* __restrict__ wr,
                                           const TwPair<T>* __restrict__ tw, const int tw_stride,
                                           const TwSeed<T>& seed) {
-    static_assert(R == 2 || R == 4 || R == 8 || R == 16 || R == 32, "radix");
+    static_assert(R == 2 || R == 4 || R == 8 || R == 16 || R == 32 || R == 64, "radix");
     if constexpr (SA_PACKED_SMALL_RADIX && sizeof(T) == 4 && R <= 4 && (MUL == MUL_REAL || MUL == MUL_NONE)) {
         // ablation, off by default (C2 2.55 -> 2.68 ms: the re-pairing costs more than the packed ops save):
         // small first-pass radices (spectrogram_mid_kernel): a complex value is already a packed (re, im) register
@@ -267,7 +298,10 @@ __device__ __forceinline__ void radix_fft(cpx<T> (&v)[P], const T* __restrict__ 
                 float lr, hr, li, hi;
                 unpack2(rec_re, lr, hr); unpack2(rec_im, li, hi);
                 w.lo = mk2<T>((T)lr, (T)li); w.hi = mk2<T>((T)hr, (T)hi);
-                if (m + 1 < R / 2) {            // advance both lanes: w <- w * om
+                if (R == 64 && m + 1 == R / 4) {      // long recurrence: restart from the exact pair half way
+                    rec_re = pack2((float)seed.q_lo.x, (float)seed.q_hi.x);
+                    rec_im = pack2((float)seed.q_lo.y, (float)seed.q_hi.y);
+                } else if (m + 1 < R / 2) {           // advance both lanes: w <- w * om
                     const pk2 orr = bcast2((float)seed.om.x), oii = bcast2((float)seed.om.y);
                     const pk2 nre = fma2(neg2(oii), rec_im, mul2(orr, rec_re));
                     rec_im = fma2(oii, rec_re, mul2(orr, rec_im));
