@@ -237,7 +237,8 @@ def main():
     # roofline of the (single) kernel of the step: algorithmic bytes = every input byte once +
     # every output byte once (8 + 4*nfft/hop = 16 B per input sample)
     alg_bytes = n_local * 8 + frames * NFFT * 4
-    kern_ms = sorted(per_step)[len(per_step) // 2]
+    kern_ms = sum(per_step) / len(per_step)            # average launch duration (one launch per step)
+    kern_best, kern_median = min(per_step), sorted(per_step)[len(per_step) // 2]
     peak, peak_kind = hbm_peak()
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     traffic = None
@@ -328,10 +329,20 @@ def main():
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic, "peak_kind": peak_kind,
                          "alg_bytes_per_launch": int(alg_bytes), "kernel_ms": round(kern_ms, 4),
+                         "kernel_ms_best": round(kern_best, 4), "kernel_ms_median": round(kern_median, 4),
                          "kernel": "spectrogram_tma_kernel<float,1024,cf32,window>"},
             "clocks": sampler.summary(),
             "gpu_launches": int(launches),
         }
+        # the FP32 pipe bound beside the HBM one: 5 nfft log2(nfft) / hop + 6 flop per input sample against
+        # 148 SMs x 128 FMA lanes x 2 flop at the SM clock sampled during the run
+        import math
+        flops_per_sample = 5.0 * NFFT * math.log2(NFFT) / HOP + 6.0
+        sm_mhz = (line["clocks"] or {}).get("sm_mhz") or 1965
+        fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+        fp32_ach = samples_per_step_local * flops_per_sample / (kern_ms * 1e-3) / 1e12
+        line["fp32_pipe"] = {"flops_per_sample": round(flops_per_sample, 1), "achieved": round(fp32_ach, 2),
+                             "peak": round(fp32_peak, 1), "unit": "TFLOP/s", "frac": round(fp32_ach / fp32_peak, 4)}
         if e2e:
             line["e2e"] = e2e
         if sustained:

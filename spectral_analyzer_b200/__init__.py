@@ -6,4 +6,6 @@ reference's service interface on top of it.
 from .services import (Engine, EngineError, SpectralService, ExtractDownConvertService,  # noqa: F401
                        AsyncExtractDownConvertService, PowerSpectralDensity, IqData)
 
+from .tiles import CanvasTileCache  # noqa: F401
+
 __version__ = "0.1.0"

@@ -106,6 +106,37 @@ class SigMfHelper:
         caps = self.metadata.get("captures") or []
         return float(caps[0].get("core:frequency") or 0.0) if caps else 0.0
 
+    def capture_segments(self):
+        """Beyond the reference (which honours captures[0] only, SigMfHelper.java:59-67): every capture of a
+        multi-capture recording as (byte_offset, sample_start, n_samples, frequency), byte_offset counted from the
+        start of the data FILE.  core:header_bytes of capture i is the number of non-sample bytes that precede its
+        samples, so its samples start at sum(header_bytes[0..i]) + sample_start * bytes_per_sample; it ends where
+        the next capture's header starts (or at the end of the file)."""
+        caps = self.metadata.get("captures") or [{}]
+        bps = bytes_per_sample(self.datatype)
+        size = os.path.getsize(self.dataPath)
+        segs, hdr = [], 0
+        for i, c in enumerate(caps):
+            hdr += int(c.get("core:header_bytes") or 0)
+            s0 = int(c.get("core:sample_start") or 0)
+            off = hdr + s0 * bps
+            if i + 1 < len(caps):
+                n = int(caps[i + 1].get("core:sample_start") or 0) - s0
+            else:
+                n = max(0, size - off) // bps
+            n = max(0, min(n, max(0, size - off) // bps))
+            segs.append((off, s0, n, float(c.get("core:frequency") or 0.0)))
+        return segs
+
+    def capture_buffer(self, index):
+        """The bytes of one capture, mapped read-only with 64-bit offsets (position 0 = its first sample): what
+        the engine is handed for that capture."""
+        off, _, n, _ = self.capture_segments()[index]
+        nbytes = n * bytes_per_sample(self.datatype)
+        if nbytes == 0:
+            return np.zeros(0, np.uint8)
+        return np.memmap(self.dataPath, dtype=np.uint8, mode="r", offset=off, shape=(nbytes,))
+
     @property
     def total_samples(self):                                           # MainController.java:603-605
         return len(self.dataBuffer) // bytes_per_sample(self.datatype)

@@ -147,3 +147,37 @@ def test_wav_mapping_through_the_engine(tmp_path, engine):
     ref = co.spectrogram(np.asarray(buf), sm.datatype, 0, 1024, 1024, "rect", 10)
     assert (got[9] == -150.0).all()
     check_db_parity(got[:9], ref[:9])
+
+
+def test_multi_capture_segments(tmp_path):
+    """Three captures, each preceded by its own header (non-conforming dataset): byte offsets, lengths and the
+    mapped bytes of each capture; captures[0] is what the reference's getDataBuffer starts at."""
+    dt, bps = "ci16_le", 4
+    parts = [synth.recording(n, dt, seed=20 + i).tobytes() for i, n in enumerate((1000, 300, 777))]
+    hdrs = [b"H" * 12, b"I" * 8, b"J" * 20]
+    blob = b"".join(h + p for h, p in zip(hdrs, parts))
+    starts = [0, 1000, 1300]
+    meta = {"global": {"core:datatype": dt, "core:sample_rate": 1e6, "core:version": "1.0.0", "core:dataset": "x.bin"},
+            "captures": [{"core:sample_start": s, "core:frequency": 1e6 * (i + 1), "core:header_bytes": len(h)}
+                         for i, (s, h) in enumerate(zip(starts, hdrs))], "annotations": []}
+    (tmp_path / "x.bin").write_bytes(blob)
+    mp = tmp_path / "x.sigmf-meta"
+    mp.write_text(json.dumps(meta))
+    h = sigmf.SigMfHelper().load(mp)
+    segs = h.capture_segments()
+    assert [s[1] for s in segs] == starts and [s[2] for s in segs] == [1000, 300, 777]
+    assert [s[3] for s in segs] == [1e6, 2e6, 3e6]
+    off = 0
+    for i, (hd, p) in enumerate(zip(hdrs, parts)):
+        off += len(hd)
+        assert segs[i][0] == off
+        assert bytes(h.capture_buffer(i)) == p
+        off += len(p)
+    assert bytes(h.getDataBuffer()[: len(parts[0])]) == parts[0]          # reference view: past captures[0]'s header
+    # single-capture conforming file: one segment covering the payload
+    mp2 = write_sigmf(tmp_path, "y", dt, parts[0])
+    h2 = sigmf.SigMfHelper().load(mp2)
+    assert h2.capture_segments() == [(0, 0, 1000, 100e6)]
+    # a truncated last capture is clipped to whole samples available
+    (tmp_path / "x.bin").write_bytes(blob[:-5])
+    assert sigmf.SigMfHelper().load(mp).capture_segments()[2][2] == 775
