@@ -19,8 +19,10 @@
  * on one engine serialise on an internal lock, different engines run concurrently.
  * There is NO CPU fallback: without a CUDA device sa_engine_create fails with SA_ERR_NO_DEVICE.
  * The *_device entry points are asynchronous on the caller's stream and use per-engine workspaces:
- * successive device calls on ONE engine must be issued on one stream (or be ordered by the caller);
- * use one engine per stream for concurrent device work.
+ * successive device calls on ONE engine must be issued on one stream (or be ordered by the caller),
+ * and a host-buffer call on that engine may only follow once the device call's stream has been
+ * synchronised (the host-buffer entry points run on the engine's own streams and return when their
+ * results are in the caller's memory).  Use one engine per stream for concurrent device work.
  */
 #ifndef SA_ENGINE_H
 #define SA_ENGINE_H

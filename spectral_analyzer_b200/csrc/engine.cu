@@ -368,6 +368,12 @@ int check_spec_params(const sa_spectrogram_params* p, int* prec_out) {
     if (p->nfft < 64 || p->nfft > 65536)
         return set_error(SA_ERR_UNSUPPORTED, "nfft %u outside 64..65536 (main-scene.fxml:129)", p->nfft);
     if (p->hop == 0) return set_error(SA_ERR_INVALID_ARG, "hop is 0");
+    // frame starts and output offsets are 64-bit signed on the device (MainController.java:984 extended to int64)
+    const uint64_t lim = 1ull << 62;
+    if (p->start_sample >= lim || p->hop >= lim || (p->n_frames && p->hop > (lim - p->start_sample) / p->n_frames))
+        return set_error(SA_ERR_INVALID_ARG, "start_sample + n_frames * hop overflows 62 bits");
+    if (p->n_frames > lim / ((uint64_t)p->nfft * 8))
+        return set_error(SA_ERR_INVALID_ARG, "n_frames * nfft output bytes overflow 62 bits");
     if (p->window < SA_WIN_RECT || p->window > SA_WIN_BLACKMAN_HARRIS) return set_error(SA_ERR_INVALID_ARG, "unknown window %d", p->window);
     if (p->db_mode != SA_DB_MAG_1E10 && p->db_mode != SA_DB_POWER) return set_error(SA_ERR_INVALID_ARG, "unknown db_mode %d", p->db_mode);
     if (p->out_kind < SA_OUT_F32_DB || p->out_kind > SA_OUT_RGBA8) return set_error(SA_ERR_INVALID_ARG, "unknown out_kind %d", p->out_kind);

@@ -296,3 +296,18 @@ def test_four_step_through_the_chunked_host_pipeline(monkeypatch, nfft, dt, prec
         else:
             check_db_parity(got, ref)
     eng.close()
+
+
+def test_index_overflow_is_rejected_not_wrapped(engine):
+    """Frame indexing is 64-bit (MainController.java:984 extended): requests whose sample or output offsets would
+    wrap are refused with INVALID_ARG before anything is launched."""
+    raw = synth.recording(4096, "cf32_le", seed=1)
+    out = np.empty((1, 1024), np.float32)
+    for kw in (dict(n_frames=1 << 40, hop=1 << 30), dict(n_frames=2, hop=1 << 62), dict(n_frames=1, start_sample=1 << 63),
+               dict(n_frames=1 << 60, hop=1)):
+        with pytest.raises(EngineError) as ei:
+            engine.spectrogram(raw, "cf32_le", 1024, kw.pop("n_frames"), out=out, **kw)
+        assert ei.value.code == 1
+    # large but representable offsets past EOF give fill rows
+    got = engine.spectrogram(raw, "cf32_le", 1024, 2, hop=1024, start_sample=1 << 40)
+    assert (got == -150.0).all()

@@ -83,7 +83,8 @@ def test_gpu_tiled_view_equals_direct_render(engine, reduce, fpc):
     raw = synth.recording(n, "ci16_le", seed=9)
     cache = CanvasTileCache(engine, tile_w=128, max_tiles=8)
     kw = dict(hop=nfft, window="hann", frames_per_column=fpc, reduce=reduce, colormap="Heatmap")
-    for start in (0, 3 * nfft * fpc + 11, 450 * nfft * fpc + 11):            # the last view runs past EOF
+    # the third view runs past EOF; the fourth overlaps tiles of the second and third (same phase)
+    for start in (0, 3 * nfft * fpc + 11, 450 * nfft * fpc + 11, 200 * nfft * fpc + 11):
         direct = engine.render_canvas(raw, "ci16_le", nfft, W, H, 1e6, start_sample=start, **kw)
         tiled = cache.view(raw, "ci16_le", nfft, W, H, 1e6, start_sample=start, **kw)
         assert np.array_equal(direct, tiled)
