@@ -12,6 +12,12 @@
 
 namespace sa {
 
+#ifndef SA_LARGE_DUAL_DEFAULT
+#define SA_LARGE_DUAL_DEFAULT 0
+#endif
+constexpr bool kLargeDualDefault = SA_LARGE_DUAL_DEFAULT != 0;
+constexpr uint64_t kLargeDualWsMb = 48;
+
 // ---------------- parallel host copies ----------------
 CopyPool::CopyPool(int workers) {
     for (int i = 0; i < workers; i++) threads_.emplace_back([this] { worker(); });
@@ -300,22 +306,50 @@ int Engine::launch_spectrogram_large(const void* d_iq, uint64_t n_samples, const
             return SA_OK;
         }
     }
-    static const uint64_t ws_mb = getenv("SA_LARGE_WS_MB") ? (uint64_t)atoi(getenv("SA_LARGE_WS_MB")) : 512;
+    // Two workspaces, two streams: even chunks run on the caller's stream, odd chunks on a helper stream forked
+    // from it, so that one chunk's column pass fills the SMs the other chunk's row pass leaves idle in its last
+    // wave, and workspaces small enough to stay in L2 no longer mean under-filled grids (SA_LARGE_DUAL=0 disables).
+    static const char* dual_env = getenv("SA_LARGE_DUAL");
+    static const bool dual_on = dual_env ? atoi(dual_env) != 0 : kLargeDualDefault;
+    static const uint64_t ws_mb = getenv("SA_LARGE_WS_MB") ? (uint64_t)atoi(getenv("SA_LARGE_WS_MB"))
+                                                            : (dual_on ? kLargeDualWsMb : 512);
     const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(p.n_frames, (ws_mb << 20) / per_frame));
+    const bool dual = dual_on && p.n_frames > chunk;
+    const int ai = (ws == 2) ? 0 : ws - 4;                 // helper index: device API 0, host-pipeline slots 1..3
     rc = ensure_scratch(ws, chunk * per_frame);
     if (rc) return rc;
-    a.ws = scratch[ws];
+    if (dual) {
+        rc = ensure_scratch(8 + ai, chunk * per_frame);
+        if (rc) return rc;
+        if (!large_aux[ai]) {
+            e = cudaStreamCreateWithFlags(&large_aux[ai], cudaStreamNonBlocking);
+            for (int j = 0; j < 2 && e == cudaSuccess; j++) e = cudaEventCreateWithFlags(&large_ev[ai][j], cudaEventDisableTiming);
+            if (e != cudaSuccess) return cuda_fail(e, "four-step helper stream");
+        }
+        e = cudaEventRecord(large_ev[ai][0], stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(large_aux[ai], large_ev[ai][0], 0);
+        if (e != cudaSuccess) return cuda_fail(e, "four-step fork");
+    }
     e = cudaFuncSetAttribute(k->fn_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->smem_cols);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k->fn_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->smem_rows);
     if (e != cudaSuccess) return cuda_fail(e, "large FFT smem attribute");
-    for (uint64_t f0 = 0; f0 < p.n_frames; f0 += chunk) {
+    uint64_t c = 0;
+    for (uint64_t f0 = 0; f0 < p.n_frames; f0 += chunk, c++) {
         const unsigned nf = (unsigned)std::min<uint64_t>(chunk, p.n_frames - f0);
+        const bool odd = dual && (c & 1);
+        cudaStream_t st = odd ? large_aux[ai] : stream;
+        a.ws = scratch[odd ? 8 + ai : ws];
         a.frame0 = (long long)f0;
-        e = cudaLaunchKernel(k->fn_cols, dim3(k->n2 / kLargeC, nf), dim3(k->cta_cols), args, k->smem_cols, stream);
+        e = cudaLaunchKernel(k->fn_cols, dim3(k->n2 / kLargeC, nf), dim3(k->cta_cols), args, k->smem_cols, st);
         if (e != cudaSuccess) return cuda_fail(e, "launch large_cols_kernel");
-        e = cudaLaunchKernel(k->fn_rows, dim3(k->n1 / kLargeC, nf), dim3(k->cta_rows), args, k->smem_rows, stream);
+        e = cudaLaunchKernel(k->fn_rows, dim3(k->n1 / kLargeC, nf), dim3(k->cta_rows), args, k->smem_rows, st);
         if (e != cudaSuccess) return cuda_fail(e, "launch large_rows_kernel");
         launches += 2;
+    }
+    if (dual) {
+        e = cudaEventRecord(large_ev[ai][1], large_aux[ai]);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, large_ev[ai][1], 0);
+        if (e != cudaSuccess) return cuda_fail(e, "four-step join");
     }
     return SA_OK;
 }
@@ -591,6 +625,10 @@ Engine::~Engine() {
         if (slots[i].stream) cudaStreamDestroy(slots[i].stream);
         if (slots[i].h_in) cudaFreeHost(slots[i].h_in);
         if (slots[i].h_out) cudaFreeHost(slots[i].h_out);
+    }
+    for (int i = 0; i < 4; i++) {
+        if (large_aux[i]) cudaStreamDestroy(large_aux[i]);
+        for (int j = 0; j < 2; j++) if (large_ev[i][j]) cudaEventDestroy(large_ev[i][j]);
     }
     delete copy_pool;
     for (auto& r : registered) cudaHostUnregister(const_cast<void*>(r));

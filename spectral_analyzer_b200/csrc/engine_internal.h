@@ -26,7 +26,7 @@ int check_spec_params(const sa_spectrogram_params* p, int* prec_out);   // valid
 void fill_load_params(LoadParams& lp, const void* base, int dtype, int big_endian);
 
 constexpr int kSlots = 3;
-constexpr int kScratch = 8;
+constexpr int kScratch = 12;
 
 struct Slot {
     cudaStream_t stream = nullptr;
@@ -72,8 +72,11 @@ struct Engine {
     // device workspaces: [0] annotation plan + taps, [1] Welch plan + partial spectra, [2] four-step FFT,
     // [3] canvas / canvas dB rows, [4] signal lists of the packer / series kernels,
     // [5..7] four-step FFT workspaces of the host pipeline's slots (their chunks run concurrently on three streams)
+    // [8..11] second four-step workspace of the same callers (two-stream chunk overlap, launch_spectrogram_large)
     void* scratch[kScratch] = {};
     size_t scratch_cap[kScratch] = {};
+    cudaStream_t large_aux[4] = {};                  // helper stream per four-step caller (device API, slots 0..2)
+    cudaEvent_t large_ev[4][2] = {};                 // fork / join events of that helper stream
 
     ~Engine();
     int twiddle_table(const SpecKernelInfo& k, const void** d_tab);
