@@ -98,7 +98,7 @@ __device__ __forceinline__ double2 ld_cg(const double2* p) { return __ldcg(p); }
 // row group `rg` (C rows k1) of `frame`: N2-point FFTs of A[k1][.] from ws_frame, dB, fft-shifted store
 template <typename T, int N1, int N2>
 __device__ __forceinline__ void large_rows_body(const LargeArgs& a, const long long frame, const cpx<T>* __restrict__ ws_frame,
-                                                const int rg, unsigned char* smem_raw) {
+                                                const int rg, unsigned char* smem_raw, const double* ltab = nullptr) {
     using G = Geo<T, N2>;
     constexpr int P = G::P, TPF = G::TPF, N = N1 * N2, C = kLargeC, THREADS = C * TPF;
     const int t = threadIdx.x % TPF, fl = threadIdx.x / TPF;      // element is the fast index
@@ -114,8 +114,8 @@ __device__ __forceinline__ void large_rows_body(const LargeArgs& a, const long l
         for (int q = 0; q < P; q++) v[q] = ld_cg(&ws[t + TPF * q]);
         TwSeed<T> seed; seed.om = mk2<T>((T)1, (T)0); seed.oh = seed.om;
         fft_frame<T, N2, false, false, true>(v, t, sm, reinterpret_cast<const cpx<T>*>(a.tw2), nullptr, seed);
-        if (a.s.db_mode == DBM_MAG_1E10) bins_to_db<T, P, DBM_MAG_1E10>(v, db);
-        else bins_to_db<T, P, DBM_POWER>(v, db);
+        if (a.s.db_mode == DBM_MAG_1E10) bins_to_db<T, P, DBM_MAG_1E10>(v, db, ltab);
+        else bins_to_db<T, P, DBM_POWER>(v, db, ltab);
     } else {
 #pragma unroll
         for (int q = 0; q < P; q++) db[q] = (T)a.s.eof_fill;
@@ -142,8 +142,14 @@ template <typename T, int N1, int N2>
 __global__ void __launch_bounds__(kLargeC * Geo<T, N2>::TPF, SA_LARGE_ROWS_MINB)
 large_rows_kernel(const LargeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const double* ltab = nullptr;
+    if constexpr (sizeof(T) == 8 && SA_F64_FAST_DB) {
+        __shared__ double s_ltab[128];
+        f64_ltab_init(s_ltab);
+        ltab = s_ltab;
+    }
     large_rows_body<T, N1, N2>(a, a.frame0 + blockIdx.y, reinterpret_cast<const cpx<T>*>(a.ws) + (size_t)blockIdx.y * (N1 * N2),
-                               blockIdx.x, smem_raw);
+                               blockIdx.x, smem_raw, ltab);
 }
 
 // ---- cluster variant (N1 == N2): one thread-block cluster of kLargeCluster CTAs per frame ----
@@ -168,6 +174,12 @@ large_cluster_kernel(const LargeArgs a) {
     constexpr int COL_GROUPS = N2 / C / kLargeCluster, ROW_GROUPS = N1 / C / kLargeCluster;
     static_assert(COL_GROUPS >= 1 && ROW_GROUPS >= 1, "every CTA of the cluster owns whole groups");
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const double* ltab = nullptr;
+    if constexpr (sizeof(T) == 8 && SA_F64_FAST_DB) {
+        __shared__ double s_ltab[128];
+        f64_ltab_init(s_ltab);
+        ltab = s_ltab;
+    }
     const unsigned rank = cluster_ctarank();
     // two slices per cluster: the column step of the next frame fills one while slower CTAs still read the other
     cpx<T>* ws = reinterpret_cast<cpx<T>*>(a.ws) + (size_t)cluster_id_x() * (2 * N);
@@ -186,7 +198,7 @@ large_cluster_kernel(const LargeArgs a) {
         cluster_sync_all();                     // every column of frame f is in the workspace; frame f - stride fully read
 #pragma unroll 1
         for (int g = 0; g < ROW_GROUPS; g++) {
-            large_rows_body<T, N1, N2>(a, a.frame0 + f, ws + (size_t)buf * N, (int)rank * ROW_GROUPS + g, smem_raw);
+            large_rows_body<T, N1, N2>(a, a.frame0 + f, ws + (size_t)buf * N, (int)rank * ROW_GROUPS + g, smem_raw, ltab);
             __syncthreads();
         }
         if (f + stride < a.s.n_frames) cols(f + stride, buf ^ 1);

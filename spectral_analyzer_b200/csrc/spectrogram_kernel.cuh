@@ -37,6 +37,9 @@ struct SpecArgs {
     int         cmap;
 };
 
+#ifndef SA_F64_FAST_DB
+#define SA_F64_FAST_DB 1        // table-driven FP64 dB epilogue (0: library log10 / sqrt)
+#endif
 __device__ __forceinline__ float lg2_approx(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
@@ -51,12 +54,39 @@ template <int MODE> __device__ __forceinline__ double to_db(double re, double im
     return 10.0 * log10(re * re + im * im + 1e-20);
 }
 
+// ---- FP64 dB without the library log10 / sqrt ----
+// The literal form costs ~100 of the ~160 instructions per bin of the FP64 kernels.  Within the FP64 tolerance of
+// 1e-9 dB:  20 log10(|X| + c) = 10 log10 p + 20 log10(1 + c / |X|),  p = |X|^2;  for p >= 1e-10 the second term is
+// (20 / ln 10) (eps - eps^2 / 2), eps = c rsqrt(p) <= 1e-5, evaluated in FP32 (< 3e-11 dB);  log2 p = e + log2 m,
+// m in [1, 2) split by its top 7 mantissa bits k: m c_k = 1 + r, c_k = rcp.approx(cell midpoint) (one MUFU, the same
+// value the table was built from), |r| <= 2^-8, log1p(r) to r^4 / 4 (truncation 2e-13), -log2 c_k from a 128-entry
+// shared-memory table filled at kernel start with the library log2.  Bins below the threshold (or non-finite) take
+// the literal form, per thread.
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rsqrt_approx(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float ltab_cell_mid(int k) { return __int_as_float(0x3f800000 | (k << 16) | 0x8000); }   // 1 + (k + 0.5) / 128
+__device__ __forceinline__ void f64_ltab_init(double* tab) {          // every thread of the CTA, before the first frame
+    for (int k = threadIdx.x; k < 128; k += blockDim.x) tab[k] = -log2((double)rcp_approx(ltab_cell_mid(k)));
+    __syncthreads();
+}
+__device__ __forceinline__ double log2_tab(const double p, const double* tab) {      // p normal, positive
+    const int hi = __double2hiint(p);
+    const int k = (hi >> 13) & 127;
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(p));
+    const double r = fma(m, (double)rcp_approx(ltab_cell_mid(k)), -1.0);
+    double q = fma(r, -0.25, 1.0 / 3.0);
+    q = fma(r, q, -0.5);
+    q = fma(r, q, 1.0);                                    // log1p(r) / r
+    const double e = (double)((hi >> 20) - 1023);
+    return fma(r * q, 1.4426950408889634074, e + tab[k]);
+}
+
 // dB of all P bins of a thread.  FP32 fast path for MAG_1E10: when |X| >= 2^-9 the FP32 sum
 // |X| + 1e-10 rounds back to |X| (ulp(|X|) >= 2^-32, so 1e-10 is below half an ulp), hence
 // 20 log10(|X| + 1e-10) equals 10 log10(|X|^2) and the square root is skipped; threads holding a
 // bin with |X|^2 < 2^-18 take the literal form.
 template <typename T, int P, int MODE>
-__device__ __forceinline__ void bins_to_db(const cpx<T> (&v)[P], T (&db)[P]) {
+__device__ __forceinline__ void bins_to_db(const cpx<T> (&v)[P], T (&db)[P], const double* tab = nullptr) {
     if constexpr (sizeof(T) == 4 && MODE == DBM_MAG_1E10) {
         // |X|^2 and the dB scale run two bins per issue slot (FMUL2 / FFMA2)
         float pmin = 3.0e38f;
@@ -73,6 +103,29 @@ __device__ __forceinline__ void bins_to_db(const cpx<T> (&v)[P], T (&db)[P]) {
         } else {
 #pragma unroll
             for (int q = 0; q < P; q++) db[q] = 6.02059991327962f * lg2_approx(sqrt_approx(db[q]) + 1e-10f);
+        }
+    } else if constexpr (sizeof(T) == 8 && SA_F64_FAST_DB) {
+        bool fast = true;
+#pragma unroll
+        for (int q = 0; q < P; q++) {
+            db[q] = fma(v[q].x, v[q].x, v[q].y * v[q].y);
+            if constexpr (MODE == DBM_MAG_1E10) fast = fast && (db[q] >= 1e-10) && (db[q] < 1e300);
+            else fast = fast && (db[q] < 1e300);           // p + 1e-20 is always a normal number; NaN fails
+        }
+        if (fast) {
+#pragma unroll
+            for (int q = 0; q < P; q++) {
+                if constexpr (MODE == DBM_MAG_1E10) {
+                    const float eps = 1e-10f * rsqrt_approx((float)db[q]);
+                    const float corr = 8.685889638065037f * eps * __fmaf_rn(-0.5f, eps, 1.0f);
+                    db[q] = fma(log2_tab(db[q], tab), 3.0102999566398119521, (double)corr);
+                } else {
+                    db[q] = 3.0102999566398119521 * log2_tab(db[q] + 1e-20, tab);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < P; q++) db[q] = to_db<MODE>(v[q].x, v[q].y);
         }
     } else {
 #pragma unroll
@@ -183,11 +236,11 @@ __device__ __forceinline__ const T* setup_window(const SpecArgs& a, unsigned cha
 // out[(k + N/2) % N] (SpectralService.java:76-82), k = t + TPF*q.
 template <typename T, int N>
 __device__ __forceinline__ void store_row(const SpecArgs& a, const long long frame, const int t,
-                                          const cpx<T> (&v)[Plan<T, N>::P]) {
+                                          const cpx<T> (&v)[Plan<T, N>::P], const double* ltab = nullptr) {
     constexpr int P = Geo<T, N>::P, TPF = Geo<T, N>::TPF;
     T db[P];
-    if (a.db_mode == DBM_MAG_1E10) bins_to_db<T, P, DBM_MAG_1E10>(v, db);
-    else bins_to_db<T, P, DBM_POWER>(v, db);
+    if (a.db_mode == DBM_MAG_1E10) bins_to_db<T, P, DBM_MAG_1E10>(v, db, ltab);
+    else bins_to_db<T, P, DBM_POWER>(v, db, ltab);
     const size_t row = (size_t)frame * N;
     const int k0 = (t + N / 2) & (N - 1);
     if (a.out_kind == OUT_F32_DB) {
@@ -223,6 +276,12 @@ spectrogram_kernel(const SpecArgs a) {
     using G = Geo<T, N>;
     constexpr int P = G::P, TPF = G::TPF, FPC = G::FPC;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const double* ltab = nullptr;
+    if constexpr (sizeof(T) == 8 && SA_F64_FAST_DB) {
+        __shared__ double s_ltab[128];
+        f64_ltab_init(s_ltab);
+        ltab = s_ltab;
+    }
     const int fl = threadIdx.x / TPF;            // frame slot in this CTA
     const int t  = threadIdx.x % TPF;            // thread within the frame
     cpx<T>* sm = reinterpret_cast<cpx<T>*>(smem_raw) + (size_t)fl * G::SM_ELEMS;
@@ -276,7 +335,7 @@ spectrogram_kernel(const SpecArgs a) {
 
         if (!in_grid) continue;
         if (!readable) { store_fill<T, N>(a, frame, t); continue; }
-        store_row<T, N>(a, frame, t, v);
+        store_row<T, N>(a, frame, t, v, ltab);
     }
 }
 
