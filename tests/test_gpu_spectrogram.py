@@ -311,3 +311,22 @@ def test_index_overflow_is_rejected_not_wrapped(engine):
     # large but representable offsets past EOF give fill rows
     got = engine.spectrogram(raw, "cf32_le", 1024, 2, hop=1024, start_sample=1 << 40)
     assert (got == -150.0).all()
+
+
+@pytest.mark.parametrize("nfft", [256, 1024, 16384])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_fp64_db_epilogue_over_the_dynamic_range(engine, nfft, mode):
+    """The FP64 dB epilogue switches between a table-driven log (|X|^2 >= 1e-10) and the literal
+    20 log10(sqrt(p) + 1e-10) per thread: frames of white noise scaled from 1e-13 to 1e100 cover both sides of the
+    threshold, exact zeros and the 1e-10 floor.  White noise keeps every bin within ~25 dB of the frame's maximum,
+    so ALL bins are held to the FP64 tolerance of 1e-9 dB."""
+    amps = [0.0, 1e-13, 1e-9, 3e-8, 1e-7, 3e-7, 1e-6, 1e-5, 1e-3, 1.0, 7.0, 1e6, 1e30, 1e100]
+    rng = np.random.default_rng(nfft + mode)
+    x = rng.standard_normal((len(amps), nfft, 2)) * np.asarray(amps)[:, None, None]
+    raw = np.ascontiguousarray(x.reshape(-1), np.float64).view(np.uint8)
+    ref = co.spectrogram(raw, "cf64_le", 0, nfft, nfft, "rect", len(amps), db_mode=mode)
+    got = engine.spectrogram(raw, "cf64_le", nfft, len(amps), hop=nfft, window="rect", out_kind="f64", db_mode=mode)
+    assert np.isfinite(got).all()
+    assert np.abs(got - ref).max() < 1e-9, np.abs(got - ref).max(axis=1)
+    # exact zeros: 20 log10(1e-10) = 10 log10(1e-20) = -200 (literal form in magnitude mode, the table log in power mode)
+    assert (got[0] == -200.0).all() if mode == 0 else np.abs(got[0] + 200.0).max() < 1e-11
