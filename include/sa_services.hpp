@@ -8,9 +8,15 @@
 // (S/ = src/main/java/net/kcundercover/spectral_analyzer/).  Java exceptions map to C++ ones:
 //   MathIllegalArgumentException -> std::invalid_argument, IndexOutOfBoundsException -> std::out_of_range.
 #pragma once
+#include <algorithm>
 #include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <list>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
+#include <utility>
 #include <vector>
 
 #include "sa_engine.h"
@@ -130,6 +136,62 @@ struct SpectrogramRenderer {
                                   (uint64_t)framesPerColumn, reduce, out.data()));
         return out;
     }
+};
+
+// Scrolling views: the reference redraws every column on each scroll-bar move (MainController.java:319 -> :980-999).
+// A view is assembled from fixed-width tiles of canvas columns kept in an LRU map, so that a scroll step renders
+// only the tiles that enter the view (same scheme as spectral_analyzer_b200/tiles.py).  Tiles are aligned on global
+// column indices of the view's phase (start % samples-per-column); the result is bit-identical to one
+// renderSpectrogram call at the same start.
+class CanvasTileCache {
+public:
+    CanvasTileCache(Engine& e, int tileW = 256, size_t maxTiles = 64) : e_(e), tileW_(tileW), maxTiles_(maxTiles) {
+        if (tileW < 1 || maxTiles < 1) throw std::invalid_argument("tileW and maxTiles must be positive");
+    }
+    size_t hits() const { return hits_; }
+    size_t misses() const { return misses_; }
+    void clear() { lru_.clear(); index_.clear(); }
+
+    std::vector<uint8_t> view(const MappedByteBuffer& buffer, int64_t currentSampleOffset, int canvasW, int canvasH,
+                              int fftSize, const std::string& datatype, double sampleRate, double minDb, double maxDb,
+                              int colormap, int64_t framesPerColumn = 1, int reduce = SA_REDUCE_NEAREST) {
+        if (currentSampleOffset < 0) throw std::invalid_argument("currentSampleOffset must be non-negative");
+        const int64_t spc = framesPerColumn * (int64_t)fftSize;
+        const int64_t phase = currentSampleOffset % spc, g0 = currentSampleOffset / spc;
+        std::vector<uint8_t> out((size_t)canvasW * canvasH * 4);
+        for (int64_t k = g0 / tileW_; k <= (g0 + canvasW - 1) / tileW_; k++) {
+            char key[256];
+            std::snprintf(key, sizeof(key), "%p/%llu/%s/%d/%d/%lld/%d/%d/%.17g/%.17g/%.17g/%lld/%lld", buffer.data,
+                          (unsigned long long)buffer.capacity, datatype.c_str(), fftSize, canvasH, (long long)framesPerColumn,
+                          reduce, colormap, minDb, maxDb, sampleRate, (long long)phase, (long long)k);
+            auto it = index_.find(key);
+            if (it == index_.end()) {
+                misses_++;
+                lru_.emplace_front(key, SpectrogramRenderer::renderSpectrogram(
+                    e_, buffer, phase + k * tileW_ * spc, tileW_, canvasH, fftSize, datatype, sampleRate, minDb, maxDb,
+                    colormap, framesPerColumn, reduce));
+                index_[key] = lru_.begin();
+                while (lru_.size() > maxTiles_) { index_.erase(lru_.back().first); lru_.pop_back(); }
+                it = index_.find(key);
+            } else {
+                hits_++;
+                lru_.splice(lru_.begin(), lru_, it->second);
+            }
+            const std::vector<uint8_t>& tile = it->second->second;
+            const int64_t lo = std::max<int64_t>(g0, k * tileW_), hi = std::min<int64_t>(g0 + canvasW, (k + 1) * tileW_);
+            for (int y = 0; y < canvasH; y++)
+                std::memcpy(&out[((size_t)y * canvasW + (size_t)(lo - g0)) * 4],
+                            &tile[((size_t)y * tileW_ + (size_t)(lo - k * tileW_)) * 4], (size_t)(hi - lo) * 4);
+        }
+        return out;
+    }
+private:
+    using Entry = std::pair<std::string, std::vector<uint8_t>>;
+    Engine& e_;
+    int tileW_;
+    size_t maxTiles_, hits_ = 0, misses_ = 0;
+    std::list<Entry> lru_;
+    std::unordered_map<std::string, std::list<Entry>::iterator> index_;
 };
 
 // S/data/IqData.java: the binary packers of the downconverted double[2][N] (getInterleavedBinary :160-187)

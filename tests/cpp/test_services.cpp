@@ -63,6 +63,18 @@ int main() {
     for (int y = 1; y < 64; y++) if (px[(size_t)(y * 4) * 4] > px[(size_t)(best * 4) * 4]) best = y;
     const int f_row = 63 - best;                                   // y flipped, MainController.java:1288
     EXPECT((int)((double)f_row / 64 * n) <= arg && arg < (int)((double)(f_row + 1) / 64 * n));
+    // tile cache: a 64-pt view over the same buffer, scrolled by 3 columns, equals the direct render; tiles are reused
+    {
+        const int nf = 64, W = 40, H = 16;
+        CanvasTileCache cache(eng, 16, 8);
+        for (int64_t start : {0, 3 * nf, 3 * nf + 5, 19 * nf + 5}) {
+            std::vector<uint8_t> direct = SpectrogramRenderer::renderSpectrogram(eng, buf, start, W, H, nf, "cf32_le", 1.0e6,
+                                                                                -160.0, -30.0, SA_CMAP_HEATMAP);
+            std::vector<uint8_t> tiled = cache.view(buf, start, W, H, nf, "cf32_le", 1.0e6, -160.0, -30.0, SA_CMAP_HEATMAP);
+            EXPECT(direct == tiled);
+        }
+        EXPECT(cache.hits() > 0 && cache.misses() > 0);
+    }
     std::printf("cpp services ok\n");
     return 0;
 }
