@@ -387,12 +387,14 @@ int32_t sa_downconvert_psd_batch(sa_engine* engine, const void* iq, uint64_t iq_
             pos += anns[i].count;
         }
     }
-    if (e != cudaSuccess) return cuda_fail(e, "H2D annotation spans");
+    // on failure nothing of the caller's may still be in flight when this returns
+    auto fail = [&](int code) { cudaStreamSynchronize(s.stream); return code; };
+    if (e != cudaSuccess) return fail(cuda_fail(e, "H2D annotation spans"));
     double* d_iq_out = (double*)s.d_out;
     double* d_psd = out_psd_db ? (double*)((char*)s.d_out + out_doubles * 8) : nullptr;
     rc = run_batch_device(engine, s.d_in, in_samples, dtype, big_endian, sample_rate, local.data(), n_ann, psd_nfft,
                           psd_hop, psd_window, d_iq_out, dev_off.data(), d_psd, s.stream);
-    if (rc) return rc;
+    if (rc) return fail(rc);
     if (out_iq) {
         for (uint32_t i = 0; i < n_ann && e == cudaSuccess; i++) {
             const uint64_t m2 = 2 * (anns[i].count / (uint64_t)anns[i].down);
@@ -401,7 +403,7 @@ int32_t sa_downconvert_psd_batch(sa_engine* engine, const void* iq, uint64_t iq_
     }
     if (e == cudaSuccess && out_psd_db)
         e = cudaMemcpyAsync(out_psd_db, d_psd, psd_bytes, cudaMemcpyDeviceToHost, s.stream);
-    if (e != cudaSuccess) return cuda_fail(e, "D2H annotation results");
+    if (e != cudaSuccess) return fail(cuda_fail(e, "D2H annotation results"));
     e = cudaStreamSynchronize(s.stream);
     if (e != cudaSuccess) return cuda_fail(e, "annotation batch");
     return SA_OK;

@@ -163,14 +163,14 @@ int32_t sa_render_canvas(sa_engine* engine, const void* iq, uint64_t iq_bytes, c
     const bool in_pinned = host_ptr_is_pinned(iq);
     uint64_t c = 0;
     cudaError_t e = cudaSuccess;
-    for (uint64_t c0 = 0; c0 < canvas_w; c0 += cpc, c++) {
+    for (uint64_t c0 = 0; c0 < canvas_w && rc == SA_OK; c0 += cpc, c++) {
         Slot& s = engine->slots[c % kSlots];
         rc = engine->ensure_slot(s, in_cap, out_cap);
-        if (rc) return rc;
+        if (rc) break;
         rc = engine->ensure_staging(s, in_pinned ? 0 : in_cap, 0);
-        if (rc) return rc;
+        if (rc) break;
         e = cudaStreamSynchronize(s.stream);
-        if (e != cudaSuccess) return cuda_fail(e, "slot sync");
+        if (e != cudaSuccess) { rc = cuda_fail(e, "slot sync"); break; }
         const uint64_t nc = std::min<uint64_t>(cpc, canvas_w - c0);
         const uint64_t nf = nc * frames_per_column;
         const uint64_t s_begin = q.start_sample + c0 * frames_per_column * q.hop;
@@ -181,21 +181,22 @@ int32_t sa_render_canvas(sa_engine* engine, const void* iq, uint64_t iq_bytes, c
             const void* src = (const char*)iq + s_begin * bps;
             if (!in_pinned) { engine->host_copy(s.h_in, src, ns * bps); src = s.h_in; }
             e = cudaMemcpyAsync(s.d_in, src, ns * bps, cudaMemcpyHostToDevice, s.stream);
-            if (e != cudaSuccess) return cuda_fail(e, "H2D");
+            if (e != cudaSuccess) { rc = cuda_fail(e, "H2D"); break; }
         }
         sa_spectrogram_params r = q;
         r.start_sample = 0;
         r.n_frames = nf;
         rc = engine->launch_spectrogram(s.d_in, ns, r, prec, s.d_out, s.stream, 5 + (int)(c % kSlots));
-        if (rc) return rc;
+        if (rc) break;
         rc = launch_canvas(engine, ca, (const float*)s.d_out, (int)c0, (int)nc, s.stream);
-        if (rc) return rc;
     }
+    // drain on every path: the staging buffers and the caller's samples must not be in flight when this returns
     for (int i = 0; i < kSlots; i++)
         if (engine->slots[i].stream) {
             e = cudaStreamSynchronize(engine->slots[i].stream);
-            if (e != cudaSuccess) return cuda_fail(e, "canvas pipeline drain");
+            if (e != cudaSuccess && rc == SA_OK) rc = cuda_fail(e, "canvas pipeline drain");
         }
+    if (rc) return rc;
     e = cudaMemcpy(out_rgba, engine->scratch[3], canvas_bytes, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) return cuda_fail(e, "D2H canvas");
     return SA_OK;
