@@ -12,7 +12,6 @@
 
 using namespace sa;
 
-struct sa_engine : public sa::Engine {};
 
 namespace {
 
@@ -278,11 +277,6 @@ static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, i
 
 }  // namespace sa
 
-#define ENGINE_ENTER(engine)                                                         \
-    if (!(engine)) return set_error(SA_ERR_INVALID_ARG, "engine is NULL");            \
-    std::lock_guard<std::mutex> lock_((engine)->mu);                                  \
-    { cudaError_t e_ = cudaSetDevice((engine)->device);                               \
-      if (e_ != cudaSuccess) return cuda_fail(e_, "cudaSetDevice"); }
 
 static int check_psd(uint32_t nfft, uint64_t* hop, int32_t window) {
     if (nfft == 0 || (nfft & (nfft - 1))) return set_error(SA_ERR_INVALID_ARG, "psd nfft %u is not a power of two", nfft);

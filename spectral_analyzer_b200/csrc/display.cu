@@ -11,13 +11,7 @@
 
 using namespace sa;
 
-struct sa_engine : public sa::Engine {};
 
-#define ENGINE_ENTER(engine)                                                         \
-    if (!(engine)) return set_error(SA_ERR_INVALID_ARG, "engine is NULL");            \
-    std::lock_guard<std::mutex> lock_((engine)->mu);                                  \
-    { cudaError_t e_ = cudaSetDevice((engine)->device);                               \
-      if (e_ != cudaSuccess) return cuda_fail(e_, "cudaSetDevice"); }
 
 namespace {
 

@@ -99,3 +99,14 @@ struct Engine {
 };
 
 }  // namespace sa
+
+// The opaque handle of include/sa_engine.h.
+struct sa_engine : public sa::Engine {};
+
+// First statement of every entry point that takes an engine: NULL check, the per-engine lock (calls on one
+// engine serialise; different engines run concurrently) and device selection for the calling thread.
+#define ENGINE_ENTER(engine)                                                         \
+    if (!(engine)) return set_error(SA_ERR_INVALID_ARG, "engine is NULL");            \
+    std::lock_guard<std::mutex> lock_((engine)->mu);                                  \
+    { cudaError_t e_ = cudaSetDevice((engine)->device);                               \
+      if (e_ != cudaSuccess) return cuda_fail(e_, "cudaSetDevice"); }
