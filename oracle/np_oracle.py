@@ -110,6 +110,8 @@ def lowpass_taps(down):
 def downconvert(buf, datatype, start_sample, count, freq_off, down, fast=False):
     """Self-defined spec of S/services/ExtractDownConvertService.java:54-117 (JDSP not vendored)."""
     kind, _ = _split(datatype)
+    if count // down == 0:                          # nothing to emit (the C restatement returns length 0 as well)
+        return np.zeros((2, 0), np.float64)
     x = decode(buf, start_sample * BYTES_PER_IQ[kind], count, datatype)
     n = np.arange(count)
     y = x * np.exp(-2j * np.pi * np.mod(freq_off * n, 1.0))
