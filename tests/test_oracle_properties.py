@@ -83,3 +83,40 @@ def test_spectrogram_properties(log2n, seed, k, amp):
     r = co.spectrogram(np.frombuffer(tq.tobytes(), np.uint8), "cf64_le", 0, nfft, nfft, "rect", 1)[0]
     assert int(np.argmax(r)) == (k + nfft // 2) % nfft                                   # fft-shifted, SpectralService.java:78
     assert abs(r.max() - 20 * np.log10(amp * nfft + 1e-10)) < 1e-9
+
+
+@settings(max_examples=40, deadline=None)
+@given(log2n=st.integers(6, 10), extra=st.integers(0, 3000), hopdiv=st.sampled_from([1, 2, 4, 8]),
+       win=st.sampled_from(WINDOWS), seed=st.integers(0, 1 << 30), fs=st.floats(1.0, 1e8))
+def test_c_and_numpy_welch_agree(log2n, extra, hopdiv, win, seed, fs):
+    nfft = 1 << log2n
+    rng = np.random.default_rng(seed)
+    iq = rng.standard_normal((2, nfft + extra))
+    a = co.psd_welch(iq, fs, nfft, hop=nfft // hopdiv, window=win)
+    b = no.psd_welch(iq, fs, nfft, hop=nfft // hopdiv, win=win)
+    assert np.allclose(a[0], b[0], rtol=1e-12, atol=1e-9 * fs / nfft)            # frequency axis centred on 0
+    assert np.abs(a[1] - b[1]).max() < 1e-9                                      # dB/Hz
+
+
+@settings(max_examples=60, deadline=None)
+@given(n=st.integers(0, 3000), seed=st.integers(0, 1 << 30), scale=st.sampled_from([0.1, 1.0, 1.5, 40.0, 1e6]),
+       fmt=st.sampled_from(["float32", "int16"]))
+def test_c_and_numpy_iq_pack_agree_bit_for_bit(n, seed, scale, fmt):
+    rng = np.random.default_rng(seed)
+    iq = rng.standard_normal((2, n)) * scale
+    if n > 3:
+        iq[0, 0], iq[1, 1], iq[0, 2] = 1.0, -1.0, 32767.5 / 32767.0             # edges of the (short)(32767 x) narrowing
+    assert co.iq_pack(iq, fmt) == no.iq_pack(iq, fmt)
+
+
+@settings(max_examples=40, deadline=None)
+@given(n=st.integers(2, 4000), seed=st.integers(0, 1 << 30), am=st.floats(0.01, 1.0), af=st.floats(0.01, 1.0),
+       fs=st.floats(1e3, 1e8), fc=st.floats(-1e9, 1e9))
+def test_c_and_numpy_analysis_series_agree(n, seed, am, af, fs, fc):
+    rng = np.random.default_rng(seed)
+    iq = rng.standard_normal((2, n)) + 0.1
+    gm, gf = co.analysis_series(iq, fs, am, af, fc)
+    rm, rf = no.analysis_series(iq, fs, am, af, fc)
+    assert np.abs(gm - rm).max() < 1e-9
+    assert np.isnan(gf[0]) and np.isnan(rf[0])
+    assert np.abs(gf[1:] - rf[1:]).max() <= 1e-9 * fs + 1e-6 * abs(fc) * 1e-9 + 1e-6
