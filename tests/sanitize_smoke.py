@@ -1,6 +1,7 @@
 """Small invocation of every kernel family, for compute-sanitizer (memcheck / racecheck) runs:
-    compute-sanitizer --tool memcheck python tools/sanitize_smoke.py
-Sizes are tiny (the tools slow kernels down 10-100x); results are still compared with the CPU checker."""
+    compute-sanitizer --tool memcheck python tests/sanitize_smoke.py
+Sizes are tiny (the tools slow kernels down 10-100x); results are still compared with the CPU checker, which is why
+this script lives under tests/: only tests, smoke() and the bench's CPU-baseline leg may use oracle/."""
 import os
 import sys
 
