@@ -68,6 +68,26 @@ def test_product_does_not_import_oracle():
                 assert "oracle" not in txt.lower(), f + " mentions the oracle"
 
 
+def test_only_tests_smoke_and_the_bench_baseline_use_the_oracle():
+    """Outside tests/ and oracle/ itself, only bench.py (cpu_baseline / --impl reference legs) and
+    __graft_entry__.py (smoke) may import it: tools, the other bench scripts, headers and profiles helpers must not."""
+    allowed = {"bench.py", "__graft_entry__.py"}
+    offenders = []
+    for dirpath, dirs, files in os.walk(ROOT):
+        rel = os.path.relpath(dirpath, ROOT)
+        top = rel.split(os.sep)[0]
+        if top in ("tests", "oracle", ".git", "gpurun_out", "baseline", ".pytest_cache", ".hypothesis") or "__pycache__" in rel:
+            dirs[:] = []
+            continue
+        for f in files:
+            if not f.endswith((".py", ".hpp", ".h", ".java", ".cu", ".cuh")) or (rel == "." and f in allowed):
+                continue
+            txt = open(os.path.join(dirpath, f), errors="ignore").read()
+            if "import oracle" in txt or "from oracle" in txt or "c_oracle" in txt or "np_oracle" in txt or "sa_oracle" in txt:
+                offenders.append(os.path.join(rel, f))
+    assert not offenders, offenders
+
+
 def test_python_binding_covers_the_header():
     """_capi.py is the 1:1 mirror of the Panama binding: every function the header declares has its argument
     types spelled out there (no implicit int marshalling of 64-bit sizes or pointers)."""
