@@ -106,3 +106,22 @@ def test_new_entry_points_validate_arguments_without_a_gpu():
     assert b"engine is NULL" in L.sa_last_error()
     p = _capi.default_params()
     assert L.sa_render_canvas(None, None, 0, C.byref(p), 4, 4, 1, 0, None) == 1
+
+
+def test_java_binding_source_matches_the_header():
+    """The Panama binding cannot be compiled here (no JDK), so its structure is checked as text: every symbol it looks
+    up is declared in include/sa_engine.h, and its StructLayout of sa_spectrogram_params lists the header's fields in
+    the header's order with matching widths (the same order the ctypes mirror uses)."""
+    java = open(os.path.join(ROOT, "java", "net", "kcundercover", "spectral_analyzer", "services",
+                             "NativeSpectralEngine.java")).read()
+    header = open(os.path.join(ROOT, "include", "sa_engine.h")).read()
+    looked_up = set(re.findall(r'fn\("(sa_\w+)"', java))
+    assert len(looked_up) >= 12 and looked_up <= set(declared_symbols()), looked_up - set(declared_symbols())
+    body = re.search(r"typedef struct sa_spectrogram_params \{(.*?)\} sa_spectrogram_params;", header, re.S).group(1)
+    c_fields = re.findall(r"^\s*(uint32_t|int32_t|uint64_t|double)\s+(\w+);", body, re.M)
+    layout = re.search(r"PARAMS = MemoryLayout\.structLayout\((.*?)\);", java, re.S).group(1)
+    j_fields = re.findall(r'(JAVA_INT|JAVA_LONG|JAVA_DOUBLE)\.withName\("(\w+)"\)', layout)
+    width = {"uint32_t": "JAVA_INT", "int32_t": "JAVA_INT", "uint64_t": "JAVA_LONG", "double": "JAVA_DOUBLE"}
+    assert [(width[t], n) for t, n in c_fields] == j_fields
+    assert [n for _, n in c_fields] == [n for n, _ in _capi.SpectrogramParams._fields_]
+    assert C.sizeof(_capi.SpectrogramParams) == 4 * 8 + 8 * 4 + 4 * 2 + 8 * 3
