@@ -125,3 +125,60 @@ def test_java_binding_source_matches_the_header():
     assert [(width[t], n) for t, n in c_fields] == j_fields
     assert [n for _, n in c_fields] == [n for n, _ in _capi.SpectrogramParams._fields_]
     assert C.sizeof(_capi.SpectrogramParams) == 4 * 8 + 8 * 4 + 4 * 2 + 8 * 3
+
+
+def _header_prototypes():
+    """name -> (return layout, [argument layouts]) in the vocabulary of java.lang.foreign."""
+    src = open(os.path.join(ROOT, "include", "sa_engine.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+
+    def layout(t):
+        t = t.strip()
+        if "*" in t:
+            return "ADDRESS"
+        base = t.replace("const", "").split()[0]
+        return {"int32_t": "JAVA_INT", "uint32_t": "JAVA_INT", "uint64_t": "JAVA_LONG", "double": "JAVA_DOUBLE",
+                "void": "VOID"}[base]
+
+    out = {}
+    for ret, name, args in re.findall(r"SA_API\s+([\w\s\*]+?)\b(sa_\w+)\s*\((.*?)\)\s*;", src, re.S):
+        args = [a for a in (x.strip() for x in args.split(",")) if a and a != "void"]
+        # an argument is "type name": the layout comes from everything before the last identifier
+        out[name] = (layout(ret), [layout(re.sub(r"\w+$", "", a) if not a.endswith("*") else a) for a in args])
+    return out
+
+
+def test_java_function_descriptors_match_the_header_prototypes():
+    java = open(os.path.join(ROOT, "java", "net", "kcundercover", "spectral_analyzer", "services",
+                             "NativeSpectralEngine.java")).read()
+    protos = _header_prototypes()
+    found = re.findall(r'fn\("(sa_\w+)",\s*FunctionDescriptor\.(ofVoid|of)\((.*?)\)\);', java, re.S)
+    assert len(found) >= 12
+    for name, kind, body in found:
+        lay = [x.strip() for x in body.replace("\n", " ").split(",") if x.strip()]
+        ret, args = ("VOID", lay) if kind == "ofVoid" else (lay[0], lay[1:])
+        assert (ret, args) == protos[name], (name, ret, args, protos[name])
+
+
+def test_ctypes_argtypes_match_the_header_prototypes():
+    """Same check for the Python mirror: widths and pointer-ness of every argument and of the return type."""
+    L = _capi.lib()
+
+    def layout(ct):
+        if ct is None:
+            return "VOID"
+        if ct in (C.c_int32, C.c_uint32, C.c_int, C.c_uint):
+            return "JAVA_INT"
+        if ct in (C.c_uint64, C.c_int64, C.c_size_t, C.c_ulonglong, C.c_longlong):
+            return "JAVA_LONG"
+        if ct is C.c_double:
+            return "JAVA_DOUBLE"
+        return "ADDRESS"                                   # c_void_p, c_char_p, POINTER(...), structure pointers
+
+    for name, (ret, args) in _header_prototypes().items():
+        f = getattr(L, name)
+        if f.argtypes is None:
+            assert not args, name
+            continue
+        assert [layout(a) for a in f.argtypes] == args, (name, f.argtypes, args)
+        assert layout(f.restype) == ret, (name, f.restype, ret)
