@@ -182,3 +182,19 @@ def test_ctypes_argtypes_match_the_header_prototypes():
             continue
         assert [layout(a) for a in f.argtypes] == args, (name, f.argtypes, args)
         assert layout(f.restype) == ret, (name, f.restype, ret)
+
+
+def test_cpp_host_mirror_compiles_and_links_on_cpu(tmp_path):
+    """include/sa_services.hpp + tests/cpp/test_services.cpp build against libsa_engine.so with plain g++ (the binary is
+    run by the GPU test; here only the build is checked, and that the header needs nothing from CUDA)."""
+    import shutil
+    import subprocess
+    if not shutil.which("g++"):
+        pytest.skip("no g++")
+    exe = str(tmp_path / "test_services")
+    lib_dir = os.path.join(ROOT, "spectral_analyzer_b200")
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "cpp", "test_services.cpp"), "-o", exe, "-L" + lib_dir, "-lsa_engine",
+                        "-Wl,-rpath," + lib_dir], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "warning" not in r.stderr, r.stderr[-2000:]
