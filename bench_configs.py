@@ -35,37 +35,42 @@ def timed(fn, steps, warmup=3):
     return t[len(t) // 2]
 
 
-def spectrogram_case(eng, name, datatype, n_samples, nfft, hop, window, out_kind, steps, **kw):
+def spectrogram_case(eng, name, datatype, n_samples, nfft, hop, window, out_kind, steps, byte_offset=0, **kw):
+    """byte_offset: the capture starts that many bytes into the device buffer (a WAV file's 44-byte header:
+    frames are then only element-aligned and the engine takes its any-alignment kernels)."""
     kind = datatype.split("_")[0]
     bps = {"cf32": 8, "ci16": 4, "cu8": 2, "ci8": 2, "cf64": 16}[kind]
-    dev = torch.device("cuda", 0)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    pad = (byte_offset + bps - 1) // bps
     if kind == "cf32":
-        raw = torch.randn(2 * n_samples, device=dev, dtype=torch.float32).mul_(0.1)
+        raw = torch.randn(2 * (n_samples + pad), device=dev, dtype=torch.float32).mul_(0.1)
     elif kind == "cf64":
-        raw = torch.randn(2 * n_samples, device=dev, dtype=torch.float64).mul_(0.1)
+        raw = torch.randn(2 * (n_samples + pad), device=dev, dtype=torch.float64).mul_(0.1)
     elif kind == "ci16":
-        raw = torch.randint(-20000, 20000, (2 * n_samples,), device=dev, dtype=torch.int16)
+        raw = torch.randint(-20000, 20000, (2 * (n_samples + pad),), device=dev, dtype=torch.int16)
     else:
-        raw = torch.randint(0, 255, (2 * n_samples,), device=dev, dtype=torch.uint8)
+        raw = torch.randint(0, 255, (2 * (n_samples + pad),), device=dev, dtype=torch.uint8)
     frames = (n_samples - nfft) // hop + 1
     obytes = {"f32": 4, "f64": 8, "rgba8": 4}[out_kind]
     out = torch.empty(frames * nfft * obytes, device=dev, dtype=torch.uint8)
     p = eng.make_params(datatype, nfft, hop, window, n_frames=frames, out=out_kind, **kw)
     stream = torch.cuda.current_stream().cuda_stream
-    ms = timed(lambda: eng.spectrogram_device(raw.data_ptr(), n_samples * bps, p, out.data_ptr(), out.numel(), stream), steps)
+    ms = timed(lambda: eng.spectrogram_device(raw.data_ptr() + byte_offset, n_samples * bps, p, out.data_ptr(), out.numel(), stream), steps)
     alg = n_samples * bps + frames * nfft * obytes
     peak, kind_p = hbm_peak()
     res = {"config": name, "datatype": datatype, "samples": n_samples, "nfft": nfft, "hop": hop, "window": window,
            "out": out_kind, "ms": round(ms, 4), "Msamples_per_s": round(frames * hop / ms / 1e3, 1),
            "alg_bytes": alg, "GBps": round(alg / ms / 1e6, 1), "roofline_frac": round(alg / ms / 1e6 / peak, 4),
-           "peak_kind": kind_p}
+           "peak_kind": kind_p, "kernel": eng.last_kernel}
     del raw, out
     torch.cuda.empty_cache()
     return res
 
 
-def annotation_case(eng, n_samples, n_ann, count, down, steps):
-    dev = torch.device("cuda", 0)
+def annotation_case(eng, n_samples, n_ann, count, down, steps, want_iq=True):
+    """want_iq=False: only the PSD rows are asked for (the Analysis dialog's PSD tab): the decimated IQ never
+    leaves the chip and the algorithmic bytes drop by its 16 B per output sample."""
+    dev = torch.device("cuda", torch.cuda.current_device())
     raw = torch.randn(2 * n_samples, device=dev, dtype=torch.float32).mul_(0.1)
     rng = np.random.default_rng(3)
     anns = (_capi.Annotation * n_ann)()
@@ -81,19 +86,22 @@ def annotation_case(eng, n_samples, n_ann, count, down, steps):
 
     def run():
         _capi.check(L.sa_downconvert_psd_batch_device(eng.handle, raw.data_ptr(), n_samples * 8, 0, 0, 1.0e6, anns, n_ann,
-                                                      8192, 2048, 1, out_iq.data_ptr(), offs, out_psd.data_ptr(), stream))
+                                                      8192, 2048, 1, out_iq.data_ptr() if want_iq else None,
+                                                      offs if want_iq else None, out_psd.data_ptr(), stream))
     ms = timed(run, steps)
-    alg = n_ann * (8 * count + 16 * m + 8 * 8192)
+    alg = n_ann * (8 * count + (16 * m if want_iq else 0) + 8 * 8192)
     peak, kind_p = hbm_peak()
-    return {"config": "C3 annotation analysis", "annotations": n_ann, "count": count, "down": down, "psd_nfft": 8192,
+    return {"config": "C3 %d annotations x 2^%d cf32 samples: NCO + FIR /%d + Welch 8192 (75%% overlap)%s"
+                      % (n_ann, count.bit_length() - 1, down, "" if want_iq else ", PSD only (no decimated IQ written)"),
+            "annotations": n_ann, "count": count, "down": down, "psd_nfft": 8192,
             "ms": round(ms, 4), "Msamples_per_s": round(n_ann * count / ms / 1e3, 1), "alg_bytes": alg,
             "GBps": round(alg / ms / 1e6, 1), "roofline_frac": round(alg / ms / 1e6 / peak, 4), "peak_kind": kind_p}
 
 
-def canvas_case(eng, n_samples, nfft, hop, W, H, reduce, steps):
+def canvas_case(eng, n_samples, nfft, hop, W, H, reduce, steps, host=True):
     """N2: whole-recording view, canvas W x H from 2^28 cf32 samples: device-resident time of the spectrogram +
     canvas kernels, and the host call (H2D of the samples, D2H of the canvas only)."""
-    dev = torch.device("cuda", 0)
+    dev = torch.device("cuda", torch.cuda.current_device())
     raw = torch.randn(2 * n_samples, device=dev, dtype=torch.float32).mul_(0.1)
     frames = (n_samples - nfft) // hop + 1
     fpc = frames // W
@@ -107,6 +115,14 @@ def canvas_case(eng, n_samples, nfft, hop, W, H, reduce, steps):
         _capi.check(L.sa_render_canvas_device(eng.handle, raw.data_ptr(), n_samples * 8, C.byref(p), W, H, fpc, red,
                                               out.data_ptr(), stream))
     ms = timed(run, steps)
+    alg = (W * nfft if reduce == "nearest" else n_samples) * 8 + W * H * 4
+    peak, kind_p = hbm_peak()
+    res = {"config": "N2 canvas %dx%d (%s) from cf32 %d-pt hop %d" % (W, H, reduce, nfft, hop), "samples": n_samples,
+           "frames_per_column": fpc, "ms": round(ms, 4), "Msamples_per_s": round(W * fpc * hop / ms / 1e3, 1),
+           "alg_bytes": alg, "GBps": round(alg / ms / 1e6, 1), "roofline_frac": round(alg / ms / 1e6 / peak, 4),
+           "d2h_bytes": W * H * 4, "peak_kind": kind_p, "kernel": eng.last_kernel}
+    if not host:
+        return res
     h_raw = torch.empty(2 * n_samples, dtype=torch.float32, pin_memory=True)
     h_raw.copy_(raw)
     h_np = h_raw.numpy()
@@ -118,14 +134,8 @@ def canvas_case(eng, n_samples, nfft, hop, W, H, reduce, steps):
         eng.render_canvas(h_np, "cf32_le", nfft, W, H, 2.4e6, hop=hop, window="hann", frames_per_column=fpc,
                           reduce=reduce, colormap="Heatmap")
     host_ms = (time.perf_counter() - t0) / 3 * 1e3
-    # nearest pick: only the W displayed frames are read
-    alg = (W * nfft if reduce == "nearest" else n_samples) * 8 + W * H * 4
-    peak, kind_p = hbm_peak()
-    return {"config": "N2 canvas %dx%d (%s) from cf32 %d-pt hop %d" % (W, H, reduce, nfft, hop), "samples": n_samples,
-            "frames_per_column": fpc, "ms": round(ms, 4), "Msamples_per_s": round(W * fpc * hop / ms / 1e3, 1),
-            "alg_bytes": alg, "GBps": round(alg / ms / 1e6, 1), "roofline_frac": round(alg / ms / 1e6 / peak, 4),
-            "host_call_ms": round(host_ms, 2), "host_Msamples_per_s": round(W * fpc * hop / host_ms / 1e3, 1),
-            "d2h_bytes": W * H * 4, "peak_kind": kind_p}
+    res.update({"host_call_ms": round(host_ms, 2), "host_Msamples_per_s": round(W * fpc * hop / host_ms / 1e3, 1)})
+    return res
 
 
 def main():

@@ -116,8 +116,13 @@ SA_API int32_t sa_parse_datatype(const char* sigmf_datatype, int32_t* dtype, int
 SA_API void    sa_spectrogram_params_init(sa_spectrogram_params* p);   /* reference defaults */
 
 /* ---- host memory: the mmapped .sigmf-data MemorySegment (SigMfHelper.java:78-84) ---- */
-/* Page-locks [ptr, ptr+bytes) so H2D copies run asynchronously at full PCIe rate.  Optional:
- * unregistered memory works through pageable copies.  read_only != 0 for PROT_READ mappings. */
+/* Page-locks [ptr, ptr+bytes) so that the range itself is the DMA source / target.  Optional.
+ * Works for anonymous memory (malloc'ed or Arena-allocated segments, heap arrays pinned by the caller).
+ * It does NOT work for the file-backed mapping FileChannel.map returns: cudaHostRegister refuses such
+ * ranges ("invalid argument", measured on the B200 hosts) and this call then returns SA_ERR_CUDA.
+ * Unregistered / pageable memory -- the mapped .sigmf-data buffer included -- is staged by the engine through
+ * its own pinned ring with parallel host copies; sa_spectrogram_file reads the file into that ring directly.
+ * read_only != 0 for PROT_READ ranges. */
 SA_API int32_t sa_register_host(sa_engine* engine, const void* ptr, uint64_t bytes, int32_t read_only);
 SA_API int32_t sa_unregister_host(sa_engine* engine, const void* ptr);
 
@@ -132,6 +137,15 @@ SA_API int32_t sa_spectrogram(sa_engine* engine, const void* iq, uint64_t iq_byt
 SA_API int32_t sa_spectrogram_device(sa_engine* engine, const void* d_iq, uint64_t iq_bytes,
                                      const sa_spectrogram_params* params, void* d_out,
                                      uint64_t out_bytes, void* cuda_stream);
+/* Same with the capture read from the data FILE (SigMfHelper.load: S/sigmf/SigMfHelper.java:59-84): sample 0
+ * is at byte data_offset of `path` (core:header_bytes), data_bytes limits the capture (0 = to the end of the
+ * file; 64-bit, the reference maps at most 2 GiB - 1, :78-82).  The engine preads the frames' bytes straight
+ * into its pinned ring with several threads: no mapped buffer, no page-fault + memcpy hop.  out: host. */
+SA_API int32_t sa_spectrogram_file(sa_engine* engine, const char* path, uint64_t data_offset, uint64_t data_bytes,
+                                   const sa_spectrogram_params* params, void* out, uint64_t out_bytes);
+/* name of the kernel the engine's last spectrogram launch selected, e.g.
+ * "spectrogram_tma_kernel<float,1024,cf32,window>" (thread-local copy, never NULL) */
+SA_API const char* sa_last_kernel_name(sa_engine* engine);
 /* SpectralService.computeMagnitudes (SpectralService.java:33-85), kept for API compatibility:
  * one frame at byte offset start_byte, rect window, 20*log10(|X|+1e-10), fft-shifted, FP64 out. */
 SA_API int32_t sa_compute_magnitudes(sa_engine* engine, const void* buffer, uint64_t capacity_bytes,

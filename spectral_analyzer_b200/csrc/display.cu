@@ -50,8 +50,11 @@ int launch_canvas(Engine* eng, CanvasArgs& ca, const float* d_db, int col0, int 
     return SA_OK;
 }
 
-uint64_t canvas_cols_per_chunk(const sa_spectrogram_params& p, uint64_t fpc, uint32_t w, uint64_t chunk_bytes) {
-    const uint64_t col_bytes = fpc * (uint64_t)p.nfft * 4;
+// in_bps: bytes per input IQ pair when the chunk's samples are staged too (host path), 0 for device-resident input:
+// a chunk is bounded by the larger of its dB rows and its input samples (a view with a large hop reads far more
+// than it writes)
+uint64_t canvas_cols_per_chunk(const sa_spectrogram_params& p, uint64_t fpc, uint32_t w, uint64_t chunk_bytes, uint64_t in_bps = 0) {
+    const uint64_t col_bytes = std::max<uint64_t>(fpc * (uint64_t)p.nfft * 4, fpc * p.hop * in_bps);
     // at most 65535 columns per launch (grid.y)
     return std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>(w, 65535), chunk_bytes / col_bytes));
 }
@@ -116,9 +119,11 @@ int32_t sa_render_canvas(sa_engine* engine, const void* iq, uint64_t iq_bytes, c
     if (rc) return rc;
     const uint64_t bps = (uint64_t)sa_bytes_per_iq(q.dtype);
     const uint64_t n_samples = iq_bytes / bps;
-    const uint64_t cpc = canvas_cols_per_chunk(q, frames_per_column, canvas_w, kCanvasChunkBytes);
+    const uint64_t cpc = canvas_cols_per_chunk(q, frames_per_column, canvas_w, kCanvasChunkBytes, bps);
     const uint64_t fpchunk = cpc * frames_per_column;
-    const uint64_t in_cap = ((fpchunk - 1) * q.hop + q.nfft) * bps;
+    // never more than the capture holds past the view's start
+    const uint64_t readable = n_samples > q.start_sample ? n_samples - q.start_sample : 0;
+    const uint64_t in_cap = std::max<uint64_t>(16, std::min<uint64_t>((fpchunk - 1) * q.hop + q.nfft, readable) * bps);
     const uint64_t out_cap = fpchunk * q.nfft * 4;
     const size_t canvas_bytes = (size_t)canvas_w * canvas_h * 4;
     rc = engine->ensure_scratch(3, canvas_bytes);
@@ -140,17 +145,19 @@ int32_t sa_render_canvas(sa_engine* engine, const void* iq, uint64_t iq_bytes, c
         for (uint64_t t = 0; t < nr; t++)
             memcpy((char*)s.h_in + t * frame_bytes, (const char*)iq + (q.start_sample + t * q.hop) * bps, frame_bytes);
         cudaError_t e2 = cudaSuccess;
+        // nothing may still be in flight on the staging buffer / the caller's memory when an error returns
+        auto fail = [&](int code) { cudaStreamSynchronize(s.stream); return code; };
         if (nr) e2 = cudaMemcpyAsync(s.d_in, s.h_in, nr * frame_bytes, cudaMemcpyHostToDevice, s.stream);
-        if (e2 != cudaSuccess) return cuda_fail(e2, "H2D packed frames");
+        if (e2 != cudaSuccess) return fail(cuda_fail(e2, "H2D packed frames"));
         sa_spectrogram_params r = q;
         r.start_sample = 0; r.hop = q.nfft; r.n_frames = total_frames;
         rc = engine->launch_spectrogram(s.d_in, nr * q.nfft, r, prec, s.d_out, s.stream, 5);
-        if (rc) return rc;
+        if (rc) return fail(rc);
         rc = launch_canvas(engine, ca, (const float*)s.d_out, 0, (int)canvas_w, s.stream);
-        if (rc) return rc;
+        if (rc) return fail(rc);
         e2 = cudaMemcpyAsync(out_rgba, engine->scratch[3], canvas_bytes, cudaMemcpyDeviceToHost, s.stream);
         if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(s.stream);
-        if (e2 != cudaSuccess) return cuda_fail(e2, "sparse canvas");
+        if (e2 != cudaSuccess) return fail(cuda_fail(e2, "sparse canvas"));
         return SA_OK;
     }
     // chunk c: H2D of its samples -> spectrogram -> canvas columns, on slot c % kSlots; only the canvas comes back
@@ -272,7 +279,7 @@ static int stage_rows(Engine* eng, const double* re, const double* im, uint64_t 
     if (rc) return rc;
     cudaError_t e = cudaMemcpyAsync(s.d_in, re, n * 8, cudaMemcpyHostToDevice, s.stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync((double*)s.d_in + n, im, n * 8, cudaMemcpyHostToDevice, s.stream);
-    if (e != cudaSuccess) return cuda_fail(e, "H2D rows");
+    if (e != cudaSuccess) { cudaStreamSynchronize(s.stream); return cuda_fail(e, "H2D rows"); }
     *slot = &s;
     return SA_OK;
 }
@@ -304,10 +311,10 @@ int32_t sa_iq_pack(sa_engine* engine, const double* re, const double* im, uint64
     if (rc) return rc;
     const uint64_t zero = 0;
     rc = iq_pack_device(engine, (const double*)s->d_in, &zero, &n, &zero, 1, format, s->d_out, s->stream);
-    if (rc) return rc;
+    if (rc) { cudaStreamSynchronize(s->stream); return rc; }      // the H2D of the caller's rows must have drained
     cudaError_t e = cudaMemcpyAsync(out, s->d_out, out_bytes, cudaMemcpyDeviceToHost, s->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
-    if (e != cudaSuccess) return cuda_fail(e, "iq pack");
+    if (e != cudaSuccess) { cudaStreamSynchronize(s->stream); return cuda_fail(e, "iq pack"); }
     return SA_OK;
 }
 
@@ -325,12 +332,12 @@ int32_t sa_analysis_series(sa_engine* engine, const double* re, const double* im
     double* d_frq = out_freq ? (double*)s->d_out + n : nullptr;
     rc = series_device(engine, (const double*)s->d_in, &zero, &n, &zero, 1, sample_rate, alpha_mag, alpha_freq, center_freq,
                        d_mag, d_frq, s->stream);
-    if (rc) return rc;
+    if (rc) { cudaStreamSynchronize(s->stream); return rc; }      // the H2D of the caller's rows must have drained
     cudaError_t e = cudaSuccess;
     if (out_mag_db) e = cudaMemcpyAsync(out_mag_db, d_mag, n * 8, cudaMemcpyDeviceToHost, s->stream);
     if (e == cudaSuccess && out_freq) e = cudaMemcpyAsync(out_freq, d_frq, n * 8, cudaMemcpyDeviceToHost, s->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
-    if (e != cudaSuccess) return cuda_fail(e, "analysis series");
+    if (e != cudaSuccess) { cudaStreamSynchronize(s->stream); return cuda_fail(e, "analysis series"); }
     return SA_OK;
 }
 

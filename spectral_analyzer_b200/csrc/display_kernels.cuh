@@ -135,6 +135,9 @@ __device__ __forceinline__ void series_scan(const SeriesArgs& a, const SeriesSig
     const double alpha = WHICH == 0 ? a.alpha_mag : a.alpha_freq;
     const double beta = 1.0 - alpha;
     const long long n = s.n - first;                     // samples in the recurrence
+    // element 0 of the frequency series is never produced by the Java loop (it starts at i = 1): NaN, also for a
+    // one-sample signal, where nothing else is written
+    if (WHICH == 1 && threadIdx.x == 0 && s.n > 0) a.out_freq[s.out_off] = __longlong_as_double(0x7ff8000000000000LL);
     if (n <= 0) return;
     const long long run = (n + kSeriesThreads - 1) / kSeriesThreads;
     const long long lo = first + (long long)threadIdx.x * run;
@@ -159,7 +162,6 @@ __device__ __forceinline__ void series_scan(const SeriesArgs& a, const SeriesSig
         y = (i == first) ? x : __dadd_rn(__dmul_rn(alpha, x), __dmul_rn(beta, y));   // Java: no FMA contraction
         out[s.out_off + i] = WHICH == 0 ? 20.0 * log10(y) : y + a.center_freq;
     }
-    if (WHICH == 1 && threadIdx.x == 0) out[s.out_off] = __longlong_as_double(0x7ff8000000000000LL);
 }
 
 __global__ void __launch_bounds__(kSeriesThreads)

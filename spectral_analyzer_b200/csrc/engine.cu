@@ -9,6 +9,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cerrno>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 namespace sa {
 
@@ -37,27 +41,51 @@ void CopyPool::worker() {
             j = queue_.back();
             queue_.pop_back();
         }
-        memcpy(j.dst, j.src, j.bytes);
+        if (j.fd >= 0) {
+            size_t done = 0;
+            while (done < j.bytes) {
+                const ssize_t r = pread(j.fd, j.dst + done, j.bytes - done, (off_t)(j.off + done));
+                if (r <= 0) { io_error_ = true; break; }
+                done += (size_t)r;
+            }
+        } else {
+            memcpy(j.dst, j.src, j.bytes);
+        }
         {
             std::lock_guard<std::mutex> l(mu_);
             if (--outstanding_ == 0) done_cv_.notify_all();
         }
     }
 }
-void CopyPool::copy(void* dst, const void* src, size_t bytes) {
+void CopyPool::run(void* dst, const void* src, int fd, uint64_t foff, size_t bytes) {
     const size_t part = std::max<size_t>(1 << 20, (bytes / (threads_.size() + 1) + 4095) & ~(size_t)4095);
-    size_t own_off = 0, own_bytes = std::min(part, bytes);
+    const size_t own_bytes = std::min(part, bytes);
     {
         std::lock_guard<std::mutex> l(mu_);
         for (size_t off = own_bytes; off < bytes; off += part) {
-            queue_.push_back({(char*)dst + off, (const char*)src + off, std::min(part, bytes - off)});
+            queue_.push_back({(char*)dst + off, src ? (const char*)src + off : nullptr, std::min(part, bytes - off), fd, foff + off});
             outstanding_++;
         }
     }
     cv_.notify_all();
-    memcpy((char*)dst + own_off, (const char*)src + own_off, own_bytes);      // the caller copies the first part
+    if (fd >= 0) {                                    // the caller moves the first part
+        size_t done = 0;
+        while (done < own_bytes) {
+            const ssize_t r = pread(fd, (char*)dst + done, own_bytes - done, (off_t)(foff + done));
+            if (r <= 0) { io_error_ = true; break; }
+            done += (size_t)r;
+        }
+    } else {
+        memcpy(dst, src, own_bytes);
+    }
     std::unique_lock<std::mutex> l(mu_);
     done_cv_.wait(l, [this] { return outstanding_ == 0; });
+}
+void CopyPool::copy(void* dst, const void* src, size_t bytes) { run(dst, src, -1, 0, bytes); }
+bool CopyPool::read(void* dst, int fd, uint64_t off, size_t bytes) {
+    io_error_ = false;
+    run(dst, nullptr, fd, off, bytes);
+    return !io_error_;
 }
 
 bool host_ptr_is_pinned(const void* p) {
@@ -165,7 +193,10 @@ static int upload_pairs(const std::vector<double>& re, const std::vector<double>
 }
 
 int Engine::twiddle_table(const SpecKernelInfo& k, const void** d_tab) {
-    const uint64_t key = ((uint64_t)k.prec << 32) | (uint32_t)k.n;
+    // the table layout depends on the whole plan (p, passes, radices), not only on (precision, n)
+    uint64_t plan = (uint64_t)k.p * 8 + (uint64_t)k.np;
+    for (int i = 0; i < 4; i++) plan = plan * 131 + (uint64_t)k.radix[i];
+    const uint64_t key = ((uint64_t)k.prec << 60) | ((plan & 0xFFFFFFFFFull) << 24) | (uint32_t)k.n;
     auto it = twiddles.find(key);
     if (it != twiddles.end()) { *d_tab = it->second; return SA_OK; }
     std::vector<double> re, im;
@@ -346,6 +377,13 @@ int Engine::launch_spectrogram_large(const void* d_iq, uint64_t n_samples, const
         if (e != cudaSuccess) return cuda_fail(e, "launch large_rows_kernel");
         launches += 2;
     }
+    {
+        static const char* const dkn[] = { "cf32", "ci16", "c8", "cf64" };
+        char nm[160];
+        snprintf(nm, sizeof(nm), "large_cols_kernel+large_rows_kernel<%s,%dx%d,%s,%s>", prec == SA_PREC_F64 ? "double" : "float",
+                 k->n1, k->n2, dkn[dk], win ? "window" : "rect");
+        last_kernel = nm;
+    }
     if (dual) {
         e = cudaEventRecord(large_ev[ai][1], large_aux[ai]);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, large_ev[ai][1], 0);
@@ -493,18 +531,34 @@ int Engine::launch_spectrogram(const void* d_iq, uint64_t n_samples, const sa_sp
     cudaError_t e = cudaLaunchKernel(k->fn, dim3(grid), dim3(k->cta), args, k->smem, stream);
     if (e != cudaSuccess) return cuda_fail(e, "launch spectrogram_kernel");
     launches++;
+    {
+        static const char* const fam[] = { "spectrogram_kernel", "spectrogram_tma_kernel", "spectrogram_mid_kernel",
+                                           "spectrogram_mid_kernel(prefetch)", "spectrogram_r64_kernel" };
+        static const char* const dkn[] = { "cf32", "ci16", "c8", "cf64" };
+        char nm[128];
+        snprintf(nm, sizeof(nm), "%s<%s,%d,%s,%s>", fam[k->tma], prec == SA_PREC_F64 ? "double" : "float", k->n, dkn[k->dk],
+                 k->win ? "window" : "rect");
+        last_kernel = nm;
+    }
     return SA_OK;
+}
+
+static CopyPool* make_copy_pool() {
+    const char* ev = getenv("SA_COPY_THREADS");
+    const unsigned hw = std::thread::hardware_concurrency();
+    int n = ev ? atoi(ev) : (int)std::min(16u, std::max(2u, hw - hw / 3));
+    return new CopyPool(std::max(1, n - 1));
 }
 
 void Engine::host_copy(void* dst, const void* src, size_t bytes) {
     if (bytes < (4u << 20)) { memcpy(dst, src, bytes); return; }
-    if (!copy_pool) {
-        const char* ev = getenv("SA_COPY_THREADS");
-        const unsigned hw = std::thread::hardware_concurrency();
-        int n = ev ? atoi(ev) : (int)std::min(16u, std::max(2u, hw - hw / 3));
-        copy_pool = new CopyPool(std::max(1, n - 1));
-    }
+    if (!copy_pool) copy_pool = make_copy_pool();
     copy_pool->copy(dst, src, bytes);
+}
+
+bool Engine::host_read(void* dst, int fd, uint64_t off, size_t bytes) {
+    if (!copy_pool) copy_pool = make_copy_pool();
+    return copy_pool->read(dst, fd, off, bytes);
 }
 
 int Engine::ensure_staging(Slot& s, size_t in_bytes, size_t out_bytes) {
@@ -558,7 +612,8 @@ int Engine::ensure_slot(Slot& s, size_t in_bytes, size_t out_bytes) {
 
 // Host-buffer spectrogram: frames are cut into chunks; chunk c runs H2D -> kernel -> D2H on
 // slot c % kSlots' stream, so copies of one chunk overlap the kernel of another.
-int Engine::spectrogram_host(const void* iq, uint64_t iq_bytes, const sa_spectrogram_params& p, int prec, void* out) {
+int Engine::spectrogram_host(const HostSource& hs, uint64_t iq_bytes, const sa_spectrogram_params& p, int prec, void* out) {
+    const void* iq = hs.ptr;
     const uint64_t bps = (uint64_t)sa_bytes_per_iq(p.dtype);
     const uint64_t n_samples = iq_bytes / bps;
     const uint64_t obytes = out_elem_bytes(p.out_kind);
@@ -571,7 +626,7 @@ int Engine::spectrogram_host(const void* iq, uint64_t iq_bytes, const sa_spectro
     const uint64_t out_cap = fpc * row_bytes;
     // pageable buffers (an mmapped file, a Java heap array) go through pinned staging with parallel host copies;
     // pinned / registered buffers are the DMA source and target themselves
-    const bool in_pinned = host_ptr_is_pinned(iq), out_pinned = host_ptr_is_pinned(out);
+    const bool in_pinned = hs.fd < 0 && host_ptr_is_pinned(iq), out_pinned = host_ptr_is_pinned(out);
     int rc = SA_OK;
     uint64_t c = 0;
     for (uint64_t f0 = 0; f0 < p.n_frames && rc == SA_OK; f0 += fpc, c++) {
@@ -590,7 +645,14 @@ int Engine::spectrogram_host(const void* iq, uint64_t iq_bytes, const sa_spectro
         const uint64_t ns = s_end > s_begin ? s_end - s_begin : 0;
         if (ns) {
             const void* src = (const char*)iq + s_begin * bps;
-            if (!in_pinned) { host_copy(s.h_in, src, ns * bps); src = s.h_in; }
+            if (hs.fd >= 0) {                                  // parallel pread straight into the pinned ring
+                if (!host_read(s.h_in, hs.fd, hs.file_off + s_begin * bps, ns * bps)) {
+                    rc = set_error(SA_ERR_OUT_OF_RANGE, "short read at byte %llu of the data file",
+                                   (unsigned long long)(hs.file_off + s_begin * bps));
+                    break;
+                }
+                src = s.h_in;
+            } else if (!in_pinned) { host_copy(s.h_in, src, ns * bps); src = s.h_in; }
             e = cudaMemcpyAsync(s.d_in, src, ns * bps, cudaMemcpyHostToDevice, s.stream);
             if (e != cudaSuccess) { rc = cuda_fail(e, "H2D"); break; }
         }
@@ -788,7 +850,46 @@ int32_t sa_spectrogram(sa_engine* engine, const void* iq, uint64_t iq_bytes, con
     const uint64_t need = params->n_frames * (uint64_t)params->nfft * out_elem_bytes(params->out_kind);
     if (out_bytes < need) return set_error(SA_ERR_SMALL_OUTPUT, "out_bytes %llu < %llu", (unsigned long long)out_bytes, (unsigned long long)need);
     if (params->n_frames == 0) return SA_OK;
-    return engine->spectrogram_host(iq, iq_bytes, *params, prec, out);
+    HostSource hs;
+    hs.ptr = iq;
+    return engine->spectrogram_host(hs, iq_bytes, *params, prec, out);
+}
+
+// File-based ingest (SigMfHelper.load, S/sigmf/SigMfHelper.java:59-84: the data file, core:header_bytes skipped):
+// the samples go from the page cache / the device straight into the pinned ring by parallel pread, without the
+// page-fault + memcpy hop of an mmapped buffer, and without the reference's 2 GiB mapping limit (:78-82).
+int32_t sa_spectrogram_file(sa_engine* engine, const char* path, uint64_t data_offset, uint64_t data_bytes,
+                            const sa_spectrogram_params* params, void* out, uint64_t out_bytes) {
+    ENGINE_ENTER(engine);
+    int prec = 0;
+    int rc = check_spec_params(params, &prec);
+    if (rc) return rc;
+    if (!path || !out) return set_error(SA_ERR_INVALID_ARG, "NULL path / buffer");
+    const uint64_t need = params->n_frames * (uint64_t)params->nfft * out_elem_bytes(params->out_kind);
+    if (out_bytes < need) return set_error(SA_ERR_SMALL_OUTPUT, "out_bytes %llu < %llu", (unsigned long long)out_bytes, (unsigned long long)need);
+    const int fd = open(path, O_RDONLY | O_CLOEXEC);
+    if (fd < 0) return set_error(SA_ERR_INVALID_ARG, "cannot open '%s': %s", path, strerror(errno));
+    struct stat st;
+    if (fstat(fd, &st) != 0) { close(fd); return set_error(SA_ERR_INVALID_ARG, "fstat '%s': %s", path, strerror(errno)); }
+    const uint64_t size = (uint64_t)st.st_size;
+    if (data_offset > size) { close(fd); return set_error(SA_ERR_OUT_OF_RANGE, "data_offset %llu beyond the %llu-byte file", (unsigned long long)data_offset, (unsigned long long)size); }
+    uint64_t avail = size - data_offset;
+    if (data_bytes && data_bytes < avail) avail = data_bytes;          // one capture of a multi-capture recording
+    if (params->n_frames == 0) { close(fd); return SA_OK; }
+    HostSource hs;
+    hs.fd = fd;
+    hs.file_off = data_offset;
+    rc = engine->spectrogram_host(hs, avail, *params, prec, out);
+    close(fd);
+    return rc;
+}
+
+const char* sa_last_kernel_name(sa_engine* engine) {
+    static thread_local std::string name;
+    if (!engine) return "";
+    std::lock_guard<std::mutex> lock_(engine->mu);
+    name = engine->last_kernel;
+    return name.c_str();
 }
 
 int32_t sa_compute_magnitudes(sa_engine* engine, const void* buffer, uint64_t capacity_bytes, uint64_t start_byte,
@@ -807,7 +908,9 @@ int32_t sa_compute_magnitudes(sa_engine* engine, const void* buffer, uint64_t ca
     if (start_byte > capacity_bytes || (uint64_t)nfft * bps > capacity_bytes - start_byte)
         return set_error(SA_ERR_OUT_OF_RANGE, "frame [%llu, +%llu) exceeds capacity %llu", (unsigned long long)start_byte,
                          (unsigned long long)(nfft * bps), (unsigned long long)capacity_bytes);
-    return engine->spectrogram_host((const char*)buffer + start_byte, (uint64_t)nfft * bps, p, prec, out);
+    HostSource hs;
+    hs.ptr = (const char*)buffer + start_byte;
+    return engine->spectrogram_host(hs, (uint64_t)nfft * bps, p, prec, out);
 }
 
 }  // extern "C"

@@ -5,6 +5,7 @@
 #include <condition_variable>
 #include <map>
 #include <mutex>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -24,6 +25,14 @@ int dtype_kind(int dtype);
 bool host_ptr_is_pinned(const void* p);     // pinned / registered host memory (DMA-able as is)
 int check_spec_params(const sa_spectrogram_params* p, int* prec_out);   // validates, resolves precision
 void fill_load_params(LoadParams& lp, const void* base, int dtype, int big_endian);
+
+// Where the host pipeline takes a capture's bytes from: caller memory (pinned: DMA source as is; pageable:
+// parallel memcpy into the pinned ring) or an open file (parallel pread straight into the pinned ring).
+struct HostSource {
+    const void* ptr = nullptr;
+    int fd = -1;
+    uint64_t file_off = 0;          // byte offset of sample 0 in the file (core:header_bytes, SigMfHelper.java:59-67)
+};
 
 constexpr int kSlots = 3;
 constexpr int kScratch = 12;
@@ -45,9 +54,13 @@ public:
     explicit CopyPool(int workers);
     ~CopyPool();
     void copy(void* dst, const void* src, size_t bytes);         // returns when every part has been copied
+    // same, the source being bytes [off, off + bytes) of an open file (parallel pread); false on a short read / error
+    bool read(void* dst, int fd, uint64_t off, size_t bytes);
 private:
     void worker();
-    struct Job { char* dst; const char* src; size_t bytes; };
+    void run(void* dst, const void* src, int fd, uint64_t off, size_t bytes);
+    struct Job { char* dst; const char* src; size_t bytes; int fd; uint64_t off; };
+    std::atomic<bool> io_error_{false};
     std::vector<std::thread> threads_;
     std::mutex mu_;
     std::condition_variable cv_, done_cv_;
@@ -61,6 +74,7 @@ struct Engine {
     int num_sms = 0;
     std::mutex mu;
     uint64_t launches = 0;
+    std::string last_kernel;                         // name of the spectrogram kernel the last launch selected
     uint64_t chunk_bytes = 64ull << 20;              // per-slot staging size of the host pipeline
     std::map<uint64_t, void*> twiddles;              // (prec, nfft) -> device table
     std::map<uint64_t, void*> windows;               // (prec, window, nfft) -> device table
@@ -85,6 +99,7 @@ struct Engine {
     int ensure_slot(Slot& s, size_t in_bytes, size_t out_bytes);
     int ensure_staging(Slot& s, size_t in_bytes, size_t out_bytes);      // pinned h_in / h_out (0 = not needed)
     void host_copy(void* dst, const void* src, size_t bytes);            // parallel memcpy (CopyPool)
+    bool host_read(void* dst, int fd, uint64_t off, size_t bytes);       // parallel pread (CopyPool)
     int flush_pending(Slot& s);                                          // h_out -> the caller's pageable buffer
     int ensure_scratch(int which, size_t bytes);
     int root_table(int n, int prec, const void** d_tab);      // W_n^j, j = 0..n-1
@@ -95,7 +110,7 @@ struct Engine {
                                  const SpecArgs& base, void* d_out, cudaStream_t stream, int ws);
     int launch_spectrogram(const void* d_iq, uint64_t n_samples, const sa_spectrogram_params& p, int prec,
                            void* d_out, cudaStream_t stream, int ws = 2);
-    int spectrogram_host(const void* iq, uint64_t iq_bytes, const sa_spectrogram_params& p, int prec, void* out);
+    int spectrogram_host(const HostSource& src, uint64_t iq_bytes, const sa_spectrogram_params& p, int prec, void* out);
 };
 
 }  // namespace sa

@@ -102,6 +102,26 @@ class Engine:
         _capi.check(_capi.lib().sa_spectrogram(self._h, ptr, nbytes, C.byref(p), out.ctypes.data, out.nbytes))
         return out
 
+    def spectrogram_file(self, path, datatype, nfft, n_frames, hop=None, window="rect", start_sample=0, out=None,
+                         data_offset=0, data_bytes=0, **kw):
+        """Same as `spectrogram`, the capture being read from the data file itself (SigMfHelper.java:59-84:
+        `data_offset` = core:header_bytes): parallel pread into the engine's pinned ring, no mapped buffer."""
+        kind = kw.get("out_kind", "f32")
+        p = self.make_params(datatype, nfft, hop, window, n_frames, start_sample, out=kind,
+                             **{k: v for k, v in kw.items() if k != "out_kind"})
+        if out is None:
+            if kind == "rgba8":
+                out = np.empty((n_frames, nfft, 4), np.uint8)
+            else:
+                out = np.empty((n_frames, nfft), np.float32 if kind == "f32" else np.float64)
+        _capi.check(_capi.lib().sa_spectrogram_file(self._h, os.fsencode(path), data_offset, data_bytes, C.byref(p),
+                                                    out.ctypes.data, out.nbytes))
+        return out
+
+    @property
+    def last_kernel(self):
+        return _capi.lib().sa_last_kernel_name(self._h).decode()
+
     def spectrogram_device(self, d_iq_ptr, iq_bytes, params, d_out_ptr, out_bytes, stream=0):
         """Device-resident variant (raw device pointers, e.g. torch tensors' data_ptr())."""
         _capi.check(_capi.lib().sa_spectrogram_device(self._h, d_iq_ptr, iq_bytes, C.byref(params), d_out_ptr,

@@ -48,7 +48,7 @@ def test_c1_headline_full_size_parseval_and_cufft_crosscheck(engine):
     """cf32, 2^28 samples (2 GiB), 1024-pt Hann, hop 512: the bench workload."""
     n, nfft, hop = 1 << 28, 1024, 512
     from bench import make_device_recording
-    d_iq = make_device_recording(torch, n, seed=1, device=torch.device(DEV))
+    d_iq = make_device_recording(torch, 0, n, torch.device(DEV))
     frames = (n - nfft) // hop + 1
     out = run_device(engine, d_iq.view(torch.uint8), "cf32_le", nfft, hop, "hann", frames).view(torch.float32).view(frames, nfft)
     assert torch.isfinite(out).all()

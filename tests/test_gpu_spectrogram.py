@@ -330,3 +330,55 @@ def test_fp64_db_epilogue_over_the_dynamic_range(engine, nfft, mode):
     assert np.abs(got - ref).max() < 1e-9, np.abs(got - ref).max(axis=1)
     # exact zeros: 20 log10(1e-10) = 10 log10(1e-20) = -200 (literal form in magnitude mode, the table log in power mode)
     assert (got[0] == -200.0).all() if mode == 0 else np.abs(got[0] + 200.0).max() < 1e-11
+
+
+@pytest.mark.parametrize("dt,header", [("cf32_le", 0), ("ci16_le", 44), ("cu8", 320)])
+def test_spectrogram_file_matches_buffer_call(engine, tmp_path, dt, header):
+    """sa_spectrogram_file (SigMfHelper.java:59-84: data file, core:header_bytes skipped) reads the capture into the
+    pinned ring itself; rows must equal the buffer call on the same bytes, EOF rows included, and a capture limited by
+    data_bytes ends where it says."""
+    nfft, hop, frames = 1024, 512, 700
+    raw = synth.recording((frames - 1) * hop + nfft - 100, dt, seed=11)
+    path = tmp_path / "rec.sigmf-data"
+    with open(path, "wb") as f:
+        f.write(b"\x7f" * header)
+        f.write(raw.tobytes())
+    ref = engine.spectrogram(raw, dt, nfft, frames, hop=hop, window="hann")
+    got = engine.spectrogram_file(str(path), dt, nfft, frames, hop=hop, window="hann", data_offset=header)
+    assert (ref[-1] == -150.0).all() and np.array_equal(got, ref)
+    half = (raw.size // 2) & ~15
+    ref_h = engine.spectrogram(raw[:half], dt, nfft, frames, hop=hop, window="hann")
+    got_h = engine.spectrogram_file(str(path), dt, nfft, frames, hop=hop, window="hann", data_offset=header, data_bytes=half)
+    assert np.array_equal(got_h, ref_h) and (got_h[-1] == -150.0).all()
+    with pytest.raises(EngineError) as e:
+        engine.spectrogram_file(str(tmp_path / "missing"), dt, nfft, 1)
+    assert e.value.code == 1
+
+
+def test_spectrogram_file_large_chunks(engine, tmp_path):
+    """several pipeline chunks and the parallel pread path (> 4 MiB per chunk)"""
+    nfft = 4096
+    raw = synth.recording(1 << 22, "ci16_le", seed=12)              # 16 MiB
+    path = tmp_path / "rec.sigmf-data"
+    raw.tofile(path)
+    frames = (1 << 22) // nfft
+    import os
+    os.environ["SA_CHUNK_MB"] = "4"
+    import spectral_analyzer_b200 as sa
+    eng = sa.Engine(0)
+    del os.environ["SA_CHUNK_MB"]
+    try:
+        got = eng.spectrogram_file(str(path), "ci16_le", nfft, frames, window="blackman_harris")
+        ref = eng.spectrogram(raw, "ci16_le", nfft, frames, window="blackman_harris")
+        assert np.array_equal(got, ref)
+        assert eng.last_kernel.startswith("spectrogram_r64_kernel<float,4096,ci16")
+    finally:
+        eng.close()
+
+
+def test_last_kernel_name_reports_the_selected_variant(engine):
+    raw = synth.recording(1024 * 8, "cf32_le", seed=1)
+    engine.spectrogram(raw, "cf32_le", 1024, 8, hop=512, window="hann")
+    assert engine.last_kernel == "spectrogram_tma_kernel<float,1024,cf32,window>"
+    engine.spectrogram(raw, "cf32_le", 1024, 7, hop=512, window="hann", start_sample=1)      # frames no longer 16-byte aligned
+    assert engine.last_kernel == "spectrogram_kernel<float,1024,cf32,window>"
