@@ -272,6 +272,23 @@ int Engine::mid_t1_table(int n, const void** d_tab) {
     return SA_OK;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+        }
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
 // Four-step path (large_fft_kernels.cuh): frames are processed in chunks whose workspace stays L2-sized.
 int Engine::launch_spectrogram_large(const void* d_iq, uint64_t n_samples, const sa_spectrogram_params& p, int prec,
                                      const SpecArgs& base, void* d_out, cudaStream_t stream, int ws) {
@@ -299,10 +316,18 @@ int Engine::launch_spectrogram_large(const void* d_iq, uint64_t n_samples, const
     const uint64_t per_frame = (uint64_t)p.nfft * elem;
     void* args[] = { &a };
     cudaError_t e;
-    // opt-in (SA_LARGE_CLUSTER=1): measured slower than the two-kernel path on B200 (DESIGN.md K6 ablation)
-    static const bool use_cluster = getenv("SA_LARGE_CLUSTER") != nullptr;
-    if (k->fn_cluster && use_cluster) {
-        // cluster path: one 8-CTA cluster per frame, per-cluster workspace slice that stays in L2
+    // 65536 points with 16-byte aligned frames, opt-in (SA_LARGE_ONCHIP=1): the on-chip cluster kernel (the frame stays
+    // in the distributed shared memory of an 8-CTA cluster between the column and the row step; no workspace, DRAM
+    // traffic = algorithmic bytes).  Measured on B200 it LOSES to the two-kernel path (config 5: 1.32 vs 0.785 ms; FP32:
+    // 1.04 vs 0.683 ms): one 256-thread CTA per SM leaves every phase latency-bound and the phases of a frame are
+    // serialised by two cluster barriers (per frame and CTA, FP64, cycles: column FFTs 11.3 k, barrier 2.1 k, DSMEM pull
+    // 5.3 k = 24 B/clk, barrier 5.0 k, row FFTs 7.0 k, dB + store 8.9 k; TMA wait 0.8 k, i.e. the loads ARE hidden) --
+    // the two kernels are issue-bound, not bound by the workspace round trip.
+    const char* onchip_env = getenv("SA_LARGE_ONCHIP");               // read per call: the tests A/B the two paths
+    const bool use_onchip = onchip_env ? atoi(onchip_env) != 0 : false;
+    const uint64_t iq_b = (uint64_t)sa_bytes_per_iq(p.dtype);
+    const bool aligned = ((uintptr_t)d_iq % 16 == 0) && ((p.start_sample * iq_b) % 16 == 0) && ((p.hop * iq_b) % 16 == 0);
+    if (k->fn_cluster && use_onchip && aligned) {
         auto it = occupancy.find(k->fn_cluster);
         int n_clusters = 0;
         cudaLaunchConfig_t cfg;
@@ -310,13 +335,13 @@ int Engine::launch_spectrogram_large(const void* d_iq, uint64_t n_samples, const
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = kLargeCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.blockDim = dim3(k->cta_cols);
+        cfg.blockDim = dim3(k->cta_cluster);
         cfg.dynamicSmemBytes = k->smem_cluster;
         cfg.stream = stream;
         cfg.attrs = attr; cfg.numAttrs = 1;
         if (it == occupancy.end()) {
             e = cudaFuncSetAttribute(k->fn_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->smem_cluster);
-            if (e != cudaSuccess) return cuda_fail(e, "large FFT cluster smem attribute");
+            if (e != cudaSuccess) return cuda_fail(e, "on-chip four-step smem attribute");
             cfg.gridDim = dim3(kLargeCluster * num_sms);
             e = cudaOccupancyMaxActiveClusters(&n_clusters, k->fn_cluster, &cfg);
             if (e != cudaSuccess || n_clusters < 1) { cudaGetLastError(); n_clusters = 0; }
@@ -324,16 +349,56 @@ int Engine::launch_spectrogram_large(const void* d_iq, uint64_t n_samples, const
         } else {
             n_clusters = it->second;
         }
-        if (n_clusters > 0) {
+        // tensor map [frame][n1][n2] over the readable frames, in 8-byte elements: strides hop and 256 samples
+        // (frames overlap when hop < nfft), box = 16 columns x 256 rows x 1 frame
+        const uint64_t first_end = p.start_sample + p.nfft;
+        const uint64_t n_read = n_samples >= first_end ? std::min<uint64_t>(p.n_frames, (n_samples - first_end) / p.hop + 1) : 0;
+        CUtensorMap tmap;
+        bool have_map = false;
+        if (n_clusters > 0 && n_read > 0 && encode_tiled_fn()) {
+            const cuuint64_t e8 = iq_b / 8;
+            const cuuint64_t gdim[3] = { (cuuint64_t)k->n2 * e8, (cuuint64_t)k->n1, (cuuint64_t)n_read };
+            const cuuint64_t gstr[2] = { (cuuint64_t)k->n2 * iq_b, (cuuint64_t)p.hop * iq_b };
+            const cuuint32_t box[3] = { (cuuint32_t)(kLargeC * e8), (cuuint32_t)k->n1, 1 };
+            const cuuint32_t estr[3] = { 1, 1, 1 };
+            void* gaddr = (char*)const_cast<void*>(d_iq) + p.start_sample * iq_b;
+            have_map = gstr[1] < (1ull << 40) &&
+                       encode_tiled_fn()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, gaddr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        }
+        if (have_map) {
             const uint64_t use = std::min<uint64_t>((uint64_t)n_clusters, p.n_frames);
-            rc = ensure_scratch(ws, 2 * use * per_frame);
+            a.ws = nullptr;
+#if SA_ONCHIP_PROF
+            rc = ensure_scratch(ws, (size_t)use * kLargeCluster * 16 * sizeof(long long));
             if (rc) return rc;
             a.ws = scratch[ws];
+#endif
             a.frame0 = 0;
             cfg.gridDim = dim3((unsigned)(use * kLargeCluster));
-            e = cudaLaunchKernelExC(&cfg, k->fn_cluster, args);
-            if (e != cudaSuccess) return cuda_fail(e, "launch large_cluster_kernel");
+            void* cargs[] = { &a, &tmap };
+            e = cudaLaunchKernelExC(&cfg, k->fn_cluster, cargs);
+            if (e != cudaSuccess) return cuda_fail(e, "launch large_onchip_kernel");
             launches++;
+#if SA_ONCHIP_PROF
+            if (getenv("SA_ONCHIP_PROF_DUMP")) {
+                cudaStreamSynchronize(stream);
+                std::vector<long long> h((size_t)use * kLargeCluster * 16);
+                cudaMemcpy(h.data(), scratch[ws], h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+                double sum[16] = {0};
+                for (size_t c = 0; c < (size_t)use * kLargeCluster; c++) for (int i = 0; i < 16; i++) sum[i] += (double)h[c * 16 + i];
+                const double fr = (double)p.n_frames * kLargeCluster;       // CTA-frames
+                fprintf(stderr, "onchip prof (cycles per frame, mean over CTAs):");
+                for (int i = 0; i < 9; i++) fprintf(stderr, " p%d=%.0f", i, sum[i] / fr);
+                fprintf(stderr, "\n");
+            }
+#endif
+            static const char* const dkn[] = { "cf32", "ci16", "c8", "cf64" };
+            char nm[160];
+            snprintf(nm, sizeof(nm), "large_onchip_kernel<%s,%dx%d,%s,%s> (%d-CTA clusters x %d)", prec == SA_PREC_F64 ? "double" : "float",
+                     k->n1, k->n2, dkn[dk], win ? "window" : "rect", kLargeCluster, n_clusters);
+            last_kernel = nm;
             return SA_OK;
         }
     }

@@ -382,3 +382,38 @@ def test_last_kernel_name_reports_the_selected_variant(engine):
     assert engine.last_kernel == "spectrogram_tma_kernel<float,1024,cf32,window>"
     engine.spectrogram(raw, "cf32_le", 1024, 7, hop=512, window="hann", start_sample=1)      # frames no longer 16-byte aligned
     assert engine.last_kernel == "spectrogram_kernel<float,1024,cf32,window>"
+
+
+@pytest.mark.parametrize("dt,prec,kind", [("cf64_le", "f64", "f64"), ("cf64_be", "f64", "f64"), ("cf32_le", "f32", "f32"), ("cf32_be", "f32", "f32")])
+def test_onchip_cluster_four_step(engine, monkeypatch, dt, prec, kind):
+    """65536 points with 16-byte aligned frames: the 8-CTA cluster kernel keeps the frame in distributed shared memory
+    (large_onchip_kernel).  More frames than resident clusters (every cluster pipelines several frames through its TMA
+    ring), 50 % overlap, two trailing EOF frames; against the oracle on a sample of frames, and the whole image
+    against the two-kernel path (SA_LARGE_ONCHIP=0)."""
+    nfft, hop, frames = 65536, 32768, 61
+    raw = synth.recording((frames - 3) * hop + nfft, dt, seed=65)
+    monkeypatch.setenv("SA_LARGE_ONCHIP", "1")                  # opt-in: measured slower than the two-kernel path
+    got = engine.spectrogram(raw, dt, nfft, frames, hop=hop, window="hann", precision=prec, out_kind=kind)
+    assert engine.last_kernel.startswith("large_onchip_kernel<%s,256x256,%s,window>" % ("double" if prec == "f64" else "float", dt[:4]))
+    assert (got[-2:] == -150.0).all()
+    pick = [0, 1, 17, 40, frames - 3]
+    for f in pick:
+        ref = co.spectrogram(raw, dt, f * hop, nfft, hop, "hann", 1)
+        if prec == "f64":
+            check_db_parity(got[f:f + 1], ref, strong_tol=1e-9, floor_tol=1e-6)
+        else:
+            check_db_parity(got[f:f + 1], ref)
+    monkeypatch.setenv("SA_LARGE_ONCHIP", "0")
+    two = engine.spectrogram(raw, dt, nfft, frames, hop=hop, window="hann", precision=prec, out_kind=kind)
+    assert engine.last_kernel.startswith("large_cols_kernel+large_rows_kernel")
+    # same arithmetic in the same order (the workspace round trip is the only difference): bit-identical
+    assert np.array_equal(got, two)
+    # rect window on the FP32 path (no window multiply instantiated) and an unaligned start (two-kernel path again)
+    monkeypatch.setenv("SA_LARGE_ONCHIP", "1")
+    if prec == "f32":
+        g2 = engine.spectrogram(raw, dt, nfft, 5, precision=prec, out_kind=kind)
+        assert engine.last_kernel.startswith("large_onchip_kernel<float,256x256,cf32,rect>")
+        check_db_parity(g2[:1], co.spectrogram(raw, dt, 0, nfft, nfft, "rect", 1))
+        g3 = engine.spectrogram(raw, dt, nfft, 3, hop=nfft + 1, precision=prec, out_kind=kind)     # odd hop: frames 8-byte aligned only
+        assert engine.last_kernel.startswith("large_cols_kernel+large_rows_kernel")
+        check_db_parity(g3[1:2], co.spectrogram(raw, dt, nfft + 1, nfft, nfft, "rect", 1))
