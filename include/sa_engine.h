@@ -49,7 +49,11 @@ enum {
 };
 
 /* SigMF core:datatype families (S/sigmf/Global.java:67-79) */
-enum { SA_CF32 = 0, SA_CI16 = 1, SA_CU8 = 2, SA_CI8 = 3, SA_CF64 = 4 };
+enum { SA_CF32 = 0, SA_CI16 = 1, SA_CU8 = 2, SA_CI8 = 3, SA_CF64 = 4,
+       /* any datatype without a decode branch in the reference (ri16_le, cf16 ...): accepted only with
+        * strict_reference, where it decodes as the reference's fall-through branches do (zeros in the
+        * spectrogram, SpectralService.java:60-63; cf32 in the downconverter, ExtractDownConvertService.java:93-96) */
+       SA_DT_OTHER = 5 };
 /* windows, periodic (DFT-even) definitions; the reference spectrogram is SA_WIN_RECT */
 enum { SA_WIN_RECT = 0, SA_WIN_HANN = 1, SA_WIN_HAMMING = 2, SA_WIN_BLACKMAN = 3, SA_WIN_BLACKMAN_HARRIS = 4 };
 /* dB scaling: MAG_1E10 is the reference, 20*log10(|X| + 1e-10) (SpectralService.java:80-81) */
@@ -64,6 +68,11 @@ enum { SA_CMAP_GRAYSCALE = 0, SA_CMAP_HEATMAP = 1 };
 enum { SA_REDUCE_NEAREST = 0, SA_REDUCE_MAX = 1, SA_REDUCE_MEAN = 2 };
 /* IqData.getInterleavedBinary formats (S/data/IqData.java:160-187) */
 enum { SA_PACK_F32 = 0, SA_PACK_I16 = 1 };
+/* analysis profile (sa_analysis_config) */
+enum { SA_DELAY_CAUSAL = 0, SA_DELAY_SAME = 1, SA_DELAY_VALID = 2 };
+enum { SA_LEN_FLOOR = 0, SA_LEN_CEIL = 1 };
+enum { SA_PSD_DENSITY = 0, SA_PSD_SPECTRUM = 1 };
+enum { SA_DETREND_NONE = 0, SA_DETREND_CONSTANT = 1 };
 
 /* Batched spectrogram request: replaces the per-frame loop MainController.java:982-999.
  * Frame t covers samples [start_sample + t*hop, +nfft) of the buffer; a frame that would
@@ -85,7 +94,9 @@ typedef struct sa_spectrogram_params {
     double   eof_fill_db;   /* -150.0 (MainController.java:996-997) */
     /* only for SA_OUT_RGBA8: renderSpectrogram's dB/Hz conversion and colour ramp */
     int32_t  colormap;      /* SA_CMAP_* */
-    int32_t  reserved0;
+    int32_t  strict_reference;  /* 1: decode exactly as SpectralService.java:42-63 does, bugs included: cf64 and
+                                 * SA_DT_OTHER have no branch there and decode to zeros (rows of -200 dB); frames are
+                                 * addressed with Global.getBytesPerSample (16 for cf64, 8 for unknown datatypes) */
     double   sample_rate;   /* fs: conversion = 10*log10(fs/nfft) + 20*log10(nfft) (:1273-1274) */
     double   min_db;        /* -160 default (main-scene.fxml:143) */
     double   max_db;        /* -30 default  (main-scene.fxml:150) */
@@ -100,6 +111,33 @@ typedef struct sa_annotation {
     int32_t  down;          /* floor(fs/bw), >= 1 (:721-728) */
     int32_t  fast;          /* 0 conventional (LPF then decimate), 1 polyphase moving average */
 } sa_annotation;
+
+/* Analysis profile of an engine: every choice JDSP v1.3.1 (build.gradle:142, NOT vendored in the reference) makes
+ * inside Resampler.downConvert / downConvertPolyphase (ExtractDownConvertService.java:106,111-112) and
+ * PowerSpectralDensity.calculatePsdWelch (AnalysisDialogController.java:308-312).  The reference pins none of
+ * them, so they are parameters here, not constants of the kernels; a maintainer who has JDSP sets them once per
+ * engine (INTEGRATION.md maps each field to the JDSP question it answers).  The service entry points keep the
+ * reference's signatures: the profile plays the role the JDSP jar plays on the JVM.
+ *   conventional:  z[m] = sum_{k<L} h[k] y[m*down + off - k],  y[n] = x[n] exp(-2 pi i freq_off n), y = 0 outside
+ *                  [0, count);  off = 0 (CAUSAL), (L-1)/2 (SAME), L-1 (VALID)
+ *   fast:          z[m] = (1/down) sum_{k<down} y[m*down + k]          (delay modes do not apply)
+ *   outputs:       FLOOR count/down | CEIL ceil(count/down) | VALID (count-L)/down + 1
+ *   PSD:           mean over segments of |FFT(w (x - mean))|^2 scaled 1/(fs sum w^2) (DENSITY) or 1/(sum w)^2
+ *                  (SPECTRUM), 10 log10, two-sided, fft-shifted; transforms in FP32 or FP64.
+ * Defaults (sa_analysis_config_init / engines that never set a profile): built-in taps (sa_lowpass_taps), CAUSAL,
+ * FLOOR, DENSITY, no detrend, FP32, strict_reference off. */
+typedef struct sa_analysis_config {
+    uint32_t struct_size;      /* sizeof(sa_analysis_config) */
+    uint32_t n_taps;           /* L; 0 with taps == NULL */
+    const double* taps;        /* h[0..L): used for every decimation factor; NULL: Hamming-windowed sinc, 8*down+1 taps */
+    int32_t  delay_mode;       /* SA_DELAY_* */
+    int32_t  length_mode;      /* SA_LEN_* */
+    int32_t  psd_scaling;      /* SA_PSD_* */
+    int32_t  psd_detrend;      /* SA_DETREND_* */
+    int32_t  psd_precision;    /* SA_PREC_F32 (default) or SA_PREC_F64 (powers of two up to 8192, any length up to ~11000) */
+    int32_t  strict_reference; /* 1: the downconverter decodes as ExtractDownConvertService.java:60-67,79-96 does, bugs
+                                * included: cf64 is read at an 8-byte stride (re = d[i], im = d[i+1]) and SA_DT_OTHER as cf32 */
+} sa_analysis_config;
 
 /* ---- lifecycle ---- */
 SA_API int32_t     sa_engine_create(int32_t device_ordinal, sa_engine** out_engine);
@@ -152,9 +190,20 @@ SA_API int32_t sa_compute_magnitudes(sa_engine* engine, const void* buffer, uint
                                      uint64_t start_byte, uint32_t nfft, int32_t dtype,
                                      int32_t big_endian, double* out_magnitudes);
 
+/* ---- analysis profile ---- */
+SA_API void     sa_analysis_config_init(sa_analysis_config* config);                 /* the defaults above */
+/* copies the configuration (taps included) into the engine; NULL restores the defaults */
+SA_API int32_t  sa_set_analysis_config(sa_engine* engine, const sa_analysis_config* config);
+/* current profile; out->taps points at the engine's copy (valid until the next sa_set_analysis_config) */
+SA_API int32_t  sa_get_analysis_config(sa_engine* engine, sa_analysis_config* out);
+/* M, the number of outputs sa_downconvert produces for `count` input samples under the engine's profile */
+SA_API uint64_t sa_downconvert_length(sa_engine* engine, uint64_t count, int32_t down, int32_t fast);
+
 /* ---- downconvert (ExtractDownConvertService.java:54-117) ---- */
-/* out_re/out_im: host arrays of at least count/down doubles (row 0 / row 1 of the Java
- * double[2][M]); *out_len receives M = count/down. */
+/* NOT parity-verified against the reference: the arithmetic behind these two calls lives in JDSP, which is not
+ * vendored; what is verified is the engine against the profile's written spec (oracle/).
+ * out_re/out_im: host arrays of at least sa_downconvert_length(count, down, fast) doubles (row 0 / row 1 of the
+ * Java double[2][M]); *out_len receives M. */
 SA_API int32_t sa_downconvert(sa_engine* engine, const void* iq, uint64_t iq_bytes, int32_t dtype,
                               int32_t big_endian, uint64_t start_sample, uint64_t count,
                               double freq_off, int32_t down, int32_t fast,
@@ -162,19 +211,23 @@ SA_API int32_t sa_downconvert(sa_engine* engine, const void* iq, uint64_t iq_byt
 SA_API int32_t sa_lowpass_taps(int32_t down, double* taps /* 8*down+1 */);
 
 /* ---- Welch PSD (JDSP calculatePsdWelch call site, AnalysisDialogController.java:303-313) ---- */
-/* re/im: host FP64 arrays of n samples (rows of double[2][n]).  hop = 0 selects nfft/4
- * (75 % overlap).  out_freq / out_db hold nfft doubles: frequency axis centred on 0 and the
- * level in dB/Hz, fft-shifted. */
+/* NOT parity-verified against the reference (JDSP, see above).  re/im: host FP64 arrays of n samples (rows of
+ * double[2][n]).  nfft: ANY length 1 <= nfft <= n -- the caller passes 8192, or n itself for signals shorter than
+ * that (AnalysisDialogController.java:303-307); powers of two 64..16384 run on the Stockham kernels, every other
+ * length on a direct DFT kernel (up to ~24000 points FP32 / ~11000 FP64).  hop = 0 selects nfft/4 (75 % overlap).
+ * out_freq / out_db hold nfft doubles: frequency axis centred on 0 ((k - nfft/2) fs / nfft) and the level in dB,
+ * bin i of the transform at (i + nfft/2) % nfft. */
 SA_API int32_t sa_psd_welch(sa_engine* engine, const double* re, const double* im, uint64_t n,
                             double fs, uint32_t nfft, uint64_t hop, int32_t window,
                             double* out_freq, double* out_db);
 
 /* ---- batched annotation analysis: downconvert + Welch PSD for many annotations, one call ----
  * iq: HOST pointer to the capture; for annotation a: decimated IQ goes to
- * out_iq + iq_offsets[a] (re block of M_a doubles followed by im block, M_a = count/down) when
+ * out_iq + iq_offsets[a] (re block of M_a doubles followed by im block, M_a = sa_downconvert_length) when
  * out_iq != NULL; the PSD (psd_nfft doubles, dB/Hz, fft-shifted; fs' = sample_rate/down) goes to
- * out_psd_db + a*psd_nfft when out_psd_db != NULL.  Annotations with M_a < psd_nfft get a PSD
- * row of NaN (the Java caller falls back to a single short window, :304-307). */
+ * out_psd_db + a*psd_nfft when out_psd_db != NULL.  An annotation with M_a < psd_nfft gets the Java caller's
+ * short-signal rule (:304-307): ONE window of M_a points; its M_a bins sit at the start of the row, the rest of
+ * the row is NaN.  With out_iq == NULL the decimated IQ never leaves the chip's L2 (PSD-only mode). */
 SA_API int32_t sa_downconvert_psd_batch(sa_engine* engine, const void* iq, uint64_t iq_bytes,
                                         int32_t dtype, int32_t big_endian, double sample_rate,
                                         const sa_annotation* anns, uint32_t n_ann,

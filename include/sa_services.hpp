@@ -45,8 +45,12 @@ public:
     Engine(const Engine&) = delete;
     Engine& operator=(const Engine&) = delete;
     sa_engine* handle() const { return h_; }
+    // anonymous memory only: cudaHostRegister refuses file-backed mappings (the engine stages those itself)
     void registerHost(const MappedByteBuffer& b) { sa_check(sa_register_host(h_, b.data, b.capacity, 1)); }
     void unregisterHost(const MappedByteBuffer& b) { sa_check(sa_unregister_host(h_, b.data)); }
+    // the engine's JDSP profile (sa_analysis_config: taps, delay / length rule, PSD scaling / detrend / precision)
+    void setAnalysisConfig(const sa_analysis_config& c) { sa_check(sa_set_analysis_config(h_, &c)); }
+    void resetAnalysisConfig() { sa_check(sa_set_analysis_config(h_, nullptr)); }
 private:
     sa_engine* h_ = nullptr;
 };
@@ -66,6 +70,20 @@ public:
         std::vector<double> out((size_t)nfft);
         sa_check(sa_compute_magnitudes(e_.handle(), buffer.data, buffer.capacity, (uint64_t)startByte, (uint32_t)nfft,
                                        dt.dtype, dt.big_endian, out.data()));
+        return out;
+    }
+    // The same waterfall read from the data file itself (SigMfHelper.load, S/sigmf/SigMfHelper.java:59-84: dataPath and
+    // core:header_bytes): parallel pread into the engine's pinned ring, no mapped buffer and no 2 GiB limit.
+    std::vector<float> computeWaterfallFromFile(const std::string& dataPath, uint64_t headerBytes, int64_t firstSample,
+                                                int64_t frames, int fftSize, int64_t hop, int window,
+                                                const std::string& datatype) const {
+        const Datatype dt(datatype);
+        sa_spectrogram_params p;
+        sa_spectrogram_params_init(&p);
+        p.dtype = dt.dtype; p.big_endian = dt.big_endian; p.nfft = (uint32_t)fftSize; p.hop = (uint64_t)hop;
+        p.window = window; p.start_sample = (uint64_t)firstSample; p.n_frames = (uint64_t)frames;
+        std::vector<float> out((size_t)frames * fftSize);
+        sa_check(sa_spectrogram_file(e_.handle(), dataPath.c_str(), headerBytes, 0, &p, out.data(), out.size() * sizeof(float)));
         return out;
     }
     // The frame loop of MainController.updateDisplay (:980-999) as one call: waterfall[canvasW][fftSize].
@@ -94,12 +112,46 @@ public:
                                                            bool fast = false) const {
         const Datatype dt(datatype);
         if (down < 1) throw std::invalid_argument("down < 1");
-        const size_t m = (size_t)count / (size_t)down;
+        const size_t m = (size_t)sa_downconvert_length(e_.handle(), (uint64_t)count, down, fast ? 1 : 0);
         std::vector<std::vector<double>> out(2, std::vector<double>(m ? m : 1));
         uint64_t n = 0;
         sa_check(sa_downconvert(e_.handle(), buffer.data, buffer.capacity, dt.dtype, dt.big_endian, (uint64_t)startSample,
                                 (uint64_t)count, freqOff, down, fast ? 1 : 0, out[0].data(), out[1].data(), &n));
         out[0].resize(n); out[1].resize(n);
+        return out;
+    }
+    // The batch loop of AnnotationController.executeCapability (S/controllers/AnnotationController.java:321-360: one
+    // extractAndDownConvertAsync(..., fast = false).join() per selected row) as ONE call: only the annotated spans cross
+    // PCIe, once.  Returns the double[2][M_i] of every annotation; when psdNfft > 0 the Welch PSD rows (dB, sampling
+    // rate sampleRate / down, fft-shifted; shorter annotations follow the caller's single-window rule, rest of the row
+    // NaN) are written to *psd as [n][psdNfft].
+    struct Annotation { int64_t startSample; int count; double freqOff; int down; };
+    std::vector<std::vector<std::vector<double>>> extractAndDownConvertBatch(
+            const MappedByteBuffer& buffer, const std::string& datatype, double sampleRate,
+            const std::vector<Annotation>& rows, int psdNfft = 0, std::vector<double>* psd = nullptr) const {
+        const Datatype dt(datatype);
+        std::vector<sa_annotation> anns(rows.size());
+        std::vector<uint64_t> offs(rows.size()), len(rows.size());
+        uint64_t total = 0;
+        for (size_t i = 0; i < rows.size(); i++) {
+            if (rows[i].down < 1) throw std::invalid_argument("down < 1");
+            anns[i].start_sample = (uint64_t)rows[i].startSample; anns[i].count = (uint64_t)rows[i].count;
+            anns[i].freq_off = rows[i].freqOff; anns[i].down = rows[i].down; anns[i].fast = 0;
+            len[i] = sa_downconvert_length(e_.handle(), anns[i].count, anns[i].down, 0);
+            offs[i] = total;
+            total += 2 * len[i];
+        }
+        std::vector<double> iq(total ? total : 1);
+        const bool want_psd = psdNfft > 0 && psd != nullptr;
+        if (want_psd) psd->assign(rows.size() * (size_t)psdNfft, 0.0);
+        sa_check(sa_downconvert_psd_batch(e_.handle(), buffer.data, buffer.capacity, dt.dtype, dt.big_endian, sampleRate,
+                                          anns.data(), (uint32_t)anns.size(), want_psd ? (uint32_t)psdNfft : 0, 0,
+                                          SA_WIN_HANN, iq.data(), offs.data(), want_psd ? psd->data() : nullptr));
+        std::vector<std::vector<std::vector<double>>> out(rows.size());
+        for (size_t i = 0; i < rows.size(); i++) {
+            const double* p = iq.data() + offs[i];
+            out[i] = { std::vector<double>(p, p + len[i]), std::vector<double>(p + len[i], p + 2 * len[i]) };
+        }
         return out;
     }
 private:

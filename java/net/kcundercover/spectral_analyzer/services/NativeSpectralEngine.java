@@ -57,6 +57,21 @@ public final class NativeSpectralEngine implements AutoCloseable {
             FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, JAVA_DOUBLE, JAVA_INT, JAVA_LONG,
                     JAVA_INT, ADDRESS, ADDRESS));
 
+    // int32 sa_spectrogram_file(engine, path, data_offset, data_bytes, params, out, out_bytes)
+    private static final MethodHandle SPECTROGRAM_FILE = fn("sa_spectrogram_file",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG, ADDRESS, ADDRESS, JAVA_LONG));
+    // uint64 sa_downconvert_length(engine, count, down, fast)
+    private static final MethodHandle DOWNCONVERT_LENGTH = fn("sa_downconvert_length",
+            FunctionDescriptor.of(JAVA_LONG, ADDRESS, JAVA_LONG, JAVA_INT, JAVA_INT));
+    // int32 sa_downconvert_psd_batch(engine, iq, iq_bytes, dtype, be, fs, anns, n_ann, psd_nfft, psd_hop, psd_window,
+    //                                out_iq, iq_offsets, out_psd_db)
+    private static final MethodHandle BATCH = fn("sa_downconvert_psd_batch",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, JAVA_INT, JAVA_INT, JAVA_DOUBLE, ADDRESS, JAVA_INT,
+                    JAVA_INT, JAVA_LONG, JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
+    private static final MethodHandle CONFIG_INIT = fn("sa_analysis_config_init", FunctionDescriptor.ofVoid(ADDRESS));
+    // int32 sa_set_analysis_config(engine, config)
+    private static final MethodHandle SET_CONFIG = fn("sa_set_analysis_config", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+
     // int32 sa_render_canvas(engine, iq, iq_bytes, params, canvas_w, canvas_h, frames_per_column, reduce, out_rgba)
     private static final MethodHandle RENDER_CANVAS = fn("sa_render_canvas",
             FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS, JAVA_INT, JAVA_INT, JAVA_LONG, JAVA_INT, ADDRESS));
@@ -74,8 +89,19 @@ public final class NativeSpectralEngine implements AutoCloseable {
             JAVA_INT.withName("window"), JAVA_INT.withName("nfft"), JAVA_INT.withName("db_mode"),
             JAVA_INT.withName("out_kind"), JAVA_INT.withName("precision"), JAVA_LONG.withName("start_sample"),
             JAVA_LONG.withName("hop"), JAVA_LONG.withName("n_frames"), JAVA_DOUBLE.withName("eof_fill_db"),
-            JAVA_INT.withName("colormap"), JAVA_INT.withName("reserved0"), JAVA_DOUBLE.withName("sample_rate"),
+            JAVA_INT.withName("colormap"), JAVA_INT.withName("strict_reference"), JAVA_DOUBLE.withName("sample_rate"),
             JAVA_DOUBLE.withName("min_db"), JAVA_DOUBLE.withName("max_db"));
+
+    /** struct sa_annotation (include/sa_engine.h): one row of the batch loop AnnotationController.java:321-360. */
+    static final StructLayout ANNOTATION = MemoryLayout.structLayout(
+            JAVA_LONG.withName("start_sample"), JAVA_LONG.withName("count"), JAVA_DOUBLE.withName("freq_off"),
+            JAVA_INT.withName("down"), JAVA_INT.withName("fast"));
+
+    /** struct sa_analysis_config (include/sa_engine.h): what JDSP decides inside downConvert / calculatePsdWelch. */
+    static final StructLayout CONFIG = MemoryLayout.structLayout(
+            JAVA_INT.withName("struct_size"), JAVA_INT.withName("n_taps"), ADDRESS.withName("taps"),
+            JAVA_INT.withName("delay_mode"), JAVA_INT.withName("length_mode"), JAVA_INT.withName("psd_scaling"),
+            JAVA_INT.withName("psd_detrend"), JAVA_INT.withName("psd_precision"), JAVA_INT.withName("strict_reference"));
 
     private final MemorySegment engine;
 
@@ -101,10 +127,62 @@ public final class NativeSpectralEngine implements AutoCloseable {
         }
     }
 
-    /** Page-locks the mapped .sigmf-data file once after SigMfHelper.load (SigMfHelper.java:78-84). */
-    public void register(MappedByteBuffer buffer) throws Throwable {
-        MemorySegment seg = MemorySegment.ofBuffer(buffer);
-        check((int) REGISTER.invoke(engine, seg, seg.byteSize(), 1));
+    /**
+     * Page-locks an ANONYMOUS native segment (Arena-allocated staging or output memory) so that it is the DMA source /
+     * target itself.  Do not call it with the MappedByteBuffer of SigMfHelper.load (SigMfHelper.java:78-84):
+     * cudaHostRegister refuses file-backed mappings (measured on the B200 hosts: "invalid argument") and this throws.
+     * The mapped buffer needs no registration: the engine stages it through its own pinned ring with parallel copies,
+     * and {@link #spectrogramFromFile} reads the data file into that ring directly.
+     */
+    public void register(MemorySegment anonymousSegment) throws Throwable {
+        check((int) REGISTER.invoke(engine, anonymousSegment, anonymousSegment.byteSize(), 0));
+    }
+
+    /**
+     * The JDSP profile of this engine (sa_set_analysis_config): taps (null = built-in design), delay mode
+     * (0 causal, 1 same, 2 valid), length mode (0 floor, 1 ceil), PSD scaling (0 density, 1 spectrum), detrend
+     * (0 none, 1 constant), PSD precision (1 FP32, 2 FP64), strict reference decode.
+     */
+    public void setAnalysisConfig(double[] taps, int delayMode, int lengthMode, int psdScaling, int psdDetrend,
+                                  int psdPrecision, boolean strictReference) throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment c = a.allocate(CONFIG);
+            CONFIG_INIT.invoke(c);
+            if (taps != null) {
+                c.set(ADDRESS, CONFIG.byteOffset(MemoryLayout.PathElement.groupElement("taps")), a.allocateFrom(JAVA_DOUBLE, taps));
+                c.set(JAVA_INT, CONFIG.byteOffset(MemoryLayout.PathElement.groupElement("n_taps")), taps.length);
+            }
+            c.set(JAVA_INT, CONFIG.byteOffset(MemoryLayout.PathElement.groupElement("delay_mode")), delayMode);
+            c.set(JAVA_INT, CONFIG.byteOffset(MemoryLayout.PathElement.groupElement("length_mode")), lengthMode);
+            c.set(JAVA_INT, CONFIG.byteOffset(MemoryLayout.PathElement.groupElement("psd_scaling")), psdScaling);
+            c.set(JAVA_INT, CONFIG.byteOffset(MemoryLayout.PathElement.groupElement("psd_detrend")), psdDetrend);
+            c.set(JAVA_INT, CONFIG.byteOffset(MemoryLayout.PathElement.groupElement("psd_precision")), psdPrecision);
+            c.set(JAVA_INT, CONFIG.byteOffset(MemoryLayout.PathElement.groupElement("strict_reference")), strictReference ? 1 : 0);
+            check((int) SET_CONFIG.invoke(engine, c));        // the engine copies the taps
+        }
+    }
+
+    /**
+     * The whole-recording waterfall straight from the data file (SigMfHelper.java:59-84: dataPath, headerBytes): no
+     * mapped buffer, no 2 GiB limit (:78-82).  Rows of float32 dB, time-major.
+     */
+    public float[] spectrogramFromFile(String dataPath, long headerBytes, long firstSample, long frames, int fftSize,
+                                       long hop, int window, String datatype) throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            int[] dt = parse(a, datatype);
+            MemorySegment p = a.allocate(PARAMS);
+            PARAMS_INIT.invoke(p);
+            p.set(JAVA_INT, PARAMS.byteOffset(MemoryLayout.PathElement.groupElement("dtype")), dt[0]);
+            p.set(JAVA_INT, PARAMS.byteOffset(MemoryLayout.PathElement.groupElement("big_endian")), dt[1]);
+            p.set(JAVA_INT, PARAMS.byteOffset(MemoryLayout.PathElement.groupElement("window")), window);
+            p.set(JAVA_INT, PARAMS.byteOffset(MemoryLayout.PathElement.groupElement("nfft")), fftSize);
+            p.set(JAVA_LONG, PARAMS.byteOffset(MemoryLayout.PathElement.groupElement("start_sample")), firstSample);
+            p.set(JAVA_LONG, PARAMS.byteOffset(MemoryLayout.PathElement.groupElement("hop")), hop);
+            p.set(JAVA_LONG, PARAMS.byteOffset(MemoryLayout.PathElement.groupElement("n_frames")), frames);
+            MemorySegment out = a.allocate(ValueLayout.JAVA_FLOAT, frames * fftSize);
+            check((int) SPECTROGRAM_FILE.invoke(engine, a.allocateFrom(dataPath), headerBytes, 0L, p, out, out.byteSize()));
+            return out.toArray(ValueLayout.JAVA_FLOAT);
+        }
     }
 
     /** Drop-in body of SpectralService.computeMagnitudes (SpectralService.java:33-85). */
@@ -147,7 +225,7 @@ public final class NativeSpectralEngine implements AutoCloseable {
                                             double freqOff, int down, boolean fast) throws Throwable {
         try (Arena a = Arena.ofConfined()) {
             int[] dt = parse(a, datatype);
-            long m = count / down;
+            long m = (long) DOWNCONVERT_LENGTH.invoke(engine, (long) count, down, fast ? 1 : 0);   // M under the engine's profile
             MemorySegment re = a.allocate(JAVA_DOUBLE, Math.max(m, 1)), im = a.allocate(JAVA_DOUBLE, Math.max(m, 1));
             MemorySegment len = a.allocate(JAVA_LONG);
             MemorySegment seg = MemorySegment.ofBuffer(buffer);
@@ -158,7 +236,49 @@ public final class NativeSpectralEngine implements AutoCloseable {
         }
     }
 
-    /** Replaces PowerSpectralDensity.calculatePsdWelch at AnalysisDialogController.java:308-312. */
+    /**
+     * ONE call for the batch loop of AnnotationController.executeCapability (AnnotationController.java:321-360, which
+     * runs extractAndDownConvertAsync(...).join() per row): rows[i] = {startSample, count, freqOff, down}; fast = false
+     * as at :336-337.  Returns the double[2][M_i] of every row and, when psdNfft > 0, the Welch PSD rows (dB, fs / down)
+     * in psdOut[i] (psdOut may be null).  Only the annotated spans cross PCIe, once.
+     */
+    public double[][][] extractAndDownConvertBatch(MappedByteBuffer buffer, String datatype, double sampleRate,
+                                                   double[][] rows, int psdNfft, double[][] psdOut) throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            int[] dt = parse(a, datatype);
+            int n = rows.length;
+            MemorySegment anns = a.allocate(ANNOTATION, n);
+            MemorySegment offs = a.allocate(JAVA_LONG, Math.max(n, 1));
+            long[] len = new long[n];
+            long total = 0;
+            for (int i = 0; i < n; i++) {
+                long base = i * ANNOTATION.byteSize();
+                anns.set(JAVA_LONG, base, (long) rows[i][0]);
+                anns.set(JAVA_LONG, base + 8, (long) rows[i][1]);
+                anns.set(JAVA_DOUBLE, base + 16, rows[i][2]);
+                anns.set(JAVA_INT, base + 24, (int) rows[i][3]);
+                anns.set(JAVA_INT, base + 28, 0);
+                len[i] = (long) DOWNCONVERT_LENGTH.invoke(engine, (long) rows[i][1], (int) rows[i][3], 0);
+                offs.setAtIndex(JAVA_LONG, i, total);
+                total += 2 * len[i];
+            }
+            MemorySegment iq = a.allocate(JAVA_DOUBLE, Math.max(total, 1));
+            MemorySegment psd = (psdNfft > 0 && psdOut != null) ? a.allocate(JAVA_DOUBLE, (long) n * psdNfft) : MemorySegment.NULL;
+            MemorySegment seg = MemorySegment.ofBuffer(buffer);
+            check((int) BATCH.invoke(engine, seg, seg.byteSize(), dt[0], dt[1], sampleRate, anns, n, psdNfft, 0L,
+                    1 /* SA_WIN_HANN */, iq, offs, psd));
+            double[][][] out = new double[n][][];
+            for (int i = 0; i < n; i++) {
+                long o = offs.getAtIndex(JAVA_LONG, i) * 8;
+                out[i] = new double[][] { iq.asSlice(o, 8 * len[i]).toArray(JAVA_DOUBLE),
+                                          iq.asSlice(o + 8 * len[i], 8 * len[i]).toArray(JAVA_DOUBLE) };
+                if (psdNfft > 0 && psdOut != null) psdOut[i] = psd.asSlice((long) i * psdNfft * 8, (long) psdNfft * 8).toArray(JAVA_DOUBLE);
+            }
+            return out;
+        }
+    }
+
+    /** Replaces PowerSpectralDensity.calculatePsdWelch at AnalysisDialogController.java:308-312 (any nfft <= data length). */
     public double[][] calculatePsdWelch(double[][] data, double fs, int nfft) throws Throwable {
         try (Arena a = Arena.ofConfined()) {
             MemorySegment re = a.allocateFrom(JAVA_DOUBLE, data[0]), im = a.allocateFrom(JAVA_DOUBLE, data[1]);

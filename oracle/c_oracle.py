@@ -11,6 +11,28 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 DTYPES = {"cf32": 0, "ci16": 1, "cu8": 2, "ci8": 3, "cf64": 4}
+DT_OTHER = 5          # a datatype without a decode branch (ri16_le, cf16 ...): only meaningful with strict_reference
+DELAY = {"causal": 0, "same": 1, "valid": 2}
+LENGTH = {"floor": 0, "ceil": 1}
+SCALING = {"density": 0, "spectrum": 1}
+DETREND = {None: 0, "none": 0, False: 0, "constant": 1}
+
+
+class AnalysisCfg(C.Structure):
+    _fields_ = [("taps", C.POINTER(C.c_double)), ("n_taps", C.c_int), ("delay_mode", C.c_int), ("length_mode", C.c_int),
+                ("psd_scaling", C.c_int), ("psd_detrend", C.c_int), ("strict_reference", C.c_int)]
+
+
+def analysis_cfg(taps=None, delay="causal", length="floor", scaling="density", detrend=None, strict_reference=False):
+    """ora_analysis_cfg; keeps the taps array alive on the returned object."""
+    c = AnalysisCfg()
+    if taps is not None:
+        c._taps = np.ascontiguousarray(taps, np.float64)
+        c.taps = c._taps.ctypes.data_as(C.POINTER(C.c_double))
+        c.n_taps = c._taps.size
+    c.delay_mode, c.length_mode = DELAY[delay], LENGTH[length]
+    c.psd_scaling, c.psd_detrend, c.strict_reference = SCALING[scaling], DETREND[detrend], int(strict_reference)
+    return c
 WINDOWS = {"rect": 0, "hann": 1, "hamming": 2, "blackman": 3, "blackman_harris": 4}
 DB_MAG_1E10, DB_POWER = 0, 1
 CMAPS = {"Grayscale": 0, "Heatmap": 1}
@@ -23,6 +45,17 @@ def parse_datatype(datatype):
     if kind not in DTYPES:
         raise ValueError("unsupported datatype " + datatype)
     return kind, (0 if datatype.endswith("_le") else 1)
+
+
+def dtype_code(datatype, strict_reference=False):
+    """(code, big_endian); with strict_reference a datatype without a decode branch maps to DT_OTHER."""
+    kind = datatype.split("_")[0]
+    be = 0 if datatype.endswith("_le") else 1
+    if kind in DTYPES:
+        return DTYPES[kind], be
+    if strict_reference:
+        return DT_OTHER, be
+    raise ValueError("unsupported datatype " + datatype)
 
 
 def build():
@@ -49,6 +82,12 @@ def lib():
         L.ora_downconvert.argtypes = [u8p, C.c_uint64, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_double,
                                       C.c_int, C.c_int, dp, dp, C.POINTER(C.c_uint64)]
         L.ora_psd_welch.argtypes = [dp, dp, C.c_uint64, C.c_double, C.c_int, C.c_uint64, C.c_int, dp, dp]
+        cfgp = C.POINTER(AnalysisCfg)
+        L.ora_downconvert_length.restype = C.c_uint64
+        L.ora_downconvert_length.argtypes = [C.c_uint64, C.c_int, C.c_int, cfgp]
+        L.ora_downconvert_ex.argtypes = [u8p, C.c_uint64, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_double,
+                                         C.c_int, C.c_int, cfgp, dp, dp, C.POINTER(C.c_uint64)]
+        L.ora_psd_welch_ex.argtypes = [dp, dp, C.c_uint64, C.c_double, C.c_int, C.c_uint64, C.c_int, cfgp, dp, dp]
         L.ora_iq_pack.argtypes = [dp, dp, C.c_uint64, C.c_int, u8p]
         L.ora_analysis_series.argtypes = [dp, dp, C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_double, dp, dp]
         L.ora_window.argtypes = [C.c_int, C.c_int, dp]
@@ -135,14 +174,27 @@ def downconvert(buf, datatype, start_sample, count, freq_off, down, fast=False):
     return np.stack([re[:n.value], im[:n.value]])
 
 
-def psd_welch(iq, fs, nfft, hop=None, window="hann"):
-    """PowerSpectralDensity.calculatePsdWelch call site (AnalysisDialogController.java:303-313)."""
+def downconvert_ex(buf, datatype, start_sample, count, freq_off, down, fast=False, cfg=None):
+    """The same with the JDSP unknowns as parameters (ora_analysis_cfg)."""
+    cfg = cfg or analysis_cfg()
+    code, be = dtype_code(datatype, bool(cfg.strict_reference))
+    a, p = _u8(buf)
+    m = int(lib().ora_downconvert_length(count, down, int(fast), C.byref(cfg)))
+    re, im = np.empty(max(m, 1), np.float64), np.empty(max(m, 1), np.float64)
+    n = C.c_uint64(0)
+    _chk(lib().ora_downconvert_ex(p, a.size, code, be, start_sample, count, freq_off, down, int(fast), C.byref(cfg),
+                                  _dp(re), _dp(im), C.byref(n)), "downconvert_ex")
+    return np.stack([re[:n.value], im[:n.value]])
+
+
+def psd_welch(iq, fs, nfft, hop=None, window="hann", cfg=None):
+    """PowerSpectralDensity.calculatePsdWelch call site (AnalysisDialogController.java:303-313); any nfft >= 1."""
     re = np.ascontiguousarray(iq[0], np.float64)
     im = np.ascontiguousarray(iq[1], np.float64)
     hop = hop or max(1, nfft // 4)
     f, d = np.empty(nfft, np.float64), np.empty(nfft, np.float64)
-    _chk(lib().ora_psd_welch(_dp(re), _dp(im), re.size, fs, nfft, hop, WINDOWS[window], _dp(f), _dp(d)),
-         "psd_welch")
+    _chk(lib().ora_psd_welch_ex(_dp(re), _dp(im), re.size, fs, nfft, hop, WINDOWS[window],
+                                C.byref(cfg) if cfg is not None else None, _dp(f), _dp(d)), "psd_welch")
     return np.stack([f, d])
 
 

@@ -312,16 +312,49 @@ int ora_lowpass_taps(int down, double* taps) {
     return 0;
 }
 
-int ora_downconvert(const uint8_t* buf, uint64_t cap_bytes, int dtype, int big_endian,
-                    uint64_t start_sample, uint64_t count, double freq_off, int down, int fast,
-                    double* out_re, double* out_im, uint64_t* out_len) {
-    int bps = ora_bytes_per_iq(dtype);
-    if (bps == 0 || down < 1) return -1;
+/* ---- configurable spec: every choice JDSP makes that the reference does not pin ----
+ * Output m of the conventional path:  z[m] = sum_{k<L} h[k] y[m*D + off - k],  y = mixed samples, y[n] = 0 outside
+ * [0, count);  off = 0 (causal), (L-1)/2 (same: group delay compensated), L-1 (valid: only full overlaps).
+ * Output count: valid -> (count-L)/D + 1 (0 if count < L); otherwise floor(count/D) or ceil(count/D).
+ * Fast path: out[m] = (1/D) sum_{k<D} y[m*D + k] (delay modes do not apply; valid counts as floor). */
+uint64_t ora_downconvert_length(uint64_t count, int down, int fast, const ora_analysis_cfg* cfg) {
+    const int L = (cfg && cfg->taps) ? cfg->n_taps : 8 * down + 1;
+    const int delay = cfg ? cfg->delay_mode : 0, len = cfg ? cfg->length_mode : 0;
+    if (!fast && delay == 2) return count >= (uint64_t)L ? (count - (uint64_t)L) / (uint64_t)down + 1 : 0;
+    return len == 1 ? (count + (uint64_t)down - 1) / (uint64_t)down : count / (uint64_t)down;
+}
+
+int ora_downconvert_ex(const uint8_t* buf, uint64_t cap_bytes, int dtype, int big_endian,
+                       uint64_t start_sample, uint64_t count, double freq_off, int down, int fast,
+                       const ora_analysis_cfg* cfg, double* out_re, double* out_im, uint64_t* out_len) {
+    const int strict = cfg ? cfg->strict_reference : 0;
+    if (down < 1) return -1;
     double* re = (double*)malloc(sizeof(double) * (count ? count : 1));
     double* im = (double*)malloc(sizeof(double) * (count ? count : 1));
     if (!re || !im) { free(re); free(im); return -3; }
-    /* ExtractDownConvertService.java:67,74-100 (cf64 decoded with the correct stride) */
-    int rc = ora_decode(buf, cap_bytes, start_sample * (uint64_t)bps, count, dtype, big_endian, 0, re, im);
+    int rc = 0;
+    if (strict && (dtype == ORA_CF64 || ora_bytes_per_iq(dtype) == 0)) {
+        /* ExtractDownConvertService.java:60-67: bytesPerIQ falls to 8 for everything that is not ci16 / cu8 / ci8;
+         * :79-81 cf64 then reads two doubles at that 8-byte stride (re = d[i], im = d[i+1]);
+         * :93-96 any other datatype is read as two floats */
+        const uint64_t start_byte = start_sample * 8u;
+        const uint64_t need = dtype == ORA_CF64 ? (count ? (count + 1) * 8u : 0) : count * 8u;
+        if (start_byte + need > cap_bytes) rc = -2;
+        for (uint64_t i = 0; i < count && !rc; i++) {
+            const uint8_t* p = buf + start_byte + i * 8u;
+            if (dtype == ORA_CF64) {
+                uint64_t a = rd64(p, big_endian), b = rd64(p + 8, big_endian);
+                memcpy(&re[i], &a, 8); memcpy(&im[i], &b, 8);
+            } else {
+                decode_one(p, ORA_CF32, big_endian, 0, &re[i], &im[i]);
+            }
+        }
+    } else {
+        int bps = ora_bytes_per_iq(dtype);
+        if (bps == 0) rc = -1;
+        /* ExtractDownConvertService.java:67,74-100 (cf64 decoded with the correct stride) */
+        else rc = ora_decode(buf, cap_bytes, start_sample * (uint64_t)bps, count, dtype, big_endian, 0, re, im);
+    }
     if (rc) { free(re); free(im); return rc; }
     /* NCO mix; phase reduced mod 1 in FP64 before the trig call */
     for (uint64_t n = 0; n < count; n++) {
@@ -330,23 +363,30 @@ int ora_downconvert(const uint8_t* buf, uint64_t cap_bytes, int dtype, int big_e
         double a = re[n], b = im[n];
         re[n] = a * c - b * s; im[n] = a * s + b * c;
     }
-    uint64_t m_out = count / (uint64_t)down;
+    const uint64_t m_out = ora_downconvert_length(count, down, fast, cfg);
     if (fast) {                                                /* :104-106 "moving average" */
         for (uint64_t m = 0; m < m_out; m++) {
             double sr = 0.0, si = 0.0;
-            for (int k = 0; k < down; k++) { sr += re[m * down + k]; si += im[m * down + k]; }
+            for (int k = 0; k < down; k++) {
+                const uint64_t n = m * (uint64_t)down + (uint64_t)k;
+                if (n < count) { sr += re[n]; si += im[n]; }
+            }
             out_re[m] = sr / down; out_im[m] = si / down;
         }
     } else {                                                   /* :109-112 "LPF - downconvert" */
-        int nt = 8 * down + 1;
-        double* h = (double*)malloc(sizeof(double) * nt);
-        ora_lowpass_taps(down, h);
+        const int nt = (cfg && cfg->taps) ? cfg->n_taps : 8 * down + 1;
+        double* h = (double*)malloc(sizeof(double) * (size_t)nt);
+        if (cfg && cfg->taps) memcpy(h, cfg->taps, sizeof(double) * (size_t)nt); else ora_lowpass_taps(down, h);
+        const int delay = cfg ? cfg->delay_mode : 0;
+        const int64_t off = delay == 1 ? (nt - 1) / 2 : delay == 2 ? nt - 1 : 0;
         for (uint64_t m = 0; m < m_out; m++) {
             double sr = 0.0, si = 0.0;
-            uint64_t n0 = m * (uint64_t)down;
+            const int64_t n0 = (int64_t)(m * (uint64_t)down) + off;
             for (int k = 0; k < nt; k++) {
-                if ((uint64_t)k > n0) break;
-                sr += h[k] * re[n0 - k]; si += h[k] * im[n0 - k];
+                const int64_t n = n0 - k;
+                if (n < 0) break;
+                if ((uint64_t)n >= count) continue;
+                sr += h[k] * re[n]; si += h[k] * im[n];
             }
             out_re[m] = sr; out_im[m] = si;
         }
@@ -357,35 +397,81 @@ int ora_downconvert(const uint8_t* buf, uint64_t cap_bytes, int dtype, int big_e
     return 0;
 }
 
-int ora_psd_welch(const double* re, const double* im, uint64_t n, double fs, int nfft,
-                  uint64_t hop, int window_id, double* out_freq, double* out_db) {
-    if (nfft <= 0 || (nfft & (nfft - 1)) || (uint64_t)nfft > n || hop == 0) return -1;
+int ora_downconvert(const uint8_t* buf, uint64_t cap_bytes, int dtype, int big_endian,
+                    uint64_t start_sample, uint64_t count, double freq_off, int down, int fast,
+                    double* out_re, double* out_im, uint64_t* out_len) {
+    return ora_downconvert_ex(buf, cap_bytes, dtype, big_endian, start_sample, count, freq_off, down, fast, NULL,
+                              out_re, out_im, out_len);
+}
+
+/* Welch PSD, any nfft >= 1 (the reference's short-signal branch passes nfft = signal length,
+ * AnalysisDialogController.java:304-307): power-of-two lengths through the radix-2 plan, everything else through
+ * the direct O(N^2) DFT with exact twiddle indices.  Segment count 1 + (n - nfft)/hop; optional per-segment mean
+ * removal (detrend = constant); density 1/(K fs sum w^2) or spectrum 1/(K (sum w)^2) scaling; two-sided; bin i
+ * lands at (i + nfft/2) % nfft (numpy fftshift, also for odd nfft); freq[k] = (k - nfft/2) fs / nfft. */
+int ora_psd_welch_ex(const double* re, const double* im, uint64_t n, double fs, int nfft,
+                     uint64_t hop, int window_id, const ora_analysis_cfg* cfg, double* out_freq, double* out_db) {
+    if (nfft <= 0 || (uint64_t)nfft > n || hop == 0) return -1;
+    const int pow2 = (nfft & (nfft - 1)) == 0 && nfft >= 2;
     double* w = (double*)malloc(sizeof(double) * nfft);
     double* a = (double*)malloc(sizeof(double) * nfft);
     double* b = (double*)malloc(sizeof(double) * nfft);
     double* acc = (double*)calloc(nfft, sizeof(double));
+    double* tr = NULL; double* ti = NULL; double* xr = NULL; double* xi = NULL;
     fft_plan plan;
-    if (!w || !a || !b || !acc || ora_window(window_id, nfft, w) || plan_init(&plan, nfft)) return -3;
-    double sw2 = 0.0;
-    for (int i = 0; i < nfft; i++) sw2 += w[i] * w[i];
+    if (!w || !a || !b || !acc || ora_window(window_id, nfft, w)) return -3;
+    if (pow2) { if (plan_init(&plan, nfft)) return -3; }
+    else {
+        tr = (double*)malloc(sizeof(double) * nfft); ti = (double*)malloc(sizeof(double) * nfft);
+        xr = (double*)malloc(sizeof(double) * nfft); xi = (double*)malloc(sizeof(double) * nfft);
+        if (!tr || !ti || !xr || !xi) return -3;
+        for (int j = 0; j < nfft; j++) { tr[j] = cos(2.0 * M_PI * j / nfft); ti[j] = -sin(2.0 * M_PI * j / nfft); }
+    }
+    double sw = 0.0, sw2 = 0.0;
+    for (int i = 0; i < nfft; i++) { sw += w[i]; sw2 += w[i] * w[i]; }
+    const int detrend = cfg ? cfg->psd_detrend : 0, scaling = cfg ? cfg->psd_scaling : 0;
     uint64_t nseg = 1 + (n - (uint64_t)nfft) / hop;
     for (uint64_t s = 0; s < nseg; s++) {
-        for (int i = 0; i < nfft; i++) { a[i] = re[s * hop + i] * w[i]; b[i] = im[s * hop + i] * w[i]; }
-        plan_fft(&plan, a, b);
+        double mr = 0.0, mi = 0.0;
+        if (detrend) {
+            for (int i = 0; i < nfft; i++) { mr += re[s * hop + i]; mi += im[s * hop + i]; }
+            mr /= nfft; mi /= nfft;
+        }
+        for (int i = 0; i < nfft; i++) { a[i] = (re[s * hop + i] - mr) * w[i]; b[i] = (im[s * hop + i] - mi) * w[i]; }
+        if (pow2) {
+            plan_fft(&plan, a, b);
+        } else {
+            for (int k = 0; k < nfft; k++) {
+                double sr = 0.0, si = 0.0;
+                int idx = 0;
+                for (int i = 0; i < nfft; i++) {
+                    sr += a[i] * tr[idx] - b[i] * ti[idx];
+                    si += a[i] * ti[idx] + b[i] * tr[idx];
+                    idx += k; if (idx >= nfft) idx -= nfft;
+                }
+                xr[k] = sr; xi[k] = si;
+            }
+            memcpy(a, xr, sizeof(double) * nfft); memcpy(b, xi, sizeof(double) * nfft);
+        }
         for (int i = 0; i < nfft; i++) acc[i] += a[i] * a[i] + b[i] * b[i];
     }
     int half = nfft / 2;
-    double scale = 1.0 / ((double)nseg * fs * sw2);
+    double scale = scaling == 1 ? 1.0 / ((double)nseg * sw * sw) : 1.0 / ((double)nseg * fs * sw2);
     for (int i = 0; i < nfft; i++) {
         int k = (i + half) % nfft;
         out_db[k] = 10.0 * log10(acc[i] * scale + 1e-30);
     }
     for (int k = 0; k < nfft; k++) out_freq[k] = ((double)k - half) * fs / nfft;
-    plan_free(&plan); free(w); free(a); free(b); free(acc);
+    if (pow2) plan_free(&plan);
+    free(w); free(a); free(b); free(acc); free(tr); free(ti); free(xr); free(xi);
     return 0;
 }
 
-/* ---------- rows next to the hot path ---------- */
+int ora_psd_welch(const double* re, const double* im, uint64_t n, double fs, int nfft,
+                  uint64_t hop, int window_id, double* out_freq, double* out_db) {
+    if (nfft <= 0 || (nfft & (nfft - 1))) return -1;
+    return ora_psd_welch_ex(re, im, n, fs, nfft, hop, window_id, NULL, out_freq, out_db);
+}
 
 /* Java narrowing (short)(double): JLS 5.1.3 double -> int (NaN -> 0, saturate, else truncate
  * toward zero), then int -> short keeps the low 16 bits. */

@@ -26,7 +26,8 @@ extern "C" {
 #endif
 
 /* datatype ids: SigMF core:datatype prefixes (Global.java:67-79) */
-enum { ORA_CF32 = 0, ORA_CI16 = 1, ORA_CU8 = 2, ORA_CI8 = 3, ORA_CF64 = 4 };
+enum { ORA_CF32 = 0, ORA_CI16 = 1, ORA_CU8 = 2, ORA_CI8 = 3, ORA_CF64 = 4,
+       ORA_OTHER = 5 /* no decode branch in the reference (ri16_le ...): zeros / cf32 fall-through, strict_reference only */ };
 /* window ids (periodic / DFT-even definitions) */
 enum { ORA_WIN_RECT = 0, ORA_WIN_HANN = 1, ORA_WIN_HAMMING = 2, ORA_WIN_BLACKMAN = 3, ORA_WIN_BLACKMAN_HARRIS = 4 };
 /* dB modes */
@@ -91,6 +92,26 @@ int ora_downconvert(const uint8_t* buf, uint64_t cap_bytes, int dtype, int big_e
  * nfft must be a power of two and <= n. */
 int ora_psd_welch(const double* re, const double* im, uint64_t n, double fs, int nfft,
                   uint64_t hop, int window_id, double* out_freq, double* out_db);
+
+/* The choices JDSP makes inside Resampler.downConvert / calculatePsdWelch that the reference does not pin
+ * (build.gradle:142, not vendored): filter taps, delay compensation, output length, PSD scaling and detrending.
+ * NULL / all-zero = the self-defined default spec above.  strict_reference reproduces the decode fall-throughs of
+ * ExtractDownConvertService.java:60-67,79-81,93-96 (cf64 read at an 8-byte stride; unknown datatypes read as cf32). */
+typedef struct ora_analysis_cfg {
+    const double* taps; int n_taps;   /* NULL: ora_lowpass_taps(down) */
+    int delay_mode;                   /* 0 causal, 1 same ((L-1)/2 samples compensated), 2 valid (full overlaps only) */
+    int length_mode;                  /* 0 floor(count/down), 1 ceil(count/down) */
+    int psd_scaling;                  /* 0 density 1/(fs sum w^2), 1 spectrum 1/(sum w)^2 */
+    int psd_detrend;                  /* 0 none, 1 constant (per-segment mean removed) */
+    int strict_reference;
+} ora_analysis_cfg;
+uint64_t ora_downconvert_length(uint64_t count, int down, int fast, const ora_analysis_cfg* cfg);
+int ora_downconvert_ex(const uint8_t* buf, uint64_t cap_bytes, int dtype, int big_endian,
+                       uint64_t start_sample, uint64_t count, double freq_off, int down, int fast,
+                       const ora_analysis_cfg* cfg, double* out_re, double* out_im, uint64_t* out_len);
+/* any nfft >= 1 (the reference's short-signal branch: nfft = signal length, AnalysisDialogController.java:304-307) */
+int ora_psd_welch_ex(const double* re, const double* im, uint64_t n, double fs, int nfft,
+                     uint64_t hop, int window_id, const ora_analysis_cfg* cfg, double* out_freq, double* out_db);
 
 /* IqData.getInterleavedBinary (S/data/IqData.java:160-187): format 0 float32, 1 int16, little-endian. */
 int ora_iq_pack(const double* re, const double* im, uint64_t n, int format, uint8_t* out);

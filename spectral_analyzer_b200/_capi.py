@@ -13,6 +13,11 @@ SA_OK = 0
 ERR_NAMES = {1: "INVALID_ARG", 2: "UNSUPPORTED", 3: "OUT_OF_RANGE", 4: "CUDA", 5: "NO_DEVICE", 6: "OOM",
              7: "SMALL_OUTPUT"}
 DTYPE = {"cf32": 0, "ci16": 1, "cu8": 2, "ci8": 3, "cf64": 4}
+DT_OTHER = 5          # datatype without a decode branch in the reference; strict_reference only
+DELAY = {"causal": 0, "same": 1, "valid": 2}
+LENGTH = {"floor": 0, "ceil": 1}
+PSD_SCALING = {"density": 0, "spectrum": 1}
+DETREND = {None: 0, False: 0, "none": 0, "constant": 1}
 WINDOW = {"rect": 0, "hann": 1, "hamming": 2, "blackman": 3, "blackman_harris": 4}
 DB_MAG_1E10, DB_POWER = 0, 1
 OUT_F32_DB, OUT_F64_DB, OUT_RGBA8 = 0, 1, 2
@@ -27,8 +32,14 @@ class SpectrogramParams(C.Structure):
                 ("window", C.c_int32), ("nfft", C.c_uint32), ("db_mode", C.c_int32),
                 ("out_kind", C.c_int32), ("precision", C.c_int32), ("start_sample", C.c_uint64),
                 ("hop", C.c_uint64), ("n_frames", C.c_uint64), ("eof_fill_db", C.c_double),
-                ("colormap", C.c_int32), ("reserved0", C.c_int32), ("sample_rate", C.c_double),
+                ("colormap", C.c_int32), ("strict_reference", C.c_int32), ("sample_rate", C.c_double),
                 ("min_db", C.c_double), ("max_db", C.c_double)]
+
+
+class AnalysisConfig(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("n_taps", C.c_uint32), ("taps", C.POINTER(C.c_double)),
+                ("delay_mode", C.c_int32), ("length_mode", C.c_int32), ("psd_scaling", C.c_int32),
+                ("psd_detrend", C.c_int32), ("psd_precision", C.c_int32), ("strict_reference", C.c_int32)]
 
 
 class Annotation(C.Structure):
@@ -77,6 +88,12 @@ def lib():
     L.sa_compute_magnitudes.argtypes = [vp, vp, u64, u64, u32, i32, i32, dp]
     L.sa_downconvert.argtypes = [vp, vp, u64, i32, i32, u64, u64, dbl, i32, i32, dp, dp, C.POINTER(u64)]
     L.sa_lowpass_taps.argtypes = [i32, dp]
+    L.sa_analysis_config_init.argtypes = [C.POINTER(AnalysisConfig)]
+    L.sa_analysis_config_init.restype = None
+    L.sa_set_analysis_config.argtypes = [vp, C.POINTER(AnalysisConfig)]
+    L.sa_get_analysis_config.argtypes = [vp, C.POINTER(AnalysisConfig)]
+    L.sa_downconvert_length.argtypes = [vp, u64, i32, i32]
+    L.sa_downconvert_length.restype = u64
     L.sa_psd_welch.argtypes = [vp, dp, dp, u64, dbl, u32, u64, i32, dp, dp]
     L.sa_downconvert_psd_batch.argtypes = [vp, vp, u64, i32, i32, dbl, C.POINTER(Annotation), u32, u32, u64, i32,
                                            dp, C.POINTER(u64), dp]
@@ -98,10 +115,14 @@ def check(rc):
         raise EngineError(rc, lib().sa_last_error().decode("utf-8", "replace"))
 
 
-def parse_datatype(datatype):
-    """'ci16_le' -> (dtype id, big_endian) through the library's own rule."""
+def parse_datatype(datatype, strict_reference=False):
+    """'ci16_le' -> (dtype id, big_endian) through the library's own rule.  With strict_reference a datatype
+    without a decode branch ('ri16_le', ...) maps to DT_OTHER instead of raising."""
     d, be = C.c_int32(), C.c_int32()
-    check(lib().sa_parse_datatype(datatype.encode(), C.byref(d), C.byref(be)))
+    rc = lib().sa_parse_datatype(datatype.encode(), C.byref(d), C.byref(be))
+    if rc == 2 and strict_reference:
+        return DT_OTHER, (0 if datatype.endswith("_le") else 1)
+    check(rc)
     return d.value, be.value
 
 

@@ -1,7 +1,8 @@
 // analysis.cu -- annotation-analysis path behind the C-ABI: NCO downconvert + FIR decimate and
 // Welch PSD (kernels in analysis_kernels.cuh).  Replaces ExtractDownConvertService.java:54-117,
 // the batch loop AnnotationController.java:321-360 and the calculatePsdWelch call at
-// AnalysisDialogController.java:308-312.
+// AnalysisDialogController.java:308-312.  Everything JDSP decides inside those calls (not vendored,
+// build.gradle:142) is a field of the engine's analysis profile (sa_analysis_config).
 #include "engine_internal.h"
 #include "analysis_kernels.cuh"
 
@@ -33,36 +34,48 @@ void lowpass_taps(int down, std::vector<double>& h) {
     for (int k = 0; k < nt; k++) h[k] /= sum;
 }
 
-struct WelchKernel { const void* fn; int n, cta, fpc; size_t smem; int p, np, radix[4]; };
+struct WelchKernel { const void* fn; const void* fin; int prec, n, cta, fpc; size_t smem; int p, np, radix[4]; };
 
-template <int N> WelchKernel make_welch() {
-    using G = Geo<float, N>;
-    using PL = Plan<float, N>;
+template <typename T, int N> WelchKernel make_welch(int prec) {
+    using G = Geo<T, N>;
+    using PL = Plan<T, N>;
     WelchKernel k;
-    k.fn = (const void*)&welch_accum_kernel<N>;
+    k.fn = (const void*)&welch_accum_kernel<T, N>;
+    k.fin = (const void*)&welch_finalize_kernel<T>;
+    k.prec = prec;
     k.n = N; k.cta = G::CTA; k.fpc = G::FPC; k.smem = G::SMEM_BYTES + G::TW_BYTES; k.p = G::P; k.np = PL::NP;
     for (int i = 0; i < 4; i++) k.radix[i] = PL::radix(i);
     return k;
 }
 
-const WelchKernel* find_welch(int n) {
-    static const WelchKernel tab[] = { make_welch<64>(), make_welch<128>(), make_welch<256>(), make_welch<512>(),
-                                       make_welch<1024>(), make_welch<2048>(), make_welch<4096>(),
-                                       make_welch<8192>(), make_welch<16384>() };
-    for (const auto& k : tab) if (k.n == n) return &k;
+const WelchKernel* find_welch(int prec, int n) {
+    static const WelchKernel tab[] = {
+        make_welch<float, 64>(1), make_welch<float, 128>(1), make_welch<float, 256>(1), make_welch<float, 512>(1),
+        make_welch<float, 1024>(1), make_welch<float, 2048>(1), make_welch<float, 4096>(1), make_welch<float, 8192>(1),
+        make_welch<float, 16384>(1),
+        make_welch<double, 64>(2), make_welch<double, 128>(2), make_welch<double, 256>(2), make_welch<double, 512>(2),
+        make_welch<double, 1024>(2), make_welch<double, 2048>(2), make_welch<double, 4096>(2), make_welch<double, 8192>(2) };
+    for (const auto& k : tab) if (k.prec == prec && k.n == n) return &k;
     return nullptr;
 }
 
-// which: 0 staged kernel with taps from global memory, 1 staged kernel with taps in the parameter bank, 2 wide
+// which: 0 staged kernel with taps from global memory, 1 staged kernel with taps in the parameter bank,
+// 2 warp-per-output kernel, 3 pipelined staged kernel (taps in the parameter bank)
 template <int DK> const void* dc_kernel_of(int which) {
-    return which == 2 ? (const void*)&downconvert_wide_kernel<DK>
-         : which == 1 ? (const void*)&downconvert_kernel<DK, true> : (const void*)&downconvert_kernel<DK, false>;
+    if (which == 2) return (const void*)&downconvert_wide_kernel<DK>;
+    if (which == 1) return (const void*)&downconvert_kernel<DK, true, false>;
+    if (which == 3) {
+        if constexpr (sizeof(typename DcRaw<DK>::raw_t) <= 8) return (const void*)&downconvert_kernel<DK, true, true>;
+        else return nullptr;
+    }
+    return (const void*)&downconvert_kernel<DK, false, false>;
 }
 const void* dc_kernel(int dk, int which) {
     switch (dk) {
         case DK_CF32: return dc_kernel_of<DK_CF32>(which);
         case DK_CI16: return dc_kernel_of<DK_CI16>(which);
         case DK_C8:   return dc_kernel_of<DK_C8>(which);
+        case DK_CF64_S8: return dc_kernel_of<DK_CF64_S8>(which);
         default:      return dc_kernel_of<DK_CF64>(which);
     }
 }
@@ -74,19 +87,13 @@ size_t dc_smem_bytes(int down, int nb, int fast) {
     return ((stage_phys + 1) & ~(size_t)1) * sizeof(float2) + (fast ? 0 : (size_t)nblk * 8 * sizeof(float2));
 }
 
-struct BatchPlan {
-    std::vector<DcAnn> anns;
-    std::vector<float> taps;            // concatenated per distinct down
-    std::vector<long long> m_out;
-    long long total_out = 0;            // doubles in the decimated-IQ output
-};
-
-int validate_anns(const sa_annotation* anns, uint32_t n_ann, uint64_t n_samples) {
+int validate_anns(const sa_annotation* anns, uint32_t n_ann, uint64_t n_samples, uint64_t extra) {
     if (!anns && n_ann) return set_error(SA_ERR_INVALID_ARG, "annotations is NULL");
     for (uint32_t i = 0; i < n_ann; i++) {
         if (anns[i].down < 1) return set_error(SA_ERR_INVALID_ARG, "annotation %u: down %d < 1", i, anns[i].down);
         if (!std::isfinite(anns[i].freq_off)) return set_error(SA_ERR_INVALID_ARG, "annotation %u: freq_off not finite", i);
-        if (anns[i].start_sample > n_samples || anns[i].count > n_samples - anns[i].start_sample)
+        const uint64_t need = anns[i].count ? anns[i].count + extra : 0;
+        if (anns[i].start_sample > n_samples || need > n_samples - anns[i].start_sample)
             return set_error(SA_ERR_OUT_OF_RANGE, "annotation %u: [%llu, +%llu) exceeds %llu samples", i,
                              (unsigned long long)anns[i].start_sample, (unsigned long long)anns[i].count,
                              (unsigned long long)n_samples);
@@ -98,78 +105,170 @@ int validate_anns(const sa_annotation* anns, uint32_t n_ann, uint64_t n_samples)
 
 namespace sa {
 
-struct WelchJob { const double* re; const double* im; long long n; double fs; };
+// taps in effect for decimation factor `down` (profile taps, or the built-in design)
+static void profile_taps(const AnalysisProfile& pf, int down, std::vector<double>& h) {
+    if (!pf.taps.empty()) h = pf.taps; else lowpass_taps(down, h);
+}
 
-// Welch PSD of FP64 planar rows already on the device; d_out_psd is [jobs][nfft] doubles.
-static int welch_device(Engine* eng, const std::vector<WelchJob>& jobs, uint32_t nfft, uint64_t hop, int window,
-                        double* d_out_psd, cudaStream_t stream) {
-    const WelchKernel* wk = find_welch((int)nfft);
-    if (!wk) return set_error(SA_ERR_UNSUPPORTED, "no Welch kernel for nfft %u (power of two, 64..16384)", nfft);
+// number of outputs
+uint64_t dc_out_len(const AnalysisProfile& pf, uint64_t count, int down, int fast) {
+    const uint64_t L = pf.taps.empty() ? 8ull * (uint64_t)down + 1 : pf.taps.size();
+    if (!fast && pf.delay_mode == SA_DELAY_VALID) return count >= L ? (count - L) / (uint64_t)down + 1 : 0;
+    return pf.length_mode == SA_LEN_CEIL ? (count + (uint64_t)down - 1) / (uint64_t)down : count / (uint64_t)down;
+}
+
+struct WelchJob { const double* re; const double* im; const float2* f32; long long n; double fs; double* d_out; };
+
+// One Welch launch: all signals share the transform length.  Prepared on the host first (so that every plan of a
+// call can be uploaded in ONE copy before the first kernel is launched: a pageable H2D copy in the middle of the
+// launch sequence synchronises the stream and serialises everything behind it), launched later.
+struct WelchLaunch {
+    std::vector<WelchSig> sigs;
+    std::vector<double*> d_out;
+    const WelchKernel* wk = nullptr;
+    uint32_t nfft = 0;
+    uint64_t hop = 0;
+    int window = 0, prec = SA_PREC_F32, nsplit = 1;
+    size_t direct_smem = 0;
+};
+
+static int welch_prepare(Engine* eng, const std::vector<WelchJob>& jobs, uint32_t nfft, uint64_t hop, int window, WelchLaunch& wl) {
+    const AnalysisProfile& pf = eng->profile;
+    wl.prec = pf.psd_precision == SA_PREC_F64 ? SA_PREC_F64 : SA_PREC_F32;
+    const size_t elem = wl.prec == SA_PREC_F64 ? 8 : 4;
+    const bool pow2 = nfft >= 64 && (nfft & (nfft - 1)) == 0;
+    wl.wk = pow2 ? find_welch(wl.prec, (int)nfft) : nullptr;
+    wl.direct_smem = ((size_t)nfft + kDirectTile) * 2 * elem;
+    if (!wl.wk && wl.direct_smem > 200 * 1024)
+        return set_error(SA_ERR_UNSUPPORTED, "psd nfft %u: %s transforms go up to %d points (powers of two) or %d points (any length)",
+                         nfft, wl.prec == SA_PREC_F64 ? "FP64" : "FP32", wl.prec == SA_PREC_F64 ? 8192 : 16384,
+                         (int)(200 * 1024 / (2 * elem)) - kDirectTile);
     const uint32_t n_sig = (uint32_t)jobs.size();
+    if (n_sig > 65535) return set_error(SA_ERR_UNSUPPORTED, "more than 65535 signals in one PSD launch");
+    wl.nfft = nfft; wl.hop = hop; wl.window = window;
     std::vector<double> w;
     host_window(window, (int)nfft, w);
-    double sw2 = 0.0;
-    for (double v : w) sw2 += v * v;
-    std::vector<WelchSig> sigs(n_sig);
+    double sw = 0.0, sw2 = 0.0;
+    for (double v : w) { sw += v; sw2 += v * v; }
+    wl.sigs.resize(n_sig);
+    wl.d_out.resize(n_sig);
     long long max_seg = 0;
     for (uint32_t i = 0; i < n_sig; i++) {
-        WelchSig& s = sigs[i];
-        s.re = jobs[i].re; s.im = jobs[i].im; s.n = jobs[i].n;
+        WelchSig& s = wl.sigs[i];
+        s.re = jobs[i].re; s.im = jobs[i].im; s.f32 = jobs[i].f32; s.n = jobs[i].n;
         s.nseg = s.n >= (long long)nfft ? 1 + (s.n - nfft) / (long long)hop : 0;
-        s.scale = s.nseg > 0 ? 1.0 / ((double)s.nseg * jobs[i].fs * sw2) : 0.0;
+        const double den = pf.psd_scaling == SA_PSD_SPECTRUM ? sw * sw : jobs[i].fs * sw2;
+        s.scale = s.nseg > 0 ? 1.0 / ((double)s.nseg * den) : 0.0;
         max_seg = std::max(max_seg, s.nseg);
+        wl.d_out[i] = jobs[i].d_out;
     }
-    // enough CTAs for about two waves; every CTA walks its share of the segments
-    const long long want = (4LL * eng->num_sms + n_sig - 1) / n_sig;
-    const int nsplit = (int)std::max<long long>(1, std::min<long long>(want, (max_seg + wk->fpc - 1) / wk->fpc));
-    const size_t sig_bytes = ((size_t)n_sig * sizeof(WelchSig) + 255) & ~(size_t)255;
-    const size_t part_bytes = (size_t)n_sig * nsplit * wk->fpc * nfft * sizeof(float);
-    int rc = eng->ensure_scratch(1, sig_bytes + part_bytes);
-    if (rc) return rc;
-    WelchSig* d_sigs = (WelchSig*)eng->scratch[1];
-    cudaError_t e = cudaMemcpyAsync(d_sigs, sigs.data(), sigs.size() * sizeof(WelchSig), cudaMemcpyHostToDevice, stream);
-    if (e != cudaSuccess) return cuda_fail(e, "upload Welch plan");
-    WelchArgs wa;
-    memset(&wa, 0, sizeof(wa));
-    wa.sigs = d_sigs;
-    wa.hop = (long long)hop;
-    SpecKernelInfo ki;
-    memset(&ki, 0, sizeof(ki));
-    ki.prec = SA_PREC_F32; ki.n = wk->n; ki.p = wk->p; ki.np = wk->np;
-    for (int i = 0; i < 4; i++) ki.radix[i] = wk->radix[i];
-    rc = eng->twiddle_table(ki, &wa.twiddle);
-    if (rc) return rc;
-    const void* wtab = nullptr;
-    rc = eng->window_table(window, (int)nfft, SA_PREC_F32, &wtab);
-    if (rc) return rc;
-    wa.window = (const float*)wtab;
-    wa.partial = (float*)((char*)eng->scratch[1] + sig_bytes);
-    wa.nsplit = nsplit;
-    wa.out_db = d_out_psd;
-    int bps = 0;
-    rc = eng->kernel_grid(wk->fn, wk->cta, wk->smem, &bps);
-    if (rc) return rc;
-    void* wargs[] = { &wa };
-    e = cudaLaunchKernel(wk->fn, dim3(nsplit, n_sig), dim3(wk->cta), wargs, wk->smem, stream);
-    if (e != cudaSuccess) return cuda_fail(e, "launch welch_accum_kernel");
-    eng->launches++;
-    int n = (int)nfft, slots = nsplit * wk->fpc;
-    void* fargs[] = { &wa, &n, &slots };
-    e = cudaLaunchKernel((const void*)&welch_finalize_kernel, dim3((n + 255) / 256, n_sig), dim3(256), fargs, 0, stream);
-    if (e != cudaSuccess) return cuda_fail(e, "launch welch_finalize_kernel");
-    eng->launches++;
+    // CTAs per signal: about four segments per frame slot, whatever else is in the launch (the summation order of a
+    // signal then depends only on its own launch's longest signal, not on how many signals share the launch)
+    wl.nsplit = 1;
+    if (wl.wk) wl.nsplit = (int)std::max<long long>(1, std::min<long long>(64, (max_seg + 4LL * wl.wk->fpc - 1) / (4LL * wl.wk->fpc)));
     return SA_OK;
 }
 
-// Runs the downconverter (and optionally the Welch PSD) for a batch on DEVICE samples.
+// d_sigs: the launch's WelchSig array on the device (already uploaded, or NULL: uploaded here from pageable memory).
+// `wsi` selects one of two workspaces (batches alternate between two streams).
+static int welch_launch(Engine* eng, const WelchLaunch& wl, const WelchSig* d_sigs, cudaStream_t stream, int wsi) {
+    const AnalysisProfile& pf = eng->profile;
+    const uint32_t n_sig = (uint32_t)wl.sigs.size(), nfft = wl.nfft;
+    if (n_sig == 0) return SA_OK;
+    const size_t elem = wl.prec == SA_PREC_F64 ? 8 : 4;
+    const WelchKernel* wk = wl.wk;
+    const size_t sig_bytes = d_sigs ? 0 : (((size_t)n_sig * sizeof(WelchSig) + 255) & ~(size_t)255);
+    // consecutive destination rows: the kernels write them in place; otherwise packed rows + one copy per run
+    bool contiguous = wl.d_out[0] != nullptr;
+    for (uint32_t i = 1; i < n_sig && contiguous; i++) contiguous = wl.d_out[i] == wl.d_out[i - 1] + nfft;
+    const size_t out_bytes = contiguous ? 0 : (((size_t)n_sig * nfft * sizeof(double) + 255) & ~(size_t)255);
+    const size_t part_bytes = wk ? (size_t)n_sig * wl.nsplit * wk->fpc * nfft * elem : 0;
+    const int slot = wsi ? 13 : 1;
+    int rc = eng->ensure_scratch(slot, std::max<size_t>(sig_bytes + out_bytes + part_bytes, 256));
+    if (rc) return rc;
+    char* base = (char*)eng->scratch[slot];
+    double* d_rows = (double*)(base + sig_bytes);
+    cudaError_t e = cudaSuccess;
+    if (!d_sigs) {
+        // pageable source: the driver has staged the bytes when the call returns
+        e = cudaMemcpyAsync(base, wl.sigs.data(), wl.sigs.size() * sizeof(WelchSig), cudaMemcpyHostToDevice, stream);
+        if (e != cudaSuccess) return cuda_fail(e, "upload Welch plan");
+        d_sigs = (const WelchSig*)base;
+    }
+    WelchArgs wa;
+    memset(&wa, 0, sizeof(wa));
+    wa.sigs = d_sigs;
+    wa.hop = (long long)wl.hop;
+    wa.detrend = pf.psd_detrend == SA_DETREND_CONSTANT ? 1 : 0;
+    wa.window_id = wl.window;
+    wa.out_db = contiguous ? wl.d_out[0] : d_rows;
+    if (wk) {
+        SpecKernelInfo ki;
+        memset(&ki, 0, sizeof(ki));
+        ki.prec = wl.prec; ki.n = wk->n; ki.p = wk->p; ki.np = wk->np;
+        for (int i = 0; i < 4; i++) ki.radix[i] = wk->radix[i];
+        rc = eng->twiddle_table(ki, &wa.twiddle);
+        if (rc) return rc;
+        rc = eng->window_table(wl.window, (int)nfft, wl.prec, &wa.window);
+        if (rc) return rc;
+        wa.partial = base + sig_bytes + out_bytes;
+        wa.nsplit = wl.nsplit;
+        int bps = 0;
+        rc = eng->kernel_grid(wk->fn, wk->cta, wk->smem, &bps);
+        if (rc) return rc;
+        void* wargs[] = { &wa };
+        e = cudaLaunchKernel(wk->fn, dim3(wl.nsplit, n_sig), dim3(wk->cta), wargs, wk->smem, stream);
+        if (e != cudaSuccess) return cuda_fail(e, "launch welch_accum_kernel");
+        eng->launches++;
+        int n = (int)nfft, slots = wl.nsplit * wk->fpc;
+        void* fargs[] = { &wa, &n, &slots };
+        e = cudaLaunchKernel(wk->fin, dim3((n + 255) / 256, n_sig), dim3(256), fargs, 0, stream);
+        if (e != cudaSuccess) return cuda_fail(e, "launch welch_finalize_kernel");
+        eng->launches++;
+    } else {
+        const void* fn = wl.prec == SA_PREC_F64 ? (const void*)&psd_direct_kernel<double> : (const void*)&psd_direct_kernel<float>;
+        int bps = 0;
+        rc = eng->kernel_grid(fn, 256, 200 * 1024, &bps);                    // raises the dynamic shared memory limit once
+        if (rc) return rc;
+        int n = (int)nfft;
+        void* dargs[] = { &wa, &n };
+        e = cudaLaunchKernel(fn, dim3((nfft + 255) / 256, n_sig), dim3(256), dargs, wl.direct_smem, stream);
+        if (e != cudaSuccess) return cuda_fail(e, "launch psd_direct_kernel");
+        eng->launches++;
+    }
+    // rows -> their destinations (contiguous runs collapse into one copy)
+    for (uint32_t i = 0; i < n_sig && e == cudaSuccess && !contiguous;) {
+        uint32_t j = i + 1;
+        while (j < n_sig && wl.d_out[j] == wl.d_out[j - 1] + nfft) j++;
+        if (wl.d_out[i])
+            e = cudaMemcpyAsync(wl.d_out[i], d_rows + (size_t)i * nfft, (size_t)(j - i) * nfft * sizeof(double),
+                                cudaMemcpyDeviceToDevice, stream);
+        i = j;
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "PSD rows");
+    return SA_OK;
+}
+
+// Runs the downconverter (and optionally the Welch PSD) for a batch on DEVICE samples.  d_out_iq == NULL: only the
+// PSD rows are produced -- the decimated IQ then lives only in the FP32 scratch rows, which are reused batch after
+// batch and stay in L2.  Batches of annotations alternate between the caller's stream and a helper stream so that
+// the (issue-bound) Welch kernels of one batch overlap the (memory-bound) downconverter of the next.
 static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, int dtype, int big_endian,
                             double sample_rate, const sa_annotation* anns, uint32_t n_ann, uint32_t psd_nfft,
                             uint64_t psd_hop, int psd_window, double* d_out_iq, const uint64_t* iq_offsets,
                             double* d_out_psd, cudaStream_t stream) {
-    const int dk = dtype_kind(dtype);
+    const AnalysisProfile& pf = eng->profile;
+    if (dtype == SA_DT_OTHER) dtype = SA_CF32;                                    // strict_reference: ExtractDownConvertService.java:93-96
+    int dk = dtype_kind(dtype);
+    if (pf.strict_reference && dtype == SA_CF64) dk = DK_CF64_S8;                 // :60-67,79-81
+    const bool raw_wide = (dk == DK_CF64 || dk == DK_CF64_S8);
+    static const char* pipe_env = getenv("SA_DC_PIPE");
+    const bool pipe_ok = (pipe_env ? atoi(pipe_env) != 0 : true) && !raw_wide;
     std::vector<DcAnn> plan(n_ann);
     std::vector<float> taps;
     std::map<int, int> taps_off;
+    std::vector<char> piped(n_ann, 0);
+    uint64_t scr_total = 0;
     for (uint32_t i = 0; i < n_ann; i++) {
         DcAnn& a = plan[i];
         const int D = anns[i].down;
@@ -177,45 +276,156 @@ static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, i
         a.count = (long long)anns[i].count;
         const double fr = anns[i].freq_off - std::floor(anns[i].freq_off);    // frac in [0,1)
         a.phase_step = (unsigned long long)std::ldexp((long double)fr, 64);   // exact 64-bit phase increment
-        a.m_out = a.count / D;
-        a.out_off = (long long)iq_offsets[i];
-        a.down = D;
         a.fast = anns[i].fast ? 1 : 0;
+        a.m_out = (long long)dc_out_len(pf, anns[i].count, D, a.fast);
+        a.out_off = iq_offsets ? (long long)iq_offsets[i] : 0;
+        a.scr_off = 0;
+        a.down = D;
+        const int L = pf.taps.empty() ? 8 * D + 1 : (int)pf.taps.size();
+        a.n_taps = L;
+        a.in_off = a.fast ? 0 : (pf.delay_mode == SA_DELAY_SAME ? (L - 1) / 2 : pf.delay_mode == SA_DELAY_VALID ? L - 1 : 0);
         if (!taps_off.count(D)) {
-            // block layout: [pad so that ht is 16-byte aligned][h[0..8D]][ht[r*8+p] = h[D*p+r]]
-            while ((taps.size() + 8 * (size_t)D + 1) % 4) taps.push_back(0.f);
-            taps_off[D] = (int)taps.size();
+            // block layout: [pad so that ht is 16-byte aligned][h[0..max(8D, L-1)] zero padded][ht[r*8+p] = h[D*p+r]]
             std::vector<double> h;
-            lowpass_taps(D, h);
+            profile_taps(pf, D, h);
+            const size_t nat = std::max<size_t>(h.size(), 8 * (size_t)D + 1);
+            h.resize(nat, 0.0);
+            while ((taps.size() + nat) % 4) taps.push_back(0.f);
+            taps_off[D] = (int)taps.size();
             for (double v : h) taps.push_back((float)v);
-            for (int r = 0; r < D; r++) for (int p = 0; p < 8; p++) taps.push_back((float)h[D * p + r]);
+            for (int r = 0; r < D; r++) for (int p = 0; p < 8; p++) taps.push_back((float)h[(size_t)D * p + r]);
         }
         a.taps_off = taps_off[D];
         a.qmagic = D > 1 ? (unsigned)(((1ull << 32) + (unsigned long long)D - 1) / (unsigned long long)D) : 0u;
-        const bool wide = a.fast ? (D > kDcStage / 8) : (D > kDcMaxDown);
+        const bool wide = (a.fast ? (D > kDcStage / 8) : (D > kDcMaxDown)) || (!a.fast && L > 8 * D + 1);
         if (wide) {
             a.nb = 0;                       // marks the warp-per-output kernel
+        } else if (pipe_ok && !a.fast && D <= 32) {
+            // pipelined variant: the whole tile is one register batch (<= 17 x 256 staged samples)
+            const int nblk = std::max(8, std::min(kDcThreads, (kDcPipeLoads * kDcThreads - 1) / D));
+            a.nb = nblk - 7;
+            piped[i] = 1;
         } else {
             const int nblk = std::max(8, std::min(kDcThreads, kDcStage / D));
             a.nb = a.fast ? nblk : nblk - 7;
         }
     }
-    // launches are grouped by (kernel, fast, down): the device list is the plan sorted by that key
-    std::vector<uint32_t> order(n_ann);
-    for (uint32_t i = 0; i < n_ann; i++) order[i] = i;
-    auto key = [&](uint32_t i) { return std::make_tuple(plan[i].nb == 0 ? 1 : 0, plan[i].fast, plan[i].down); };
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return key(x) < key(y); });
-    std::vector<DcAnn> sorted(n_ann);
-    for (uint32_t i = 0; i < n_ann; i++) sorted[i] = plan[order[i]];
+    // ---- batches: annotations in caller order, cut where the FP32 rows of a batch reach the batch size
+    const bool want_psd = d_out_psd != nullptr;
+    static const char* batch_env = getenv("SA_DC_BATCH_MB");
+    const uint64_t batch_mb = batch_env && atoi(batch_env) > 0 ? (uint64_t)atoi(batch_env) : 128;
+    const uint64_t scr_cap_elems = (batch_mb << 20) / sizeof(float2);
+    std::vector<std::pair<uint32_t, uint32_t>> batches;
+    if (want_psd) {
+        uint32_t b0 = 0;
+        uint64_t acc = 0;
+        for (uint32_t i = 0; i < n_ann; i++) {
+            if (i > b0 && acc + (uint64_t)plan[i].m_out > scr_cap_elems) { batches.push_back({b0, i}); b0 = i; acc = 0; }
+            plan[i].scr_off = (long long)acc;
+            acc += (uint64_t)plan[i].m_out;
+            scr_total = std::max(scr_total, acc);
+        }
+        batches.push_back({b0, n_ann});
+    } else {
+        batches.push_back({0, n_ann});
+    }
+    const bool dual = want_psd && batches.size() > 1;
+    int rc = SA_OK;
+    if (want_psd) {
+        rc = eng->ensure_scratch(12, 2 * std::max<uint64_t>(scr_total, 1) * sizeof(float2));
+        if (rc) return rc;
+    }
+    // annotation plan (device): batch by batch, inside a batch sorted by (kernel, fast, down) so that launches group
+    std::vector<DcAnn> sorted;
+    sorted.reserve(n_ann);
+    std::vector<uint32_t> order;
+    order.reserve(n_ann);
+    auto key = [&](uint32_t i) { return std::make_tuple(plan[i].nb == 0 ? 2 : (piped[i] ? 0 : 1), plan[i].fast, plan[i].down); };
+    for (auto& b : batches) {
+        std::vector<uint32_t> o;
+        for (uint32_t i = b.first; i < b.second; i++) o.push_back(i);
+        std::stable_sort(o.begin(), o.end(), [&](uint32_t x, uint32_t y) { return key(x) < key(y); });
+        for (uint32_t i : o) { order.push_back(i); sorted.push_back(plan[i]); }
+    }
+    // Welch launches of every batch, prepared before anything is launched.  Transform length min(psd_nfft, M) per
+    // annotation (AnalysisDialogController.java:303-307); rows shorter than psd_nfft are padded with NaN.
+    std::vector<std::vector<WelchLaunch>> welch(batches.size());
+    std::vector<std::vector<uint32_t>> short_rows(batches.size());
+    size_t n_sigs_total = 0;
+    if (want_psd) {
+        for (size_t bi = 0; bi < batches.size(); bi++) {
+            const int par = dual ? (int)(bi & 1) : 0;
+            const float2* scr = (const float2*)eng->scratch[12] + (size_t)par * scr_total;
+            std::map<uint32_t, std::vector<WelchJob>> by_n;
+            for (uint32_t i = batches[bi].first; i < batches[bi].second; i++) {
+                WelchJob j;
+                j.re = nullptr; j.im = nullptr;
+                j.f32 = scr + plan[i].scr_off;
+                j.n = plan[i].m_out;
+                j.fs = sample_rate / (double)plan[i].down;
+                j.d_out = d_out_psd + (size_t)i * psd_nfft;
+                const uint32_t nf = (uint32_t)std::min<long long>((long long)psd_nfft, plan[i].m_out);
+                if (nf < psd_nfft) short_rows[bi].push_back(i);
+                if (nf > 0) by_n[nf].push_back(j);
+            }
+            for (auto& kv : by_n) {
+                const uint64_t hop = kv.first == psd_nfft ? psd_hop : std::max<uint64_t>(1, kv.first / 4);
+                welch[bi].emplace_back();
+                rc = welch_prepare(eng, kv.second, kv.first, hop, psd_window, welch[bi].back());
+                if (rc) return rc;
+                n_sigs_total += kv.second.size();
+            }
+        }
+    }
+    // ONE upload of everything the kernels read: annotation plan, taps, Welch plans -- from a pinned buffer, so that
+    // the copy is asynchronous and nothing later in the launch sequence has to touch pageable memory
     const size_t ann_bytes = (sorted.size() * sizeof(DcAnn) + 255) & ~(size_t)255;
     const size_t taps_bytes = (taps.size() * sizeof(float) + 255) & ~(size_t)255;
-    int rc = eng->ensure_scratch(0, ann_bytes + taps_bytes);
+    const size_t sig_bytes = (n_sigs_total * sizeof(WelchSig) + 255) & ~(size_t)255;
+    const size_t plan_bytes = ann_bytes + taps_bytes + sig_bytes;
+    rc = eng->ensure_scratch(0, plan_bytes);
     if (rc) return rc;
+    cudaError_t e = cudaSuccess;
+    if (eng->h_plan_cap < plan_bytes) {
+        if (eng->h_plan) { cudaEventSynchronize(eng->plan_ev); cudaFreeHost(eng->h_plan); }
+        eng->h_plan = nullptr; eng->h_plan_cap = 0;
+        e = cudaHostAlloc(&eng->h_plan, plan_bytes + (plan_bytes >> 1), cudaHostAllocPortable);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaHostAlloc(plan)");
+        eng->h_plan_cap = plan_bytes + (plan_bytes >> 1);
+    }
+    if (!eng->plan_ev) {
+        e = cudaEventCreateWithFlags(&eng->plan_ev, cudaEventDisableTiming);
+        if (e != cudaSuccess) return cuda_fail(e, "plan event");
+    } else {
+        e = cudaEventSynchronize(eng->plan_ev);                 // the previous call's upload has left the buffer
+        if (e != cudaSuccess) return cuda_fail(e, "plan event wait");
+    }
+    char* hp = (char*)eng->h_plan;
+    memcpy(hp, sorted.data(), sorted.size() * sizeof(DcAnn));
+    memcpy(hp + ann_bytes, taps.data(), taps.size() * sizeof(float));
+    {
+        size_t off = ann_bytes + taps_bytes;
+        for (auto& wb : welch) for (auto& wl : wb) { memcpy(hp + off, wl.sigs.data(), wl.sigs.size() * sizeof(WelchSig)); off += wl.sigs.size() * sizeof(WelchSig); }
+    }
     DcAnn* d_anns = (DcAnn*)eng->scratch[0];
     float* d_taps = (float*)((char*)eng->scratch[0] + ann_bytes);
-    cudaError_t e = cudaMemcpyAsync(d_anns, sorted.data(), sorted.size() * sizeof(DcAnn), cudaMemcpyHostToDevice, stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice, stream);
+    const WelchSig* d_sigs = (const WelchSig*)((char*)eng->scratch[0] + ann_bytes + taps_bytes);
+    e = cudaMemcpyAsync(eng->scratch[0], hp, plan_bytes, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaEventRecord(eng->plan_ev, stream);
     if (e != cudaSuccess) return cuda_fail(e, "upload annotation plan");
+
+    cudaStream_t st[2] = { stream, stream };
+    if (dual) {
+        if (!eng->dc_aux) {
+            e = cudaStreamCreateWithFlags(&eng->dc_aux, cudaStreamNonBlocking);
+            for (int j = 0; j < 2 && e == cudaSuccess; j++) e = cudaEventCreateWithFlags(&eng->dc_ev[j], cudaEventDisableTiming);
+            if (e != cudaSuccess) return cuda_fail(e, "analysis helper stream");
+        }
+        st[1] = eng->dc_aux;
+        e = cudaEventRecord(eng->dc_ev[0], stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(eng->dc_aux, eng->dc_ev[0], 0);
+        if (e != cudaSuccess) return cuda_fail(e, "analysis fork");
+    }
 
     DcArgs da;
     memset(&da, 0, sizeof(da));
@@ -227,62 +437,99 @@ static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, i
     DcTapParams tp;                      // copied into the launch by cudaLaunchKernel (kernel-parameter bank)
     tp.h_last = 0.f; tp.down = 0;
     void* args[] = { &da, &tp };
-    for (uint32_t g0 = 0; g0 < n_ann;) {
-        uint32_t g1 = g0 + 1;
-        while (g1 < n_ann && key(order[g1]) == key(order[g0])) g1++;
-        const DcAnn& first = sorted[g0];
-        da.ann_base = (int)g0;
-        if (first.nb == 0) {              // warp-per-output kernel: all wide annotations in one launch
-            g1 = n_ann;
-            long long tiles = 0;
-            for (uint32_t i = g0; i < g1; i++) tiles = std::max<long long>(tiles, (sorted[i].m_out + 7) / 8);
-            if (tiles > 0) {
-                e = cudaLaunchKernel(dc_kernel(dk, 2), dim3((unsigned)tiles, g1 - g0), dim3(256), args, 0, stream);
-                if (e != cudaSuccess) return cuda_fail(e, "launch downconvert_wide_kernel");
-                eng->launches++;
+    uint32_t pos = 0;                    // position in `sorted`
+    size_t sig_pos = 0;                  // position in the uploaded WelchSig array
+    for (size_t bi = 0; bi < batches.size(); bi++) {
+        const int par = dual ? (int)(bi & 1) : 0;
+        cudaStream_t s = st[par];
+        const uint32_t bn = batches[bi].second - batches[bi].first;
+        da.scratch = want_psd ? (float2*)eng->scratch[12] + (size_t)par * scr_total : nullptr;
+        for (uint32_t g0 = pos; g0 < pos + bn;) {
+            uint32_t g1 = g0 + 1;
+            while (g1 < pos + bn && key(order[g1]) == key(order[g0])) g1++;
+            const DcAnn& first = sorted[g0];
+            da.ann_base = (int)g0;
+            da.tiles_per_cta = 1;
+            if (first.nb == 0) {              // warp-per-output kernel
+                long long tiles = 0;
+                for (uint32_t i = g0; i < g1; i++) tiles = std::max<long long>(tiles, (sorted[i].m_out + 7) / 8);
+                if (tiles > 0) {
+                    e = cudaLaunchKernel(dc_kernel(dk, 2), dim3((unsigned)tiles, g1 - g0), dim3(256), args, 0, s);
+                    if (e != cudaSuccess) return cuda_fail(e, "launch downconvert_wide_kernel");
+                    eng->launches++;
+                }
+            } else {
+                long long tiles = 0;
+                for (uint32_t i = g0; i < g1; i++) tiles = std::max<long long>(tiles, (sorted[i].m_out + first.nb - 1) / first.nb);
+                const int D = first.down;
+                const bool pipe = piped[order[g0]] != 0;
+                const bool ptaps = !first.fast && D <= kDcParamMaxDown;
+                if (ptaps) {
+                    const float* h = taps.data() + first.taps_off;
+                    tp.h_last = h[8 * D];
+                    tp.down = D;
+                    memcpy(tp.ht, h + (std::max<size_t>((size_t)first.n_taps, 8 * (size_t)D + 1)), sizeof(float) * 8 * (size_t)D);
+                }
+                const size_t smem = dc_smem_bytes(D, first.nb, first.fast);
+                const void* fn = dc_kernel(dk, pipe ? 3 : (ptaps ? 1 : 0));
+                if (pipe) da.tiles_per_cta = kDcPipeTiles;
+                const long long ctas = (tiles + da.tiles_per_cta - 1) / da.tiles_per_cta;
+                if (ctas > 0) {
+                    size_t& have = eng->dc_smem_set[fn];
+                    if (have < smem) {            // raise the kernel's dynamic shared memory limit only when it grows
+                        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                        if (e != cudaSuccess) return cuda_fail(e, "downconvert smem attribute");
+                        have = smem;
+                    }
+                    e = cudaLaunchKernel(fn, dim3((unsigned)ctas, g1 - g0), dim3(kDcThreads), args, smem, s);
+                    if (e != cudaSuccess) return cuda_fail(e, "launch downconvert_kernel");
+                    eng->launches++;
+                }
             }
-        } else {
-            long long tiles = 0;
-            for (uint32_t i = g0; i < g1; i++) tiles = std::max<long long>(tiles, (sorted[i].m_out + first.nb - 1) / first.nb);
-            const int D = first.down;
-            const bool ptaps = !first.fast && D <= kDcParamMaxDown;
-            if (ptaps) {
-                const float* h = taps.data() + first.taps_off;
-                tp.h_last = h[8 * D];
-                tp.down = D;
-                memcpy(tp.ht, h + 8 * D + 1, sizeof(float) * 8 * (size_t)D);
+            g0 = g1;
+        }
+        pos += bn;
+        if (want_psd) {
+            // NaN padding first (the short spectra are written over the row start)
+            for (uint32_t i : short_rows[bi]) {
+                e = cudaMemsetAsync(d_out_psd + (size_t)i * psd_nfft, 0xFF, (size_t)psd_nfft * sizeof(double), s);   // 0xFF..FF = NaN
+                if (e != cudaSuccess) return cuda_fail(e, "PSD row padding");
             }
-            const size_t smem = dc_smem_bytes(D, first.nb, first.fast);
-            const void* fn = dc_kernel(dk, ptaps ? 1 : 0);
-            if (tiles > 0) {
-                e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                if (e != cudaSuccess) return cuda_fail(e, "downconvert smem attribute");
-                e = cudaLaunchKernel(fn, dim3((unsigned)tiles, g1 - g0), dim3(kDcThreads), args, smem, stream);
-                if (e != cudaSuccess) return cuda_fail(e, "launch downconvert_kernel");
-                eng->launches++;
+            for (auto& wl : welch[bi]) {
+                rc = welch_launch(eng, wl, d_sigs + sig_pos, s, par);
+                if (rc) return rc;
+                sig_pos += wl.sigs.size();
             }
         }
-        g0 = g1;
     }
-    if (!d_out_psd) return SA_OK;
-    std::vector<WelchJob> jobs(n_ann);
-    for (uint32_t i = 0; i < n_ann; i++) {
-        jobs[i].re = d_out_iq + plan[i].out_off;
-        jobs[i].im = jobs[i].re + plan[i].m_out;
-        jobs[i].n = plan[i].m_out;
-        jobs[i].fs = sample_rate / (double)plan[i].down;
+    if (dual) {
+        e = cudaEventRecord(eng->dc_ev[1], eng->dc_aux);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, eng->dc_ev[1], 0);
+        if (e != cudaSuccess) return cuda_fail(e, "analysis join");
     }
-    return welch_device(eng, jobs, psd_nfft, psd_hop, psd_window, d_out_psd, stream);
+    return SA_OK;
 }
 
 }  // namespace sa
 
 
 static int check_psd(uint32_t nfft, uint64_t* hop, int32_t window) {
-    if (nfft == 0 || (nfft & (nfft - 1))) return set_error(SA_ERR_INVALID_ARG, "psd nfft %u is not a power of two", nfft);
-    if (nfft < 64 || nfft > 16384) return set_error(SA_ERR_UNSUPPORTED, "psd nfft %u outside 64..16384", nfft);
-    if (*hop == 0) *hop = nfft / 4;           // 75 % overlap
+    if (nfft == 0) return set_error(SA_ERR_INVALID_ARG, "psd nfft is 0");
+    if (*hop == 0) *hop = std::max<uint32_t>(1, nfft / 4);           // 75 % overlap
     if (window < SA_WIN_RECT || window > SA_WIN_BLACKMAN_HARRIS) return set_error(SA_ERR_INVALID_ARG, "unknown window %d", window);
+    return SA_OK;
+}
+
+// dtype as the downconverter sees it: with strict_reference a datatype without a decode branch is read as cf32
+// (ExtractDownConvertService.java:93-96) and all non-integer types use an 8-byte stride (:60-67)
+static int dc_dtype(const sa_engine* engine, int32_t dtype, uint64_t* bps) {
+    if (dtype == SA_DT_OTHER || (dtype == SA_CF64 && engine->profile.strict_reference)) {
+        if (!engine->profile.strict_reference) return set_error(SA_ERR_UNSUPPORTED, "datatype without a decode branch (strict_reference is off)");
+        *bps = 8;
+        return SA_OK;
+    }
+    *bps = (uint64_t)sa_bytes_per_iq(dtype);
+    if (!*bps) return set_error(SA_ERR_INVALID_ARG, "unknown dtype %d", dtype);
     return SA_OK;
 }
 
@@ -296,18 +543,75 @@ int32_t sa_lowpass_taps(int32_t down, double* taps) {
     return SA_OK;
 }
 
+void sa_analysis_config_init(sa_analysis_config* c) {
+    if (!c) return;
+    memset(c, 0, sizeof(*c));
+    c->struct_size = sizeof(*c);
+    c->delay_mode = SA_DELAY_CAUSAL;
+    c->length_mode = SA_LEN_FLOOR;
+    c->psd_scaling = SA_PSD_DENSITY;
+    c->psd_detrend = SA_DETREND_NONE;
+    c->psd_precision = SA_PREC_F32;
+}
+
+int32_t sa_set_analysis_config(sa_engine* engine, const sa_analysis_config* c) {
+    ENGINE_ENTER(engine);
+    AnalysisProfile pf;
+    if (c) {
+        if (c->struct_size != sizeof(*c)) return set_error(SA_ERR_INVALID_ARG, "config.struct_size %u != %zu", c->struct_size, sizeof(*c));
+        if (c->delay_mode < SA_DELAY_CAUSAL || c->delay_mode > SA_DELAY_VALID) return set_error(SA_ERR_INVALID_ARG, "unknown delay_mode %d", c->delay_mode);
+        if (c->length_mode != SA_LEN_FLOOR && c->length_mode != SA_LEN_CEIL) return set_error(SA_ERR_INVALID_ARG, "unknown length_mode %d", c->length_mode);
+        if (c->psd_scaling != SA_PSD_DENSITY && c->psd_scaling != SA_PSD_SPECTRUM) return set_error(SA_ERR_INVALID_ARG, "unknown psd_scaling %d", c->psd_scaling);
+        if (c->psd_detrend != SA_DETREND_NONE && c->psd_detrend != SA_DETREND_CONSTANT) return set_error(SA_ERR_INVALID_ARG, "unknown psd_detrend %d", c->psd_detrend);
+        if (c->psd_precision != SA_PREC_AUTO && c->psd_precision != SA_PREC_F32 && c->psd_precision != SA_PREC_F64)
+            return set_error(SA_ERR_INVALID_ARG, "unknown psd_precision %d", c->psd_precision);
+        if ((c->taps == nullptr) != (c->n_taps == 0)) return set_error(SA_ERR_INVALID_ARG, "taps / n_taps disagree");
+        if (c->n_taps > (1u << 20)) return set_error(SA_ERR_UNSUPPORTED, "more than 2^20 taps");
+        for (uint32_t i = 0; i < c->n_taps; i++)
+            if (!std::isfinite(c->taps[i])) return set_error(SA_ERR_INVALID_ARG, "tap %u is not finite", i);
+        if (c->taps) pf.taps.assign(c->taps, c->taps + c->n_taps);
+        pf.delay_mode = c->delay_mode; pf.length_mode = c->length_mode;
+        pf.psd_scaling = c->psd_scaling; pf.psd_detrend = c->psd_detrend;
+        pf.psd_precision = c->psd_precision == SA_PREC_F64 ? SA_PREC_F64 : SA_PREC_F32;
+        pf.strict_reference = c->strict_reference ? 1 : 0;
+    }
+    engine->profile = pf;
+    return SA_OK;
+}
+
+int32_t sa_get_analysis_config(sa_engine* engine, sa_analysis_config* out) {
+    ENGINE_ENTER(engine);
+    if (!out) return set_error(SA_ERR_INVALID_ARG, "out is NULL");
+    const AnalysisProfile& pf = engine->profile;
+    sa_analysis_config_init(out);
+    out->taps = pf.taps.empty() ? nullptr : pf.taps.data();       // engine-owned, valid until the next sa_set_analysis_config
+    out->n_taps = (uint32_t)pf.taps.size();
+    out->delay_mode = pf.delay_mode; out->length_mode = pf.length_mode;
+    out->psd_scaling = pf.psd_scaling; out->psd_detrend = pf.psd_detrend;
+    out->psd_precision = pf.psd_precision; out->strict_reference = pf.strict_reference;
+    return SA_OK;
+}
+
+uint64_t sa_downconvert_length(sa_engine* engine, uint64_t count, int32_t down, int32_t fast) {
+    if (!engine || down < 1) return 0;
+    std::lock_guard<std::mutex> lock_(engine->mu);
+    return dc_out_len(engine->profile, count, down, fast);
+}
+
 int32_t sa_downconvert_psd_batch_device(sa_engine* engine, const void* d_iq, uint64_t iq_bytes, int32_t dtype,
                                         int32_t big_endian, double sample_rate, const sa_annotation* anns,
                                         uint32_t n_ann, uint32_t psd_nfft, uint64_t psd_hop, int32_t psd_window,
                                         double* d_out_iq, const uint64_t* iq_offsets, double* d_out_psd_db,
                                         void* cuda_stream) {
     ENGINE_ENTER(engine);
-    const uint64_t bps = (uint64_t)sa_bytes_per_iq(dtype);
-    if (!bps) return set_error(SA_ERR_INVALID_ARG, "unknown dtype %d", dtype);
+    uint64_t bps = 0;
+    int rc = dc_dtype(engine, dtype, &bps);
+    if (rc) return rc;
     if (n_ann == 0) return SA_OK;
-    if (!d_out_iq || !iq_offsets) return set_error(SA_ERR_INVALID_ARG, "d_out_iq / iq_offsets is NULL (the PSD reads the decimated rows)");
+    if (!d_out_iq && !d_out_psd_db) return set_error(SA_ERR_INVALID_ARG, "both outputs are NULL");
+    if (d_out_iq && !iq_offsets) return set_error(SA_ERR_INVALID_ARG, "iq_offsets is NULL");
     if ((uintptr_t)d_iq % bps) return set_error(SA_ERR_INVALID_ARG, "d_iq must be aligned to %llu bytes", (unsigned long long)bps);
-    int rc = validate_anns(anns, n_ann, iq_bytes / bps);
+    rc = validate_anns(anns, n_ann, iq_bytes / bps, (dtype == SA_CF64 && engine->profile.strict_reference) ? 1 : 0);
     if (rc) return rc;
     if (d_out_psd_db) { rc = check_psd(psd_nfft, &psd_hop, psd_window); if (rc) return rc; }
     return run_batch_device(engine, d_iq, iq_bytes / bps, dtype, big_endian, sample_rate, anns, n_ann, psd_nfft, psd_hop,
@@ -319,38 +623,40 @@ int32_t sa_downconvert_psd_batch(sa_engine* engine, const void* iq, uint64_t iq_
                                  uint64_t psd_hop, int32_t psd_window, double* out_iq, const uint64_t* iq_offsets,
                                  double* out_psd_db) {
     ENGINE_ENTER(engine);
-    const uint64_t bps = (uint64_t)sa_bytes_per_iq(dtype);
-    if (!bps) return set_error(SA_ERR_INVALID_ARG, "unknown dtype %d", dtype);
+    uint64_t bps = 0;
+    int rc = dc_dtype(engine, dtype, &bps);
+    if (rc) return rc;
     if (n_ann == 0) return SA_OK;
     if (!iq) return set_error(SA_ERR_INVALID_ARG, "iq is NULL");
     if (out_iq && !iq_offsets) return set_error(SA_ERR_INVALID_ARG, "iq_offsets is NULL");
-    int rc = validate_anns(anns, n_ann, iq_bytes / bps);
+    const uint64_t extra = (dtype == SA_CF64 && engine->profile.strict_reference) ? 1 : 0;   // the stride bug reads one double past the span
+    rc = validate_anns(anns, n_ann, iq_bytes / bps, extra);
     if (rc) return rc;
     if (out_psd_db) { rc = check_psd(psd_nfft, &psd_hop, psd_window); if (rc) return rc; }
 
     // Only the annotated spans cross PCIe: each annotation's samples are copied into a packed
-    // device buffer and the plan is rebased onto it.
+    // device buffer (16-byte aligned spans) and the plan is rebased onto it.
     Slot& s = engine->slots[0];
     std::vector<sa_annotation> local(anns, anns + n_ann);
     std::vector<uint64_t> dev_off(n_ann);
+    const uint64_t align = 16 / std::min<uint64_t>(bps, 16);                       // samples per 16 bytes
     uint64_t in_samples = 0, out_doubles = 0;
     for (uint32_t i = 0; i < n_ann; i++) {
         local[i].start_sample = in_samples;
-        in_samples += anns[i].count;
+        in_samples += (anns[i].count + extra + align - 1) / align * align;
         dev_off[i] = out_doubles;
-        out_doubles += 2 * (anns[i].count / (uint64_t)anns[i].down);
+        out_doubles += 2 * dc_out_len(engine->profile, anns[i].count, anns[i].down, anns[i].fast);
     }
     const size_t psd_bytes = out_psd_db ? (size_t)n_ann * psd_nfft * sizeof(double) : 0;
-    rc = engine->ensure_slot(s, std::max<size_t>(in_samples * bps, 16), std::max<size_t>(out_doubles * 8 + psd_bytes, 16));
+    const size_t iq_out_bytes = out_iq ? (size_t)out_doubles * 8 : 0;
+    rc = engine->ensure_slot(s, std::max<size_t>(in_samples * bps, 16), std::max<size_t>(iq_out_bytes + psd_bytes, 16));
     if (rc) return rc;
     cudaError_t e = cudaSuccess;
-    uint64_t pos = 0;
     if (host_ptr_is_pinned(iq)) {
         for (uint32_t i = 0; i < n_ann && e == cudaSuccess; i++) {
             if (anns[i].count)
-                e = cudaMemcpyAsync((char*)s.d_in + pos * bps, (const char*)iq + anns[i].start_sample * bps,
-                                    anns[i].count * bps, cudaMemcpyHostToDevice, s.stream);
-            pos += anns[i].count;
+                e = cudaMemcpyAsync((char*)s.d_in + local[i].start_sample * bps, (const char*)iq + anns[i].start_sample * bps,
+                                    (anns[i].count + extra) * bps, cudaMemcpyHostToDevice, s.stream);
         }
     } else {
         // pageable capture (mmapped file): pieces of <= 32 MiB alternate between the pinned staging buffers of
@@ -369,29 +675,29 @@ int32_t sa_downconvert_psd_batch(sa_engine* engine, const void* iq, uint64_t iq_
         }
         int k = 0;
         for (uint32_t i = 0; i < n_ann && e == cudaSuccess; i++) {
-            const uint64_t total = anns[i].count * bps;
+            const uint64_t total = (anns[i].count ? anns[i].count + extra : 0) * bps;
             for (uint64_t off = 0; off < total && e == cudaSuccess; off += piece, k ^= 1) {
                 const size_t nb = (size_t)std::min<uint64_t>(piece, total - off);
                 e = cudaEventSynchronize(ev[k]);                 // a never-recorded event is complete
                 if (e != cudaSuccess) break;
                 engine->host_copy(st[k]->h_in, (const char*)iq + anns[i].start_sample * bps + off, nb);
-                e = cudaMemcpyAsync((char*)s.d_in + pos * bps + off, st[k]->h_in, nb, cudaMemcpyHostToDevice, s.stream);
+                e = cudaMemcpyAsync((char*)s.d_in + local[i].start_sample * bps + off, st[k]->h_in, nb, cudaMemcpyHostToDevice, s.stream);
                 if (e == cudaSuccess) e = cudaEventRecord(ev[k], s.stream);
             }
-            pos += anns[i].count;
         }
     }
     // on failure nothing of the caller's may still be in flight when this returns
-    auto fail = [&](int code) { cudaStreamSynchronize(s.stream); return code; };
+    auto fail = [&](int code) { cudaStreamSynchronize(s.stream); if (engine->dc_aux) cudaStreamSynchronize(engine->dc_aux); return code; };
     if (e != cudaSuccess) return fail(cuda_fail(e, "H2D annotation spans"));
-    double* d_iq_out = (double*)s.d_out;
-    double* d_psd = out_psd_db ? (double*)((char*)s.d_out + out_doubles * 8) : nullptr;
+    double* d_iq_out = out_iq ? (double*)s.d_out : nullptr;
+    double* d_psd = out_psd_db ? (double*)((char*)s.d_out + iq_out_bytes) : nullptr;
+    if (!d_iq_out && !d_psd) return fail(set_error(SA_ERR_INVALID_ARG, "both outputs are NULL"));
     rc = run_batch_device(engine, s.d_in, in_samples, dtype, big_endian, sample_rate, local.data(), n_ann, psd_nfft,
                           psd_hop, psd_window, d_iq_out, dev_off.data(), d_psd, s.stream);
     if (rc) return fail(rc);
     if (out_iq) {
         for (uint32_t i = 0; i < n_ann && e == cudaSuccess; i++) {
-            const uint64_t m2 = 2 * (anns[i].count / (uint64_t)anns[i].down);
+            const uint64_t m2 = 2 * dc_out_len(engine->profile, anns[i].count, anns[i].down, anns[i].fast);
             if (m2) e = cudaMemcpyAsync(out_iq + iq_offsets[i], d_iq_out + dev_off[i], m2 * 8, cudaMemcpyDeviceToHost, s.stream);
         }
     }
@@ -408,7 +714,8 @@ int32_t sa_downconvert(sa_engine* engine, const void* iq, uint64_t iq_bytes, int
                        double* out_re, double* out_im, uint64_t* out_len) {
     if (!out_re || !out_im || !out_len) return set_error(SA_ERR_INVALID_ARG, "NULL output");
     if (down < 1) return set_error(SA_ERR_INVALID_ARG, "down %d < 1", down);
-    const uint64_t m = count / (uint64_t)down;
+    if (!engine) return set_error(SA_ERR_INVALID_ARG, "engine is NULL");
+    const uint64_t m = sa_downconvert_length(engine, count, down, fast);
     sa_annotation a;
     a.start_sample = start_sample; a.count = count; a.freq_off = freq_off; a.down = down; a.fast = fast;
     std::vector<double> tmp(std::max<uint64_t>(2 * m, 1));
@@ -435,16 +742,21 @@ int32_t sa_psd_welch(sa_engine* engine, const double* re, const double* im, uint
     if (rc) return rc;
     double* d_rows = (double*)s.d_out;
     double* d_psd = d_rows + 2 * n;
+    auto fail = [&](int code) { cudaStreamSynchronize(s.stream); return code; };     // the caller's rows may be in flight
     cudaError_t e = cudaMemcpyAsync(d_rows, re, n * 8, cudaMemcpyHostToDevice, s.stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_rows + n, im, n * 8, cudaMemcpyHostToDevice, s.stream);
-    if (e != cudaSuccess) return cuda_fail(e, "H2D psd rows");
+    if (e != cudaSuccess) return fail(cuda_fail(e, "H2D psd rows"));
     std::vector<WelchJob> jobs(1);
-    jobs[0].re = d_rows; jobs[0].im = d_rows + n; jobs[0].n = (long long)n; jobs[0].fs = fs;
-    rc = welch_device(engine, jobs, nfft, hop, window, d_psd, s.stream);
-    if (rc) return rc;
+    jobs[0].re = d_rows; jobs[0].im = d_rows + n; jobs[0].f32 = nullptr; jobs[0].n = (long long)n; jobs[0].fs = fs;
+    jobs[0].d_out = d_psd;
+    WelchLaunch wl;
+    rc = welch_prepare(engine, jobs, nfft, hop, window, wl);
+    if (rc) return fail(rc);
+    rc = welch_launch(engine, wl, nullptr, s.stream, 0);
+    if (rc) return fail(rc);
     e = cudaMemcpyAsync(out_db, d_psd, (size_t)nfft * 8, cudaMemcpyDeviceToHost, s.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
-    if (e != cudaSuccess) return cuda_fail(e, "psd welch");
+    if (e != cudaSuccess) return fail(cuda_fail(e, "psd welch"));
     for (uint32_t k = 0; k < nfft; k++) out_freq[k] = ((double)k - (double)(nfft / 2)) * fs / (double)nfft;
     return SA_OK;
 }

@@ -3,12 +3,17 @@
 // Replaces S/services/ExtractDownConvertService.java:54-117 (decode loop :74-100 + the JDSP
 // Resampler calls :106,:111-112) and the JDSP PowerSpectralDensity.calculatePsdWelch call of
 // S/controllers/AnalysisDialogController.java:308-312.  JDSP is not vendored in the reference, so
-// the arithmetic follows this repository's documented spec (DESIGN.md "downconvert / Welch"):
-//   y[n]  = x[n] * exp(-2 pi i f n)                      n = 0 at the first extracted sample
-//   conv  : z[m] = sum_{k=0}^{8D} h[k] y[mD - k]         Hamming-windowed sinc, causal, zero history
+// every choice it makes is a parameter of the engine's analysis profile (sa_analysis_config,
+// include/sa_engine.h); the defaults are this repository's documented spec (DESIGN.md "downconvert / Welch"):
+//   y[n]  = x[n] * exp(-2 pi i f n)                      n = 0 at the first extracted sample, y = 0 outside [0, count)
+//   conv  : z[m] = sum_{k<L} h[k] y[mD + off - k]        default h: Hamming-windowed sinc, L = 8D+1; off = 0 (causal),
+//                                                        (L-1)/2 (same) or L-1 (valid)
 //   fast  : z[m] = (1/D) sum_{k<D} y[mD + k]             moving average, then decimate
-//   M     = count / D
-//   Welch : Hann, hop nfft/4, two-sided, mean |FFT|^2 / (fs sum w^2), 10 log10, fft-shifted
+//   M     = floor(count / D) | ceil(count / D) | (count - L)/D + 1 (valid)
+//   Welch : window, hop, optional per-segment mean removal, two-sided, mean |FFT|^2 scaled 1/(fs sum w^2) (density) or
+//           1/(sum w)^2 (spectrum), 10 log10, fft-shifted; FP32 or FP64 transforms; any nfft (powers of two through
+//           the Stockham kernels, everything else through the direct DFT kernel: the reference's short-signal branch,
+//           AnalysisDialogController.java:304-307, passes nfft = signal length)
 #pragma once
 #include "decode.cuh"
 
@@ -18,12 +23,15 @@ struct DcAnn {
     long long start_sample;          // first extracted sample of the capture
     long long count;
     unsigned long long phase_step;   // frac(freq_off) * 2^64 : NCO phase is an exact 64-bit accumulator
-    long long out_off;               // offset (in doubles) of this annotation's re block in the output
-    long long m_out;                 // count / down
+    long long out_off;               // offset (in doubles) of this annotation's re block in the FP64 output
+    long long scr_off;               // offset (in float2) of this annotation in the FP32 scratch rows
+    long long m_out;                 // outputs
+    long long in_off;                // delay shift `off` above
     int down;
     int fast;
-    int nb;                          // outputs per tile of the staged kernel
-    int taps_off;                    // offset (floats) of this D's tap block in the tap table
+    int nb;                          // outputs per tile of the staged kernel (0: warp-per-output kernel)
+    int taps_off;                    // offset (floats) of this annotation's tap block in the tap table
+    int n_taps;                      // L (warp-per-output kernel)
     unsigned qmagic;                 // ceil(2^32 / down) (0 for down == 1): staged-index / down by umulhi
 };
 
@@ -31,9 +39,11 @@ struct DcArgs {
     LoadParams lp;
     long long n_samples;             // IQ pairs readable from lp.base
     const DcAnn* anns;
-    const float* taps;               // per D: h[0..8D] natural order, then ht[r*8 + p] = h[D*p + r]
-    double* out;                     // planar: re[M] then im[M] per annotation
+    const float* taps;               // per block: h[0..8D] natural order (zero padded), then ht[r*8 + p] = h[D*p + r]
+    double* out;                     // planar: re[M] then im[M] per annotation (the Java double[2][M]); may be NULL
+    float2* scratch;                 // interleaved FP32 rows for the Welch kernel (stays in L2); may be NULL
     int ann_base;                    // first annotation of this launch (launches are grouped by down)
+    int tiles_per_cta;
 };
 
 // Taps of ONE decimation factor as a kernel parameter: every lane of a warp uses the same 8 taps per
@@ -49,6 +59,27 @@ struct DcTapParams {
 constexpr int kDcThreads = 256;
 constexpr int kDcStage = 8192;       // staged samples per tile (shared memory budget)
 constexpr int kDcMaxDown = 512;      // larger decimations take the warp-per-output kernel
+constexpr int kDcPipeLoads = 17;     // pipelined variant: the whole tile (<= 17 x 256 samples) is one register batch
+constexpr int kDcPipeTiles = 8;      // consecutive tiles of one annotation per CTA (pipelined variant)
+
+// The reference's cf64 stride bug, reproduced only with strict_reference (ExtractDownConvertService.java:60-67,79-81):
+// IQ pair i is read as the two doubles at byte offset 8 i (re = d[i], im = d[i+1]).
+constexpr int DK_CF64_S8 = 4;
+template <typename T> struct Loader<T, DK_CF64_S8> : Loader<T, DK_CF64> {};
+
+template <int DK> struct DcRaw {
+    using LD = Loader<float, DK>;
+    using raw_t = typename LD::raw_t;
+    static __device__ __forceinline__ raw_t ld(const void* base, long long i) { return __ldg(reinterpret_cast<const raw_t*>(base) + i); }
+};
+template <> struct DcRaw<DK_CF64_S8> {
+    using LD = Loader<float, DK_CF64>;
+    using raw_t = uint4;
+    static __device__ __forceinline__ raw_t ld(const void* base, long long i) {
+        const uint2 a = __ldg(reinterpret_cast<const uint2*>(base) + i), b = __ldg(reinterpret_cast<const uint2*>(base) + i + 1);
+        return make_uint4(a.x, a.y, b.x, b.y);
+    }
+};
 
 // x * exp(-2 pi i phase), phase from the top 32 bits of the 64-bit accumulator
 __device__ __forceinline__ float2 nco_mix(float2 x, unsigned long long phase) {
@@ -60,11 +91,11 @@ __device__ __forceinline__ float2 nco_mix(float2 x, unsigned long long phase) {
 
 template <int DK>
 __device__ __forceinline__ float2 load_mixed(const DcArgs& a, const DcAnn& an, long long n) {
-    // n relative to the annotation start; zero history before it (causal filter)
-    if (n < 0) return make_float2(0.f, 0.f);
-    const long long g = an.start_sample + n;
-    cpx<float> x = a.lp.swap ? Loader<float, DK>::template load<true>(a.lp, g)
-                             : Loader<float, DK>::template load<false>(a.lp, g);
+    // n relative to the annotation start; zero outside [0, count)
+    if (n < 0 || n >= an.count) return make_float2(0.f, 0.f);
+    using R = DcRaw<DK>;
+    const typename R::raw_t raw = R::ld(a.lp.base, an.start_sample + n);
+    const cpx<float> x = a.lp.swap ? R::LD::template decode<true>(a.lp, raw) : R::LD::template decode<false>(a.lp, raw);
     return nco_mix(make_float2(x.x, x.y), an.phase_step * (unsigned long long)n);
 }
 
@@ -75,160 +106,187 @@ __device__ __forceinline__ float2 nco_phasor(unsigned long long phase) {
     __sincosf(ang, &s, &c);
     return make_float2(c, -s);
 }
-__device__ __forceinline__ float2 cmul(float2 x, float2 p) {
-    return make_float2(__fmaf_rn(x.x, p.x, -x.y * p.y), __fmaf_rn(x.x, p.y, x.y * p.x));
-}
-
-// Stages the decoded + mixed samples n = nlo .. nlo + n_stage - 1 of one tile: stage[i + (i / D) * pad].
-// One sample per thread and step (coalesced), kDcUnroll independent loads in flight per thread before the
-// first is consumed; the NCO phase of every sample comes from the exact 64-bit accumulator.  Samples before
-// the annotation start (n < 0) are the zero history of the causal filter.
-constexpr int kDcUnrollMax = 16;      // loads in flight per thread (16-byte cf64 pairs: 8, register budget); C3: 8 -> 16 = +4 %
 
 __device__ __forceinline__ void sts64(uint32_t addr, float x, float y) {
     asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(x), "f"(y) : "memory");
 }
 
-template <int DK, bool SWAP, bool INTERIOR>
-__device__ __forceinline__ void dc_stage_tile_impl(const DcArgs& a, const DcAnn& an, float2* __restrict__ stage,
-                                                   const long long nlo, const int n_stage, const int pad) {
-    using LD = Loader<float, DK>;
-    using raw_t = typename LD::raw_t;
-    constexpr int kDcUnroll = sizeof(raw_t) <= 8 ? kDcUnrollMax : kDcUnrollMax / 2;
-    const raw_t* src = reinterpret_cast<const raw_t*>(a.lp.base) + (an.start_sample + nlo) + threadIdx.x;
-    // the phasor advances kDcThreads samples per step: one complex multiply by wstep (packed: P = (c, -s),
-    // Q = i P, P' = P.x W + P.y (i W)), re-seeded from the exact 64-bit phase at every batch of kDcUnroll samples
+// One register batch of a tile: U coalesced loads per thread (sample i0 + tid + 256 u of the tile), all issued before
+// the first is consumed.  Samples outside the annotation ([lo, hi) in tile coordinates) are not read.
+template <int DK, int U>
+__device__ __forceinline__ void dc_load_batch(const DcArgs& a, const DcAnn& an, typename DcRaw<DK>::raw_t (&raw)[U],
+                                              const long long nlo, const int i0, const int lo, const int hi) {
+    using R = DcRaw<DK>;
+    const long long s = an.start_sample + nlo + i0 + threadIdx.x;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const int ii = i0 + (int)threadIdx.x + u * kDcThreads;
+        raw[u] = typename R::raw_t();
+        if (ii >= lo && ii < hi) raw[u] = R::ld(a.lp.base, s + u * kDcThreads);
+    }
+}
+
+// Decodes and mixes a register batch into the staged tile: stage[i + (i / D) * pad].  The NCO phasor of the batch
+// is seeded from the exact 64-bit phase and advances 256 samples per step by one packed complex multiply.
+template <int DK, bool SWAP, int U>
+__device__ __forceinline__ void dc_stage_batch(const DcArgs& a, const DcAnn& an, const typename DcRaw<DK>::raw_t (&raw)[U],
+                                               float2* __restrict__ stage, const long long nlo, const int i0,
+                                               const int n_stage, const int lo, const int hi, const int pad) {
+    using LD = typename DcRaw<DK>::LD;
     const float2 wstep = nco_phasor(an.phase_step * (unsigned long long)kDcThreads);
     const pk2 W = pack2(wstep.x, wstep.y), iW = pack2(-wstep.y, wstep.x);
     const unsigned qmagic = pad ? an.qmagic : 0u;                // i / D == umulhi(i, ceil(2^32 / D)) for i*D < 2^32
     const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
-    for (int i = threadIdx.x; i < n_stage; i += kDcThreads * kDcUnroll, src += kDcThreads * kDcUnroll) {
-        raw_t raw[kDcUnroll];
+    const float2 ph0 = nco_phasor(an.phase_step * (unsigned long long)(nlo + i0 + (long long)threadIdx.x));
+    pk2 P = pack2(ph0.x, ph0.y);
 #pragma unroll
-        for (int u = 0; u < kDcUnroll; u++) {
-            const int ii = i + u * kDcThreads;
-            raw[u] = raw_t();
-            if (ii < n_stage && (INTERIOR || nlo + ii >= 0)) raw[u] = __ldg(src + u * kDcThreads);
-        }
-        const float2 ph0 = nco_phasor(an.phase_step * (unsigned long long)(nlo + i));
-        pk2 P = pack2(ph0.x, ph0.y);
-#pragma unroll
-        for (int u = 0; u < kDcUnroll; u++) {
-            const int ii = i + u * kDcThreads;
-            const cpx<float> d = LD::template decode<SWAP>(a.lp, raw[u]);
-            float px, py;
-            unpack2(P, px, py);
-            // y = d * P = d.x (P.x, P.y) + d.y (-P.y, P.x)
-            pk2 Y = fma2(pack2(d.y, d.y), pack2(-py, px), mul2(pack2(d.x, d.x), P));
-            if (!INTERIOR && nlo + ii < 0) Y = pack2(0.f, 0.f);
-            float yx, yy;
-            unpack2(Y, yx, yy);
-            if (ii < n_stage) sts64(stage_s + 8u * (unsigned)(ii + (int)__umulhi((unsigned)ii, qmagic)), yx, yy);
-            if (u + 1 < kDcUnroll) P = fma2(pack2(py, py), iW, mul2(pack2(px, px), W));
-        }
+    for (int u = 0; u < U; u++) {
+        const int ii = i0 + (int)threadIdx.x + u * kDcThreads;
+        const cpx<float> d = LD::template decode<SWAP>(a.lp, raw[u]);
+        float px, py;
+        unpack2(P, px, py);
+        // y = d * P = d.x (P.x, P.y) + d.y (-P.y, P.x)
+        pk2 Y = fma2(pack2(d.y, d.y), pack2(-py, px), mul2(pack2(d.x, d.x), P));
+        if (ii < lo || ii >= hi) Y = pack2(0.f, 0.f);             // zero history / zero tail of the filter
+        float yx, yy;
+        unpack2(Y, yx, yy);
+        if (ii < n_stage) sts64(stage_s + 8u * (unsigned)(ii + (int)__umulhi((unsigned)ii, qmagic)), yx, yy);
+        if (u + 1 < U) P = fma2(pack2(py, py), iW, mul2(pack2(px, px), W));
     }
 }
 
-template <int DK>
-__device__ __forceinline__ void dc_stage_tile(const DcArgs& a, const DcAnn& an, float2* __restrict__ stage,
-                                              const long long nlo, const int n_stage, const int pad) {
-    if (nlo >= 0) {
-        if (a.lp.swap) dc_stage_tile_impl<DK, true, true>(a, an, stage, nlo, n_stage, pad);
-        else           dc_stage_tile_impl<DK, false, true>(a, an, stage, nlo, n_stage, pad);
-    } else {
-        if (a.lp.swap) dc_stage_tile_impl<DK, true, false>(a, an, stage, nlo, n_stage, pad);
-        else           dc_stage_tile_impl<DK, false, false>(a, an, stage, nlo, n_stage, pad);
-    }
-}
+constexpr int kDcUnrollMax = 16;      // loads in flight per thread of the non-pipelined variant (16-byte pairs: 8)
 
 // Staged kernel (down <= kDcMaxDown): one tile = an.nb consecutive outputs of one annotation.
 // Samples are decoded and mixed ONCE into shared memory; thread b then forms the 8 polyphase
 // partial sums C_p[b] = sum_r h[Dp + r] y[bD - r] of input block b, and
-// z[m] = sum_p C_p[m - p] + h[8D] y[(m-8)D].
-template <int DK, bool PTAPS>
-__global__ void __launch_bounds__(kDcThreads, 4)
+// z[m] = sum_p C_p[m - p] + h[8D] y[(m-8)D]   (tile-local indices; `in_off` shifts the whole tile).
+// PIPE: a CTA walks kDcPipeTiles consecutive tiles of its annotation; the raw samples of tile i+1 are loaded
+// into registers right after tile i has been staged and travel under tile i's FIR, combine and stores.
+// (Ablation, removed: a compile-time decimation factor with the loop over r unrolled.  FFMA2 takes its scalar operand
+// from a vector register only, so the taps still travel LDCU -> MOV -> register pair: 19 instructions per tap row
+// against 13 for the run-time loop, whose LDC.64 lands the tap pairs in vector registers directly.)
+template <int DK, bool PTAPS, bool PIPE>
+__global__ void __launch_bounds__(kDcThreads, PIPE ? 3 : 4)
 downconvert_kernel(const DcArgs a, const __grid_constant__ DcTapParams tp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    using raw_t = typename DcRaw<DK>::raw_t;
+    constexpr int U = PIPE ? kDcPipeLoads : (sizeof(raw_t) <= 8 ? kDcUnrollMax : kDcUnrollMax / 2);
     const DcAnn an = a.anns[a.ann_base + blockIdx.y];
     const int D = an.down;
-    const long long m0 = (long long)blockIdx.x * an.nb;
-    if (an.nb == 0 || m0 >= an.m_out) return;      // nb == 0: handled by downconvert_wide_kernel
-    const int nbt = (int)min((long long)an.nb, an.m_out - m0);
-    const int pad = (D & 1) ? 0 : 1;                 // odd stride between blocks: conflict-free LDS.64
+    if (an.nb == 0) return;                           // handled by downconvert_wide_kernel
+    const long long n_tiles = (an.m_out + an.nb - 1) / an.nb;
+    long long tile = (long long)blockIdx.x * a.tiles_per_cta;
+    const long long tile_end = min(n_tiles, tile + a.tiles_per_cta);
+    if (tile >= tile_end) return;
+    const int pad = (D & 1) ? 0 : 1;                  // odd stride between blocks: conflict-free LDS.64
     float2* stage = reinterpret_cast<float2*>(smem_raw);
     const int halo = an.fast ? 0 : 7;
-    const int nblk = nbt + halo;
-    const int n_stage = an.fast ? nbt * D : nblk * D + 1;
-    const int stage_phys = n_stage + n_stage / D + 2;
-    float4* csm = reinterpret_cast<float4*>(stage + ((stage_phys + 1) & ~1));   // C_p[b]: 8 float2 per block
     const float* h = a.taps + an.taps_off;
     const float* ht = h + 8 * D + 1;
-    const long long nlo = an.fast ? m0 * D : (m0 - 8) * D;
+    const float h_last = PTAPS ? tp.h_last : h[8 * D];
 
-    dc_stage_tile<DK>(a, an, stage, nlo, n_stage, pad);
-    __syncthreads();
-    double* out_re = a.out + an.out_off + m0;
-    double* out_im = out_re + an.m_out;
-    if (an.fast) {
-        for (int j = threadIdx.x; j < nbt; j += kDcThreads) {
-            const float2* s = stage + j * (D + pad);
-            float sr = 0.f, si = 0.f;
-            for (int k = 0; k < D; k++) { sr += s[k].x; si += s[k].y; }
-            const float inv = 1.0f / (float)D;
-            out_re[j] = (double)(sr * inv);
-            out_im[j] = (double)(si * inv);
-        }
-        return;
-    }
-    float2* csm_t = reinterpret_cast<float2*>(csm);               // C_p[b] at csm_t[p * nblk + b]
-    for (int b = threadIdx.x; b < nblk; b += kDcThreads) {
-        // accumulators packed over p: ax[i] = (Re C_2i, Re C_2i+1), ay[i] likewise (FFMA2: the tap pairs
-        // arrive adjacent from the 128-bit loads, the sample is broadcast into both lanes)
-        pk2 ax[4], ay[4];
-#pragma unroll
-        for (int p = 0; p < 4; p++) { ax[p] = pack2(0.f, 0.f); ay[p] = pack2(0.f, 0.f); }
-        // block b (local) holds staged indices (b+1)*D - r, r = 0..D-1
-        const float2* s_hi = stage + (b + 1) * (D + pad);       // r = 0 sits here (next block's slot 0)
-        const float2* s_lo = stage + b * (D + pad) + D;         // r > 0: b*(D+pad) + D - r
-        const float4* t4 = reinterpret_cast<const float4*>(ht);
-        for (int r = 0; r < D; r++) {
-            const float2 s = (r == 0) ? s_hi[0] : s_lo[-r];
-            float4 ta, tb;
-            if constexpr (PTAPS) {
-                ta = make_float4(tp.ht[8 * r], tp.ht[8 * r + 1], tp.ht[8 * r + 2], tp.ht[8 * r + 3]);
-                tb = make_float4(tp.ht[8 * r + 4], tp.ht[8 * r + 5], tp.ht[8 * r + 6], tp.ht[8 * r + 7]);
-            } else {
-                ta = __ldg(&t4[2 * r]); tb = __ldg(&t4[2 * r + 1]);
+    // geometry of a tile (the last one of an annotation may be short)
+    auto geom = [&](long long tl, int& nbt, int& nblk, int& n_stage, long long& nlo, int& lo, int& hi) {
+        const long long m0 = tl * an.nb;
+        nbt = (int)min((long long)an.nb, an.m_out - m0);
+        nblk = nbt + halo;
+        n_stage = an.fast ? nbt * D : nblk * D + 1;
+        nlo = an.fast ? m0 * D : (m0 - 8) * D + an.in_off;
+        lo = (int)max(0LL, min((long long)n_stage, -nlo));
+        hi = (int)max(0LL, min((long long)n_stage, an.count - nlo));
+    };
+    int nbt, nblk, n_stage, lo, hi;
+    long long nlo;
+    geom(tile, nbt, nblk, n_stage, nlo, lo, hi);
+    raw_t raw[U];
+    if constexpr (PIPE) dc_load_batch<DK, U>(a, an, raw, nlo, 0, lo, hi);
+    for (; tile < tile_end; tile++) {
+        const long long m0 = tile * an.nb;
+        // ---- stage: decode + mix once into shared memory
+        if constexpr (PIPE) {
+            if (a.lp.swap) dc_stage_batch<DK, true, U>(a, an, raw, stage, nlo, 0, n_stage, lo, hi, pad);
+            else           dc_stage_batch<DK, false, U>(a, an, raw, stage, nlo, 0, n_stage, lo, hi, pad);
+        } else {
+            for (int i0 = 0; i0 < n_stage; i0 += kDcThreads * U) {
+                dc_load_batch<DK, U>(a, an, raw, nlo, i0, lo, hi);
+                if (a.lp.swap) dc_stage_batch<DK, true, U>(a, an, raw, stage, nlo, i0, n_stage, lo, hi, pad);
+                else           dc_stage_batch<DK, false, U>(a, an, raw, stage, nlo, i0, n_stage, lo, hi, pad);
             }
-            const pk2 sx = pack2(s.x, s.x), sy = pack2(s.y, s.y);
-            const pk2 t01 = pack2(ta.x, ta.y), t23 = pack2(ta.z, ta.w), t45 = pack2(tb.x, tb.y), t67 = pack2(tb.z, tb.w);
-            ax[0] = fma2(t01, sx, ax[0]); ay[0] = fma2(t01, sy, ay[0]);
-            ax[1] = fma2(t23, sx, ax[1]); ay[1] = fma2(t23, sy, ay[1]);
-            ax[2] = fma2(t45, sx, ax[2]); ay[2] = fma2(t45, sy, ay[2]);
-            ax[3] = fma2(t67, sx, ax[3]); ay[3] = fma2(t67, sy, ay[3]);
         }
-#pragma unroll
-        for (int p = 0; p < 4; p++) {
-            float x0, x1, y0, y1;
-            unpack2(ax[p], x0, x1); unpack2(ay[p], y0, y1);
-            csm_t[(2 * p) * nblk + b] = make_float2(x0, y0);
-            csm_t[(2 * p + 1) * nblk + b] = make_float2(x1, y1);
+        __syncthreads();
+        const int c_nbt = nbt, c_nblk = nblk, c_nstage = n_stage;
+        if constexpr (PIPE) {           // next tile's samples fly under this tile's arithmetic
+            if (tile + 1 < tile_end) {
+                geom(tile + 1, nbt, nblk, n_stage, nlo, lo, hi);
+                dc_load_batch<DK, U>(a, an, raw, nlo, 0, lo, hi);
+            }
         }
-    }
-    __syncthreads();
-    const float h_last = h[8 * D];
-    for (int j = threadIdx.x; j < nbt; j += kDcThreads) {
-        // output m = m0 + j uses local blocks (j + 7 - p), p = 0..7, and staged sample j*D
-        const float2 s = stage[j * (D + pad)];
-        float zr = h_last * s.x, zi = h_last * s.y;
+        const int stage_phys = c_nstage + c_nstage / D + 2;
+        float2* csm_t = stage + ((stage_phys + 1) & ~1);               // C_p[b] at csm_t[p * nblk + b]
+        double* out_re = a.out ? a.out + an.out_off + m0 : nullptr;
+        double* out_im = a.out ? out_re + an.m_out : nullptr;
+        float2* scr = a.scratch ? a.scratch + an.scr_off + m0 : nullptr;
+        if (an.fast) {
+            for (int j = threadIdx.x; j < c_nbt; j += kDcThreads) {
+                const float2* s = stage + j * (D + pad);
+                float sr = 0.f, si = 0.f;
+                for (int k = 0; k < D; k++) { sr += s[k].x; si += s[k].y; }
+                const float inv = 1.0f / (float)D;
+                if (out_re) { out_re[j] = (double)(sr * inv); out_im[j] = (double)(si * inv); }
+                if (scr) scr[j] = make_float2(sr * inv, si * inv);
+            }
+        } else {
+            for (int b = threadIdx.x; b < c_nblk; b += kDcThreads) {
+                // accumulators packed over p: ax[i] = (Re C_2i, Re C_2i+1), ay[i] likewise (FFMA2: the tap pairs
+                // arrive adjacent from the 128-bit loads, the sample is broadcast into both lanes)
+                pk2 ax[4], ay[4];
 #pragma unroll
-        for (int p = 0; p < 8; p++) { const float2 c = csm_t[p * nblk + (j + 7 - p)]; zr += c.x; zi += c.y; }
-        out_re[j] = (double)zr;
-        out_im[j] = (double)zi;
+                for (int p = 0; p < 4; p++) { ax[p] = pack2(0.f, 0.f); ay[p] = pack2(0.f, 0.f); }
+                // block b (local) holds staged indices (b+1)*D - r, r = 0..D-1
+                const float2* s_hi = stage + (b + 1) * (D + pad);       // r = 0 sits here (next block's slot 0)
+                const float2* s_lo = stage + b * (D + pad) + D;         // r > 0: b*(D+pad) + D - r
+                const float4* t4 = reinterpret_cast<const float4*>(ht);
+                for (int r = 0; r < D; r++) {
+                    const float2 s = (r == 0) ? s_hi[0] : s_lo[-r];
+                    float4 ta, tb;
+                    if constexpr (PTAPS) {
+                        ta = make_float4(tp.ht[8 * r], tp.ht[8 * r + 1], tp.ht[8 * r + 2], tp.ht[8 * r + 3]);
+                        tb = make_float4(tp.ht[8 * r + 4], tp.ht[8 * r + 5], tp.ht[8 * r + 6], tp.ht[8 * r + 7]);
+                    } else {
+                        ta = __ldg(&t4[2 * r]); tb = __ldg(&t4[2 * r + 1]);
+                    }
+                    const pk2 sx = pack2(s.x, s.x), sy = pack2(s.y, s.y);
+                    const pk2 t01 = pack2(ta.x, ta.y), t23 = pack2(ta.z, ta.w), t45 = pack2(tb.x, tb.y), t67 = pack2(tb.z, tb.w);
+                    ax[0] = fma2(t01, sx, ax[0]); ay[0] = fma2(t01, sy, ay[0]);
+                    ax[1] = fma2(t23, sx, ax[1]); ay[1] = fma2(t23, sy, ay[1]);
+                    ax[2] = fma2(t45, sx, ax[2]); ay[2] = fma2(t45, sy, ay[2]);
+                    ax[3] = fma2(t67, sx, ax[3]); ay[3] = fma2(t67, sy, ay[3]);
+                }
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    float x0, x1, y0, y1;
+                    unpack2(ax[p], x0, x1); unpack2(ay[p], y0, y1);
+                    csm_t[(2 * p) * c_nblk + b] = make_float2(x0, y0);
+                    csm_t[(2 * p + 1) * c_nblk + b] = make_float2(x1, y1);
+                }
+            }
+            __syncthreads();
+            for (int j = threadIdx.x; j < c_nbt; j += kDcThreads) {
+                // output m = m0 + j uses local blocks (j + 7 - p), p = 0..7, and staged sample j*D
+                const float2 s = stage[j * (D + pad)];
+                float zr = h_last * s.x, zi = h_last * s.y;
+#pragma unroll
+                for (int p = 0; p < 8; p++) { const float2 c = csm_t[p * c_nblk + (j + 7 - p)]; zr += c.x; zi += c.y; }
+                if (out_re) { out_re[j] = (double)zr; out_im[j] = (double)zi; }
+                if (scr) scr[j] = make_float2(zr, zi);
+            }
+        }
+        __syncthreads();                 // stage / C_p are rewritten by the next tile
     }
 }
 
-// Fallback for very large decimations: one warp per output, lanes stride over the taps.
+// Fallback for very large decimations or tap counts above 8D+1: one warp per output, lanes stride over the taps.
 template <int DK>
 __global__ void __launch_bounds__(256)
 downconvert_wide_kernel(const DcArgs a) {
@@ -243,97 +301,221 @@ downconvert_wide_kernel(const DcArgs a) {
         for (int k = lane; k < D; k += 32) { const float2 y = load_mixed<DK>(a, an, m * D + k); zr += y.x; zi += y.y; }
         zr /= (float)D; zi /= (float)D;
     } else {
-        for (int k = lane; k <= 8 * D; k += 32) {
-            const float2 y = load_mixed<DK>(a, an, m * D - k);
+        for (int k = lane; k < an.n_taps; k += 32) {
+            const float2 y = load_mixed<DK>(a, an, m * D + an.in_off - k);
             zr = __fmaf_rn(h[k], y.x, zr); zi = __fmaf_rn(h[k], y.y, zi);
         }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { zr += __shfl_xor_sync(0xffffffffu, zr, o); zi += __shfl_xor_sync(0xffffffffu, zi, o); }
     if (lane == 0) {
-        a.out[an.out_off + m] = (double)zr;
-        a.out[an.out_off + an.m_out + m] = (double)zi;
+        if (a.out) {
+            a.out[an.out_off + m] = (double)zr;
+            a.out[an.out_off + an.m_out + m] = (double)zi;
+        }
+        if (a.scratch) a.scratch[an.scr_off + m] = make_float2(zr, zi);
     }
 }
 
 // ---------------- Welch ----------------
 struct WelchSig {
-    const double* re;      // planar FP64 input (the downconverter's output rows)
+    const double* re;      // planar FP64 input (the downconverter's output rows), or
     const double* im;
+    const float2* f32;     // interleaved FP32 rows (the downconverter's scratch); used when not NULL
     long long n;           // samples
-    double scale;          // 1 / (nseg * fs * sum w^2)
+    double scale;          // 1 / (nseg * fs * sum w^2)  |  1 / (nseg * (sum w)^2)
     long long nseg;
 };
 
 struct WelchArgs {
     const WelchSig* sigs;
     long long hop;
-    const float* window;
+    const void* window;    // T[N]
     const void* twiddle;
-    float* partial;        // [sig][slot][N], slot = split * FPC + frame slot
+    void* partial;         // T [sig][slot][N], slot = split * FPC + frame slot
     int nsplit;
+    int detrend;           // 1: subtract the segment's mean before the window
+    int window_id;         // direct kernel: window evaluated in the kernel
     double* out_db;        // [sig][N], fft-shifted
 };
 
-template <int N>
-__global__ void __launch_bounds__(Geo<float, N>::CTA, Geo<float, N>::MINB)
+template <typename T> __device__ __forceinline__ cpx<T> welch_load(const WelchSig& sg, long long i) {
+    if (sg.f32) { const float2 v = __ldg(&sg.f32[i]); return mk2<T>((T)v.x, (T)v.y); }
+    return mk2<T>((T)__ldg(&sg.re[i]), (T)__ldg(&sg.im[i]));
+}
+
+// mean over the TPF threads x P values of one frame (detrend = constant)
+template <typename T, int TPF, int P, int CTA>
+__device__ __forceinline__ cpx<T> frame_mean(const cpx<T> (&v)[P], cpx<T>* red) {
+    T sx = 0, sy = 0;
+#pragma unroll
+    for (int q = 0; q < P; q++) { sx += v[q].x; sy += v[q].y; }
+    constexpr int W = TPF < 32 ? TPF : 32;
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) { sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o); }
+    if constexpr (TPF > 32) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        constexpr int WPF = TPF / 32;                 // warps per frame
+        __syncthreads();
+        if (lane == 0) red[warp] = mk2<T>(sx, sy);
+        __syncthreads();
+        const int w0 = (warp / WPF) * WPF;
+        sx = 0; sy = 0;
+#pragma unroll
+        for (int k = 0; k < WPF; k++) { sx += red[w0 + k].x; sy += red[w0 + k].y; }
+    }
+    const T inv = (T)1 / (T)(TPF * P);
+    return mk2<T>(sx * inv, sy * inv);
+}
+
+template <typename T, int N>
+__global__ void __launch_bounds__(Geo<T, N>::CTA, Geo<T, N>::MINB)
 welch_accum_kernel(const WelchArgs a) {
-    using G = Geo<float, N>;
+    using G = Geo<T, N>;
     constexpr int P = G::P, TPF = G::TPF, FPC = G::FPC;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ cpx<T> red[32];
     const int fl = threadIdx.x / TPF, t = threadIdx.x % TPF;
-    float2* sm = reinterpret_cast<float2*>(smem_raw) + (size_t)fl * G::SM_ELEMS;
-    const float2* tw = reinterpret_cast<const float2*>(a.twiddle);
+    cpx<T>* sm = reinterpret_cast<cpx<T>*>(smem_raw) + (size_t)fl * G::SM_ELEMS;
+    const cpx<T>* tw = reinterpret_cast<const cpx<T>*>(a.twiddle);
     if constexpr (G::TW_SMEM) {      // one-warp-per-frame plans read their twiddles from shared memory
-        float2* tsm = reinterpret_cast<float2*>(smem_raw + G::SMEM_BYTES);
-        for (int i = threadIdx.x; i < (int)(G::TW_BYTES / sizeof(float2)); i += G::CTA) tsm[i] = __ldg(&tw[i]);
+        cpx<T>* tsm = reinterpret_cast<cpx<T>*>(smem_raw + G::SMEM_BYTES);
+        for (int i = threadIdx.x; i < (int)(G::TW_BYTES / sizeof(cpx<T>)); i += G::CTA) tsm[i] = __ldg(&tw[i]);
         __syncthreads();
         tw = tsm;
     }
-    const TwSeed<float> seed = load_tw_seed<float, N>(reinterpret_cast<const float2*>(a.twiddle), t);
+    const TwSeed<T> seed = load_tw_seed<T, N>(reinterpret_cast<const cpx<T>*>(a.twiddle), t);
+    const T* win = reinterpret_cast<const T*>(a.window);
     const WelchSig sg = a.sigs[blockIdx.y];
-    float acc[P];
+    T acc[P];
 #pragma unroll
-    for (int q = 0; q < P; q++) acc[q] = 0.f;
+    for (int q = 0; q < P; q++) acc[q] = (T)0;
     const long long stride = (long long)a.nsplit * FPC;
     const long long iters = (sg.nseg + stride - 1) / stride;
     for (long long it = 0; it < iters; it++) {
         const long long seg = it * stride + (long long)blockIdx.x * FPC + fl;
         const bool valid = seg < sg.nseg;
-        float2 v[P];
+        cpx<T> v[P];
         if (valid) {
-            const double* re = sg.re + seg * a.hop + t;
-            const double* im = sg.im + seg * a.hop + t;
+            const long long s0 = seg * a.hop + t;
 #pragma unroll
-            for (int q = 0; q < P; q++) {
-                const float w = __ldg(&a.window[t + TPF * q]);
-                v[q] = make_float2((float)__ldg(&re[TPF * q]) * w, (float)__ldg(&im[TPF * q]) * w);
-            }
+            for (int q = 0; q < P; q++) v[q] = welch_load<T>(sg, s0 + TPF * q);
         } else {
 #pragma unroll
-            for (int q = 0; q < P; q++) v[q] = make_float2(0.f, 0.f);
+            for (int q = 0; q < P; q++) v[q] = mk2<T>((T)0, (T)0);
         }
-        fft_frame<float, N, false>(v, t, sm, tw, nullptr, seed);
+        if (a.detrend) {                 // launch-uniform
+            const cpx<T> m = frame_mean<T, TPF, P, G::CTA>(v, red);
+#pragma unroll
+            for (int q = 0; q < P; q++) { v[q].x -= m.x; v[q].y -= m.y; }
+        }
+#pragma unroll
+        for (int q = 0; q < P; q++) { const T w = __ldg(&win[t + TPF * q]); v[q].x *= w; v[q].y *= w; }
+        fft_frame<T, N, false>(v, t, sm, tw, nullptr, seed);
         if (valid) {
 #pragma unroll
-            for (int q = 0; q < P; q++) acc[q] += __fmaf_rn(v[q].x, v[q].x, v[q].y * v[q].y);
+            for (int q = 0; q < P; q++) acc[q] += fma_t(v[q].x, v[q].x, v[q].y * v[q].y);
         }
     }
-    float* part = a.partial + (((size_t)blockIdx.y * a.nsplit + blockIdx.x) * FPC + fl) * N;
+    T* part = reinterpret_cast<T*>(a.partial) + (((size_t)blockIdx.y * a.nsplit + blockIdx.x) * FPC + fl) * N;
 #pragma unroll
     for (int q = 0; q < P; q++) part[t + TPF * q] = acc[q];
 }
 
-// sums the partial spectra in a fixed order (deterministic), scales to density, dB, fft-shift
+// sums the partial spectra in a fixed order (deterministic), scales, dB, fft-shift
+template <typename T>
 __global__ void welch_finalize_kernel(const WelchArgs a, const int n, const int slots) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const WelchSig sg = a.sigs[blockIdx.y];
-    const float* part = a.partial + (size_t)blockIdx.y * slots * n + k;
+    const T* part = reinterpret_cast<const T*>(a.partial) + (size_t)blockIdx.y * slots * n + k;
     double s = 0.0;
     for (int i = 0; i < slots; i++) s += (double)part[(size_t)i * n];
     const double v = sg.nseg > 0 ? 10.0 * log10(s * sg.scale + 1e-30) : __longlong_as_double(0x7ff8000000000000LL);
     a.out_db[(size_t)blockIdx.y * n + ((k + n / 2) & (n - 1))] = v;
+}
+
+// ---- any transform length: direct DFT (the reference's short-signal branch passes nfft = signal length) ----
+// Grid (bins / 256, signals).  The CTA builds W_nfft^j (FP64 sincospi, rounded once to T) in shared memory; the segment
+// goes through shared memory in tiles (mean removed, window evaluated in FP64); thread k accumulates bin k with the
+// exact twiddle index (k n) mod nfft kept by an integer recurrence.  O(nfft^2) per segment: meant for nfft < 8192.
+constexpr int kDirectTile = 1024;
+
+__device__ __forceinline__ double window_value(int id, int i, int n) {
+    const double x = 2.0 * (double)i / (double)n;            // in units of pi
+    switch (id) {
+        case SA_WIN_HANN:     return 0.5 - 0.5 * cospi(x);
+        case SA_WIN_HAMMING:  return 0.54 - 0.46 * cospi(x);
+        case SA_WIN_BLACKMAN: return 0.42 - 0.5 * cospi(x) + 0.08 * cospi(2 * x);
+        case SA_WIN_BLACKMAN_HARRIS: return 0.35875 - 0.48829 * cospi(x) + 0.14128 * cospi(2 * x) - 0.01168 * cospi(3 * x);
+        default: return 1.0;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+psd_direct_kernel(const WelchArgs a, const int nfft) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red_x[8], red_y[8];
+    cpx<T>* tw = reinterpret_cast<cpx<T>*>(smem_raw);
+    cpx<T>* xs = tw + nfft;
+    const WelchSig sg = a.sigs[blockIdx.y];
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    for (int j = threadIdx.x; j < nfft; j += 256) {
+        double s, c;
+        sincospi(2.0 * (double)j / (double)nfft, &s, &c);
+        tw[j] = mk2<T>((T)c, (T)(-s));
+    }
+    T acc = (T)0;
+    for (long long seg = 0; seg < sg.nseg; seg++) {
+        const long long s0 = seg * a.hop;
+        double mx = 0.0, my = 0.0;
+        if (a.detrend) {
+            double sx = 0.0, sy = 0.0;
+            for (int i = threadIdx.x; i < nfft; i += 256) { const cpx<double> v = welch_load<double>(sg, s0 + i); sx += v.x; sy += v.y; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o); }
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) { red_x[threadIdx.x >> 5] = sx; red_y[threadIdx.x >> 5] = sy; }
+            __syncthreads();
+            for (int w = 0; w < 8; w++) { mx += red_x[w]; my += red_y[w]; }
+            mx /= (double)nfft; my /= (double)nfft;
+        }
+        T xr0 = 0, xi0 = 0, xr1 = 0, xi1 = 0;       // two interleaved partial sums per component
+        int idx = 0;
+        for (int n0 = 0; n0 < nfft; n0 += kDirectTile) {
+            const int len = min(kDirectTile, nfft - n0);
+            __syncthreads();
+            for (int i = threadIdx.x; i < len; i += 256) {
+                const cpx<double> v = welch_load<double>(sg, s0 + n0 + i);
+                const double w = window_value(a.window_id, n0 + i, nfft);
+                xs[i] = mk2<T>((T)((v.x - mx) * w), (T)((v.y - my) * w));
+            }
+            __syncthreads();
+            if (k < nfft) {
+                int i = 0;
+                for (; i + 1 < len; i += 2) {
+                    const cpx<T> x0 = xs[i], w0 = tw[idx];
+                    idx += k; if (idx >= nfft) idx -= nfft;
+                    const cpx<T> x1 = xs[i + 1], w1 = tw[idx];
+                    idx += k; if (idx >= nfft) idx -= nfft;
+                    xr0 = fma_t(-x0.y, w0.y, fma_t(x0.x, w0.x, xr0)); xi0 = fma_t(x0.y, w0.x, fma_t(x0.x, w0.y, xi0));
+                    xr1 = fma_t(-x1.y, w1.y, fma_t(x1.x, w1.x, xr1)); xi1 = fma_t(x1.y, w1.x, fma_t(x1.x, w1.y, xi1));
+                }
+                if (i < len) {
+                    const cpx<T> x0 = xs[i], w0 = tw[idx];
+                    idx += k; if (idx >= nfft) idx -= nfft;
+                    xr0 = fma_t(-x0.y, w0.y, fma_t(x0.x, w0.x, xr0)); xi0 = fma_t(x0.y, w0.x, fma_t(x0.x, w0.y, xi0));
+                }
+            }
+        }
+        const T xr = xr0 + xr1, xi = xi0 + xi1;
+        acc += fma_t(xr, xr, xi * xi);
+    }
+    if (k < nfft) {
+        const double v = sg.nseg > 0 ? 10.0 * log10((double)acc * sg.scale + 1e-30) : __longlong_as_double(0x7ff8000000000000LL);
+        a.out_db[(size_t)blockIdx.y * nfft + (size_t)((k + nfft / 2) % nfft)] = v;
+    }
 }
 
 }  // namespace sa

@@ -80,7 +80,7 @@ int32_t sa_render_canvas_device(sa_engine* engine, const void* d_iq, uint64_t iq
     int prec = 0;
     rc = check_spec_params(&q, &prec);
     if (rc) return rc;
-    const uint64_t bps = (uint64_t)sa_bytes_per_iq(q.dtype);
+    const uint64_t bps = spec_bytes_per_iq(q);
     if ((uintptr_t)d_iq % bps) return set_error(SA_ERR_INVALID_ARG, "d_iq must be aligned to %llu bytes", (unsigned long long)bps);
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     const uint64_t cpc = canvas_cols_per_chunk(q, frames_per_column, canvas_w, 4 * kCanvasChunkBytes);
@@ -117,7 +117,7 @@ int32_t sa_render_canvas(sa_engine* engine, const void* iq, uint64_t iq_bytes, c
     int prec = 0;
     rc = check_spec_params(&q, &prec);
     if (rc) return rc;
-    const uint64_t bps = (uint64_t)sa_bytes_per_iq(q.dtype);
+    const uint64_t bps = spec_bytes_per_iq(q);
     const uint64_t n_samples = iq_bytes / bps;
     const uint64_t cpc = canvas_cols_per_chunk(q, frames_per_column, canvas_w, kCanvasChunkBytes, bps);
     const uint64_t fpchunk = cpc * frames_per_column;

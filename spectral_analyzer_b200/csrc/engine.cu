@@ -492,6 +492,30 @@ void fill_load_params(LoadParams& lp, const void* base, int dtype, int big_endia
 
 static bool is_pow2(uint64_t x) { return x && !(x & (x - 1)); }
 
+// strict_reference: datatypes SpectralService.computeMagnitudes has no branch for decode to zeros (:60-63)
+static bool strict_zero(const sa_spectrogram_params& p) {
+    return p.strict_reference && (p.dtype == SA_CF64 || p.dtype == SA_DT_OTHER);
+}
+// bytes per IQ pair as the frame loop sees them: Global.getBytesPerSample (S/sigmf/Global.java:67-79), fallback 8
+uint64_t spec_bytes_per_iq(const sa_spectrogram_params& p) {
+    if (p.dtype == SA_DT_OTHER) return p.strict_reference ? 8 : 0;
+    return (uint64_t)sa_bytes_per_iq(p.dtype);
+}
+
+// rows of a strict_zero request: every readable frame is 20 log10(0 + 1e-10) = -200 dB (10 log10(1e-20) in power
+// mode), frames past the end are eof_fill
+__global__ void strict_fill_kernel(const SpecArgs a, const int nfft) {
+    const long long frame = blockIdx.x;
+    const bool readable = a.start_sample + frame * a.hop + nfft <= a.n_samples;      // MainController.java:987
+    const double v = readable ? -200.0 : a.eof_fill;
+    const size_t row = (size_t)frame * nfft;
+    for (int k = threadIdx.x; k < nfft; k += blockDim.x) {
+        if (a.out_kind == OUT_F32_DB) reinterpret_cast<float*>(a.out)[row + k] = (float)v;
+        else if (a.out_kind == OUT_F64_DB) reinterpret_cast<double*>(a.out)[row + k] = v;
+        else reinterpret_cast<uint32_t*>(a.out)[row + k] = colormap_rgba((float)v, a);
+    }
+}
+
 static size_t out_elem_bytes(int out_kind) { return out_kind == SA_OUT_F64_DB ? 8 : 4; }
 
 // Validates a request and resolves precision; returns SA_OK or an error.
@@ -499,7 +523,9 @@ int check_spec_params(const sa_spectrogram_params* p, int* prec_out) {
     if (!p) return set_error(SA_ERR_INVALID_ARG, "params is NULL");
     if (p->struct_size != sizeof(sa_spectrogram_params))
         return set_error(SA_ERR_INVALID_ARG, "params.struct_size %u != %zu", p->struct_size, sizeof(sa_spectrogram_params));
-    if (sa_bytes_per_iq(p->dtype) == 0) return set_error(SA_ERR_INVALID_ARG, "unknown dtype %d", p->dtype);
+    if (p->dtype == SA_DT_OTHER && !p->strict_reference)
+        return set_error(SA_ERR_UNSUPPORTED, "datatype without a decode branch (SA_DT_OTHER) needs strict_reference");
+    if (spec_bytes_per_iq(*p) == 0) return set_error(SA_ERR_INVALID_ARG, "unknown dtype %d", p->dtype);
     if (!is_pow2(p->nfft))   // commons-math3 throws MathIllegalArgumentException (SpectralService.java:29)
         return set_error(SA_ERR_INVALID_ARG, "nfft %u is not a power of two", p->nfft);
     if (p->nfft < 64 || p->nfft > 65536)
@@ -522,7 +548,7 @@ int check_spec_params(const sa_spectrogram_params* p, int* prec_out) {
     int prec = p->precision;
     if (prec == SA_PREC_AUTO) prec = (p->dtype == SA_CF64) ? SA_PREC_F64 : SA_PREC_F32;
     if (prec != SA_PREC_F32 && prec != SA_PREC_F64) return set_error(SA_ERR_INVALID_ARG, "unknown precision %d", p->precision);
-    if (p->dtype == SA_CF64 && prec == SA_PREC_F32)
+    if (p->dtype == SA_CF64 && prec == SA_PREC_F32 && !p->strict_reference)
         return set_error(SA_ERR_UNSUPPORTED, "cf64 input runs on the FP64 path only");
     *prec_out = prec;
     return SA_OK;
@@ -550,6 +576,21 @@ int Engine::launch_spectrogram(const void* d_iq, uint64_t n_samples, const sa_sp
         a.inv_range = (float)(1.0 / (p.max_db - p.min_db));
         a.cmap_bias = (float)(-(conv + p.min_db) / (p.max_db - p.min_db));
         a.cmap = p.colormap;
+    }
+    if (strict_zero(p)) {                  // no sample is ever read
+        for (uint64_t f0 = 0; f0 < p.n_frames; f0 += 65535u * 1024u) {
+            const unsigned nf = (unsigned)std::min<uint64_t>(p.n_frames - f0, 65535u * 1024u);
+            SpecArgs b = a;
+            b.start_sample = a.start_sample + (long long)(f0 * p.hop);
+            b.out = (char*)d_out + f0 * p.nfft * out_elem_bytes(p.out_kind);
+            int n = (int)p.nfft;
+            void* fargs[] = { &b, &n };
+            cudaError_t fe = cudaLaunchKernel((const void*)&strict_fill_kernel, dim3(nf), dim3(256), fargs, 0, stream);
+            if (fe != cudaSuccess) return cuda_fail(fe, "launch strict_fill_kernel");
+            launches++;
+        }
+        last_kernel = "strict_fill_kernel";
+        return SA_OK;
     }
     // transforms too large for one SM's shared memory take the four-step path
     if (p.nfft > 16384 || (prec == SA_PREC_F64 && p.nfft > 8192))
@@ -679,7 +720,8 @@ int Engine::ensure_slot(Slot& s, size_t in_bytes, size_t out_bytes) {
 // slot c % kSlots' stream, so copies of one chunk overlap the kernel of another.
 int Engine::spectrogram_host(const HostSource& hs, uint64_t iq_bytes, const sa_spectrogram_params& p, int prec, void* out) {
     const void* iq = hs.ptr;
-    const uint64_t bps = (uint64_t)sa_bytes_per_iq(p.dtype);
+    const uint64_t bps = spec_bytes_per_iq(p);
+    const bool no_data = strict_zero(p);
     const uint64_t n_samples = iq_bytes / bps;
     const uint64_t obytes = out_elem_bytes(p.out_kind);
     const uint64_t row_bytes = (uint64_t)p.nfft * obytes;
@@ -708,7 +750,7 @@ int Engine::spectrogram_host(const HostSource& hs, uint64_t iq_bytes, const sa_s
         uint64_t s_end = s_begin + (nf - 1) * p.hop + p.nfft;
         if (s_end > n_samples) s_end = n_samples;             // frames past EOF become fill rows
         const uint64_t ns = s_end > s_begin ? s_end - s_begin : 0;
-        if (ns) {
+        if (ns && !no_data) {
             const void* src = (const char*)iq + s_begin * bps;
             if (hs.fd >= 0) {                                  // parallel pread straight into the pinned ring
                 if (!host_read(s.h_in, hs.fd, hs.file_off + s_begin * bps, ns * bps)) {
@@ -757,6 +799,10 @@ Engine::~Engine() {
         if (large_aux[i]) cudaStreamDestroy(large_aux[i]);
         for (int j = 0; j < 2; j++) if (large_ev[i][j]) cudaEventDestroy(large_ev[i][j]);
     }
+    if (h_plan) cudaFreeHost(h_plan);
+    if (plan_ev) cudaEventDestroy(plan_ev);
+    if (dc_aux) cudaStreamDestroy(dc_aux);
+    for (int j = 0; j < 2; j++) if (dc_ev[j]) cudaEventDestroy(dc_ev[j]);
     delete copy_pool;
     for (auto& r : registered) cudaHostUnregister(const_cast<void*>(r));
     for (int i = 0; i < kScratch; i++) if (scratch[i]) cudaFree(scratch[i]);
@@ -898,7 +944,7 @@ int32_t sa_spectrogram_device(sa_engine* engine, const void* d_iq, uint64_t iq_b
     int rc = check_spec_params(params, &prec);
     if (rc) return rc;
     if (!d_out || (!d_iq && iq_bytes)) return set_error(SA_ERR_INVALID_ARG, "NULL buffer");
-    const uint64_t bps = (uint64_t)sa_bytes_per_iq(params->dtype);
+    const uint64_t bps = spec_bytes_per_iq(*params);
     if ((uintptr_t)d_iq % bps) return set_error(SA_ERR_INVALID_ARG, "d_iq must be aligned to %llu bytes", (unsigned long long)bps);
     const uint64_t need = params->n_frames * (uint64_t)params->nfft * out_elem_bytes(params->out_kind);
     if (out_bytes < need) return set_error(SA_ERR_SMALL_OUTPUT, "out_bytes %llu < %llu", (unsigned long long)out_bytes, (unsigned long long)need);
@@ -964,17 +1010,19 @@ int32_t sa_compute_magnitudes(sa_engine* engine, const void* buffer, uint64_t ca
     sa_spectrogram_params_init(&p);
     p.dtype = dtype; p.big_endian = big_endian; p.nfft = nfft; p.hop = nfft; p.n_frames = 1;
     p.out_kind = SA_OUT_F64_DB;
+    p.strict_reference = engine->profile.strict_reference;      // the engine's profile: zeros for cf64 / unknown datatypes
     int prec = 0;
     int rc = check_spec_params(&p, &prec);
     if (rc) return rc;
     if (!buffer || !out) return set_error(SA_ERR_INVALID_ARG, "NULL buffer");
-    const uint64_t bps = (uint64_t)sa_bytes_per_iq(dtype);
-    // buffer.getShort/getFloat past the limit throws IndexOutOfBoundsException in Java
-    if (start_byte > capacity_bytes || (uint64_t)nfft * bps > capacity_bytes - start_byte)
+    const uint64_t bps = spec_bytes_per_iq(p);
+    // buffer.getShort/getFloat past the limit throws IndexOutOfBoundsException in Java (nothing is read for the
+    // datatypes that decode to zeros)
+    if (!strict_zero(p) && (start_byte > capacity_bytes || (uint64_t)nfft * bps > capacity_bytes - start_byte))
         return set_error(SA_ERR_OUT_OF_RANGE, "frame [%llu, +%llu) exceeds capacity %llu", (unsigned long long)start_byte,
                          (unsigned long long)(nfft * bps), (unsigned long long)capacity_bytes);
     HostSource hs;
-    hs.ptr = (const char*)buffer + start_byte;
+    hs.ptr = (const char*)buffer + (strict_zero(p) ? 0 : start_byte);
     return engine->spectrogram_host(hs, (uint64_t)nfft * bps, p, prec, out);
 }
 

@@ -25,6 +25,7 @@ int dtype_kind(int dtype);
 bool host_ptr_is_pinned(const void* p);     // pinned / registered host memory (DMA-able as is)
 int check_spec_params(const sa_spectrogram_params* p, int* prec_out);   // validates, resolves precision
 void fill_load_params(LoadParams& lp, const void* base, int dtype, int big_endian);
+uint64_t spec_bytes_per_iq(const sa_spectrogram_params& p);   // Global.getBytesPerSample, strict_reference aware
 
 // Where the host pipeline takes a capture's bytes from: caller memory (pinned: DMA source as is; pageable:
 // parallel memcpy into the pinned ring) or an open file (parallel pread straight into the pinned ring).
@@ -34,8 +35,20 @@ struct HostSource {
     uint64_t file_off = 0;          // byte offset of sample 0 in the file (core:header_bytes, SigMfHelper.java:59-67)
 };
 
+// The engine's analysis profile: what JDSP decides inside Resampler.downConvert* / calculatePsdWelch
+// (sa_analysis_config, include/sa_engine.h); defaults = the repository's documented spec.
+struct AnalysisProfile {
+    std::vector<double> taps;                 // empty: built-in Hamming-windowed sinc, 8*down+1 taps
+    int delay_mode = SA_DELAY_CAUSAL;
+    int length_mode = SA_LEN_FLOOR;
+    int psd_scaling = SA_PSD_DENSITY;
+    int psd_detrend = SA_DETREND_NONE;
+    int psd_precision = SA_PREC_F32;
+    int strict_reference = 0;
+};
+
 constexpr int kSlots = 3;
-constexpr int kScratch = 12;
+constexpr int kScratch = 14;
 
 struct Slot {
     cudaStream_t stream = nullptr;
@@ -87,10 +100,18 @@ struct Engine {
     // [3] canvas / canvas dB rows, [4] signal lists of the packer / series kernels,
     // [5..7] four-step FFT workspaces of the host pipeline's slots (their chunks run concurrently on three streams)
     // [8..11] second four-step workspace of the same callers (two-stream chunk overlap, launch_spectrogram_large)
+    // [12] FP32 rows the downconverter hands to the Welch kernels (two halves, reused batch after batch: L2 resident),
+    // [13] Welch plan + partial spectra of the helper stream's batches
     void* scratch[kScratch] = {};
     size_t scratch_cap[kScratch] = {};
     cudaStream_t large_aux[4] = {};                  // helper stream per four-step caller (device API, slots 0..2)
     cudaEvent_t large_ev[4][2] = {};                 // fork / join events of that helper stream
+    AnalysisProfile profile;                         // sa_set_analysis_config
+    cudaStream_t dc_aux = nullptr;                   // annotation batches alternate between the caller's stream and this one
+    cudaEvent_t dc_ev[2] = {};                       // fork / join
+    void* h_plan = nullptr; size_t h_plan_cap = 0;   // pinned staging of a call's annotation / tap / Welch plans
+    cudaEvent_t plan_ev = nullptr;                   // the last upload from h_plan has completed
+    std::map<const void*, size_t> dc_smem_set;       // dynamic shared memory limit already granted per kernel
 
     ~Engine();
     int twiddle_table(const SpecKernelInfo& k, const void** d_tab);

@@ -225,7 +225,7 @@ large_onchip_kernel(const LargeArgs a, const __grid_constant__ CUtensorMap tmap)
     static_assert(sizeof(raw_t) == sizeof(cpx<T>), "the raw slice and A[k1][n2] share the X buffer");
     constexpr int P = G::P, TPF = G::TPF, N = OG::N, N2 = OG::N2, C = OG::C, COLS = OG::COLS, GROUPS = OG::GROUPS;
     static_assert(GROUPS == 2 && TPF == 16 && P == 16, "geometry of the 256-point plans");
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const double* ltab = nullptr;
     if constexpr (sizeof(T) == 8 && SA_F64_FAST_DB) {
         __shared__ double s_ltab[128];

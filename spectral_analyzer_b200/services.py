@@ -39,6 +39,7 @@ class Engine:
         self._h = C.c_void_p()
         _capi.check(_capi.lib().sa_engine_create(device, C.byref(self._h)))
         self.device = device
+        self._strict = False
 
     def close(self):
         if self._h:
@@ -59,6 +60,40 @@ class Engine:
     def kernel_launches(self):
         return int(_capi.lib().sa_kernel_launches(self._h))
 
+    # ---- analysis profile: the choices JDSP makes inside downConvert / calculatePsdWelch (sa_analysis_config) ----
+    def set_analysis_config(self, taps=None, delay="causal", length="floor", psd_scaling="density", psd_detrend=None,
+                            psd_precision="f32", strict_reference=False):
+        c = _capi.AnalysisConfig()
+        _capi.lib().sa_analysis_config_init(C.byref(c))
+        keep = None
+        if taps is not None:
+            keep = np.ascontiguousarray(taps, np.float64)
+            c.taps = keep.ctypes.data_as(C.POINTER(C.c_double))
+            c.n_taps = keep.size
+        c.delay_mode, c.length_mode = _capi.DELAY[delay], _capi.LENGTH[length]
+        c.psd_scaling, c.psd_detrend = _capi.PSD_SCALING[psd_scaling], _capi.DETREND[psd_detrend]
+        c.psd_precision = {"f32": _capi.PREC_F32, "f64": _capi.PREC_F64}[psd_precision]
+        c.strict_reference = int(bool(strict_reference))
+        _capi.check(_capi.lib().sa_set_analysis_config(self._h, C.byref(c)))      # the engine copies the taps
+        self._strict = bool(strict_reference)
+
+    def reset_analysis_config(self):
+        _capi.check(_capi.lib().sa_set_analysis_config(self._h, None))
+        self._strict = False
+
+    def analysis_config(self):
+        c = _capi.AnalysisConfig()
+        _capi.check(_capi.lib().sa_get_analysis_config(self._h, C.byref(c)))
+        inv = lambda d, v: [k for k, x in d.items() if x == v and isinstance(k, str)][0]
+        return {"taps": None if not c.n_taps else np.array([c.taps[i] for i in range(c.n_taps)]),
+                "delay": inv(_capi.DELAY, c.delay_mode), "length": inv(_capi.LENGTH, c.length_mode),
+                "psd_scaling": inv(_capi.PSD_SCALING, c.psd_scaling), "psd_detrend": inv(_capi.DETREND, c.psd_detrend),
+                "psd_precision": "f64" if c.psd_precision == _capi.PREC_F64 else "f32",
+                "strict_reference": bool(c.strict_reference)}
+
+    def downconvert_length(self, count, down, fast=False):
+        return int(_capi.lib().sa_downconvert_length(self._h, count, down, int(bool(fast))))
+
     def register_host(self, buffer, read_only=True):
         _, ptr, n = _host_view(buffer)
         _capi.check(_capi.lib().sa_register_host(self._h, ptr, n, int(read_only)))
@@ -70,9 +105,10 @@ class Engine:
     # ---- spectrogram ----
     def make_params(self, datatype, nfft, hop=None, window="rect", n_frames=0, start_sample=0,
                     db_mode=_capi.DB_MAG_1E10, out="f32", precision="auto", eof_fill_db=-150.0,
-                    colormap="Grayscale", sample_rate=1.0, min_db=-160.0, max_db=-30.0):
+                    colormap="Grayscale", sample_rate=1.0, min_db=-160.0, max_db=-30.0, strict_reference=False):
         p = _capi.default_params()
-        p.dtype, p.big_endian = _capi.parse_datatype(datatype)
+        p.dtype, p.big_endian = _capi.parse_datatype(datatype, strict_reference)
+        p.strict_reference = int(bool(strict_reference))
         p.nfft = nfft
         p.hop = nfft if hop is None else hop
         p.window = _capi.WINDOW[window]
@@ -130,10 +166,10 @@ class Engine:
     # ---- downconvert / PSD ----
     def downconvert(self, buffer, datatype, start_sample, count, freq_off, down, fast=False):
         _, ptr, nbytes = _host_view(buffer)
-        dt, be = _capi.parse_datatype(datatype)
+        dt, be = _capi.parse_datatype(datatype, self._strict)
         if down < 1:
             raise EngineError(1, "down must be >= 1")
-        m = count // down
+        m = self.downconvert_length(count, down, fast)
         out = np.empty((2, max(m, 1)), np.float64)
         n = C.c_uint64(0)
         dp = C.POINTER(C.c_double)
@@ -157,14 +193,16 @@ class Engine:
         """annotations: iterable of (start_sample, count, freq_off, down, fast).
         Returns (list of [2, M_a] float64 arrays or None, [n_ann, psd_nfft] float64 or None)."""
         _, ptr, nbytes = _host_view(buffer)
-        dt, be = _capi.parse_datatype(datatype)
+        dt, be = _capi.parse_datatype(datatype, self._strict)
         anns = (_capi.Annotation * len(annotations))()
         offs = (C.c_uint64 * len(annotations))()
         total = 0
+        lens = []
         for i, (s, c, f, d, fast) in enumerate(annotations):
             anns[i] = _capi.Annotation(int(s), int(c), float(f), int(d), int(bool(fast)))
             offs[i] = total
-            total += 2 * (int(c) // int(d))
+            lens.append(self.downconvert_length(int(c), int(d), fast))
+            total += 2 * lens[-1]
         out_iq = np.empty(max(total, 1), np.float64) if want_iq else None
         out_psd = np.empty((len(annotations), psd_nfft), np.float64) if want_psd else None
         dp = C.POINTER(C.c_double)
@@ -175,8 +213,8 @@ class Engine:
         iq_list = None
         if want_iq:
             iq_list = []
-            for i, (s, c, f, d, fast) in enumerate(annotations):
-                m = int(c) // int(d)
+            for i in range(len(annotations)):
+                m = lens[i]
                 iq_list.append(out_iq[offs[i]:offs[i] + 2 * m].reshape(2, m))
         return iq_list, out_psd
 
@@ -243,7 +281,7 @@ class SpectralService:
         (commons-math3 MathIllegalArgumentException) and OUT_OF_RANGE for reads past the buffer
         (IndexOutOfBoundsException)."""
         _, ptr, nbytes = _host_view(buffer)
-        dt, be = _capi.parse_datatype(datatype)
+        dt, be = _capi.parse_datatype(datatype, self.engine._strict)
         out = np.empty(nfft, np.float64)
         _capi.check(_capi.lib().sa_compute_magnitudes(self.engine.handle, ptr, nbytes, startByte, nfft, dt, be,
                                                       out.ctypes.data_as(C.POINTER(C.c_double))))

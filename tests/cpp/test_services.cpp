@@ -75,6 +75,31 @@ int main() {
         }
         EXPECT(cache.hits() > 0 && cache.misses() > 0);
     }
+    // the annotation batch of AnnotationController.java:321-360 as one call: rows equal the per-annotation service,
+    // PSD rows equal calculatePsdWelch of each row; a short annotation follows the single-window rule (rest NaN)
+    {
+        std::vector<ExtractDownConvertService::Annotation> rows = { {0, 4 * n, 37.0 / n, 4}, {512, 2048, -0.1, 8}, {100, 900, 0.2, 4} };
+        std::vector<double> psd_rows;
+        auto batch = dc.extractAndDownConvertBatch(buf, "cf32_le", 1.0e6, rows, 256, &psd_rows);
+        EXPECT(batch.size() == rows.size() && psd_rows.size() == rows.size() * 256);
+        for (size_t i = 0; i < rows.size(); i++) {
+            auto one = dc.extractAndDownConvert(buf, rows[i].startSample, rows[i].count, "cf32_le", rows[i].freqOff, rows[i].down);
+            EXPECT(batch[i][0] == one[0] && batch[i][1] == one[1]);
+            const int m = (int)one[0].size(), nf = m < 256 ? m : 256;
+            auto p1 = PowerSpectralDensity::calculatePsdWelch(eng, one, 1.0e6 / rows[i].down, nf);
+            for (int k = 0; k < nf; k++) EXPECT(std::fabs(psd_rows[i * 256 + k] - p1[1][k]) < 1e-9);
+            for (int k = nf; k < 256; k++) EXPECT(std::isnan(psd_rows[i * 256 + k]));
+        }
+        // a JDSP profile with delay compensation and ceil length: one more output, the DC tone settles 4*down samples earlier
+        sa_analysis_config cfg;
+        sa_analysis_config_init(&cfg);
+        cfg.delay_mode = SA_DELAY_SAME; cfg.length_mode = SA_LEN_CEIL;
+        eng.setAnalysisConfig(cfg);
+        auto zs = dc.extractAndDownConvert(buf, 0, 4 * n - 3, "cf32_le", 37.0 / n, 4);
+        EXPECT(zs[0].size() == (size_t)n);                              // ceil((4n - 3) / 4)
+        EXPECT(std::fabs(zs[0][4] - 1.0) < 1e-3 && std::fabs(z[0][4] - 1.0) > 1e-3);    // all 33 taps overlap data at m = 4 only when centred
+        eng.resetAnalysisConfig();
+    }
     std::printf("cpp services ok\n");
     return 0;
 }

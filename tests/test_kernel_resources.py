@@ -60,9 +60,11 @@ def test_register_and_stack_budgets():
     # no kernel anywhere keeps a large local frame
     worst = max(res.items(), key=lambda kv: kv[1]["STACK"])
     assert worst[1]["STACK"] <= 256, worst
-    # downconverter: 64 registers -> 4 CTAs of 256 threads per SM
+    # downconverter: 64 registers -> 4 CTAs of 256 threads per SM; the pipelined variant (template flag PIPE, "ELb1ELb1E")
+    # carries the next tile's 17 raw samples in registers: <= 85 registers -> 3 CTAs per SM
     dc = {k: v for k, v in res.items() if "downconvert_kernel" in k}
-    assert dc and all(v["REG"] <= 64 for v in dc.values()), dc
+    assert dc and any("ELb1ELb1E" in k for k in dc)
+    assert all(v["REG"] <= (85 if "ELb1ELb1E" in k else 64) and v["STACK"] <= 64 for k, v in dc.items()), dc
 
 
 def count(text, pattern):

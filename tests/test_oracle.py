@@ -201,3 +201,48 @@ def test_analysis_series_known_answers_and_golden():
     nm, nf = no.analysis_series(a["dc"], 250e3, 0.2, 0.05, 915e6)
     assert np.abs(cm - g["mag"]).max() < 1e-10 and np.abs(cf[1:] - g["frq"][1:]).max() < 1e-5
     assert np.abs(cm - nm).max() < 1e-10 and np.abs(cf[1:] - nf[1:]).max() < 1e-5
+
+
+@pytest.mark.parametrize("n", [63, 777, 1000, 1024])
+@pytest.mark.parametrize("scaling,detrend", [("density", None), ("spectrum", "constant"), ("density", "constant")])
+def test_welch_any_length_against_scipy(n, scaling, detrend):
+    """ora_psd_welch_ex (any transform length; the reference's short-signal branch passes nfft = N,
+    AnalysisDialogController.java:304-307) against scipy.signal.welch: segments, scaling, mean removal, axis."""
+    import scipy.signal as ss
+    rng = np.random.default_rng(n)
+    x = rng.normal(size=3 * n + 5) + 1j * rng.normal(size=3 * n + 5) + (1.5 - 0.5j)
+    iq = np.stack([x.real, x.imag])
+    hop = max(1, n // 4)
+    f, d = co.psd_welch(iq, 1e3, n, hop=hop, window="hann", cfg=co.analysis_cfg(scaling=scaling, detrend=detrend))
+    fr, p = ss.welch(x, fs=1e3, window=ss.get_window("hann", n, fftbins=True), nperseg=n, noverlap=n - hop, nfft=n,
+                     detrend=detrend if detrend else False, return_onesided=False, scaling=scaling)
+    assert np.abs(d - 10 * np.log10(np.fft.fftshift(p) + 1e-30)).max() < 1e-8
+    assert np.allclose(f, np.fft.fftshift(fr))
+
+
+@pytest.mark.parametrize("delay", ["causal", "same", "valid"])
+@pytest.mark.parametrize("length", ["floor", "ceil"])
+@pytest.mark.parametrize("down,ntaps", [(4, None), (4, 21), (7, 100)])
+def test_downconvert_profile_against_scipy(delay, length, down, ntaps):
+    """ora_downconvert_ex: taps, delay compensation and length rule against numpy / scipy.signal.lfilter."""
+    import scipy.signal as ss
+    count, start, f = 5003, 11, 0.0917
+    raw = synth.recording(count + start, "cf32_le", seed=12)
+    taps = None
+    if ntaps:
+        taps = ss.firwin(ntaps, 1.0 / down)
+    cfg = co.analysis_cfg(taps=taps, delay=delay, length=length)
+    got = co.downconvert_ex(raw, "cf32_le", start, count, f, down, False, cfg)
+    h = taps if taps is not None else co.lowpass_taps(down)
+    x = np.frombuffer(raw.tobytes(), np.complex64)[start:start + count].astype(np.complex128)
+    y = x * np.exp(-2j * np.pi * np.mod(f * np.arange(count), 1.0))
+    L = len(h)
+    off = {"causal": 0, "same": (L - 1) // 2, "valid": L - 1}[delay]
+    full = ss.lfilter(h, 1.0, np.concatenate([y, np.zeros(off + down)]))       # full[n] = sum h[k] y[n - k], zero tail
+    if delay == "valid":
+        m = (count - L) // down + 1 if count >= L else 0
+    else:
+        m = count // down if length == "floor" else -(-count // down)
+    ref = full[off + down * np.arange(m)]
+    assert got.shape == (2, m)
+    assert np.abs(got[0] + 1j * got[1] - ref).max() < 1e-12
