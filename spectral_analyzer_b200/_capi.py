@@ -85,6 +85,8 @@ def lib():
     L.sa_spectrogram_file.argtypes = [vp, C.c_char_p, u64, u64, C.POINTER(SpectrogramParams), vp, u64]
     L.sa_last_kernel_name.restype = C.c_char_p
     L.sa_last_kernel_name.argtypes = [vp]
+    # ablation only (csrc/tc_ablation.cu): not declared in include/sa_engine.h, not part of the drop-in boundary
+    L.sa_ablation_tc_spectrogram_device.argtypes = [vp, vp, u64, C.POINTER(SpectrogramParams), vp, u64, i32, vp]
     L.sa_compute_magnitudes.argtypes = [vp, vp, u64, u64, u32, i32, i32, dp]
     L.sa_downconvert.argtypes = [vp, vp, u64, i32, i32, u64, u64, dbl, i32, i32, dp, dp, C.POINTER(u64)]
     L.sa_lowpass_taps.argtypes = [i32, dp]
