@@ -41,6 +41,23 @@ void fill_canvas_args(CanvasArgs& ca, const sa_spectrogram_params& p, uint32_t w
     ca.cmap_bias = (float)(-(conv + p.min_db) / (p.max_db - p.min_db));
 }
 
+// second stage of the fused pooling: acc (|X|^2 reduced over each column's frames) -> pixels of columns [col0, col0 + ncols)
+int launch_canvas_power(Engine* eng, const CanvasArgs& ca, const sa_spectrogram_params& p, const float* d_acc, int col0,
+                        int ncols, cudaStream_t stream) {
+    CanvasPowerArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.acc = d_acc; pa.out = ca.out;
+    pa.nfft = ca.nfft; pa.canvas_w = ca.canvas_w; pa.canvas_h = ca.canvas_h; pa.col0 = col0; pa.ncols = ncols;
+    pa.reduce = ca.reduce; pa.cmap = ca.cmap; pa.db_mode = p.db_mode;
+    pa.inv_count = 1.0f / (float)ca.fpc;
+    pa.inv_range = ca.inv_range; pa.cmap_bias = ca.cmap_bias;
+    void* args[] = { &pa };
+    cudaError_t e = cudaLaunchKernel((const void*)&canvas_power_kernel, dim3((ca.canvas_h + 255) / 256, ncols), dim3(256), args, 0, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "launch canvas_power_kernel");
+    eng->launches++;
+    return SA_OK;
+}
+
 int launch_canvas(Engine* eng, CanvasArgs& ca, const float* d_db, int col0, int ncols, cudaStream_t stream) {
     ca.db = d_db; ca.col0 = col0; ca.ncols = ncols;
     void* args[] = { &ca };
@@ -83,11 +100,26 @@ int32_t sa_render_canvas_device(sa_engine* engine, const void* d_iq, uint64_t iq
     const uint64_t bps = spec_bytes_per_iq(q);
     if ((uintptr_t)d_iq % bps) return set_error(SA_ERR_INVALID_ARG, "d_iq must be aligned to %llu bytes", (unsigned long long)bps);
     cudaStream_t stream = (cudaStream_t)cuda_stream;
+    CanvasArgs ca;
+    fill_canvas_args(ca, q, canvas_w, canvas_h, frames_per_column, reduce, (uint32_t*)d_out_rgba);
+    static const char* fuse_env = getenv("SA_CANVAS_FUSED");
+    const bool fuse_ok = !(fuse_env && atoi(fuse_env) == 0);
+    if (reduce != SA_REDUCE_NEAREST && fuse_ok && Engine::can_pool(q, prec) && canvas_w <= 65535) {
+        // MAX / MEAN: the frame reduction happens in the spectrogram epilogue (no dB rows are ever written); one launch
+        // over all frames, then one small kernel over the canvas
+        const size_t acc_bytes = (size_t)canvas_w * q.nfft * sizeof(float);
+        rc = engine->ensure_scratch(3, acc_bytes);
+        if (rc) return rc;
+        cudaError_t e = cudaMemsetAsync(engine->scratch[3], 0, acc_bytes, stream);
+        if (e != cudaSuccess) return cuda_fail(e, "clear pooling accumulator");
+        rc = engine->launch_spectrogram(d_iq, iq_bytes / bps, q, prec, engine->scratch[3], stream, 2, reduce == SA_REDUCE_MAX ? 1 : 2,
+                                        frames_per_column);
+        if (rc) return rc;
+        return launch_canvas_power(engine, ca, q, (const float*)engine->scratch[3], 0, (int)canvas_w, stream);
+    }
     const uint64_t cpc = canvas_cols_per_chunk(q, frames_per_column, canvas_w, 4 * kCanvasChunkBytes);
     rc = engine->ensure_scratch(3, cpc * frames_per_column * q.nfft * 4);
     if (rc) return rc;
-    CanvasArgs ca;
-    fill_canvas_args(ca, q, canvas_w, canvas_h, frames_per_column, reduce, (uint32_t*)d_out_rgba);
     for (uint64_t c0 = 0; c0 < canvas_w; c0 += cpc) {
         const uint64_t nc = std::min<uint64_t>(cpc, canvas_w - c0);
         sa_spectrogram_params r = q;
@@ -161,6 +193,8 @@ int32_t sa_render_canvas(sa_engine* engine, const void* iq, uint64_t iq_bytes, c
         return SA_OK;
     }
     // chunk c: H2D of its samples -> spectrogram -> canvas columns, on slot c % kSlots; only the canvas comes back
+    static const char* fuse_env = getenv("SA_CANVAS_FUSED");
+    const bool fused = reduce != SA_REDUCE_NEAREST && !(fuse_env && atoi(fuse_env) == 0) && Engine::can_pool(q, prec);
     const bool in_pinned = host_ptr_is_pinned(iq);
     uint64_t c = 0;
     cudaError_t e = cudaSuccess;
@@ -187,6 +221,15 @@ int32_t sa_render_canvas(sa_engine* engine, const void* iq, uint64_t iq_bytes, c
         sa_spectrogram_params r = q;
         r.start_sample = 0;
         r.n_frames = nf;
+        if (fused) {                       // the chunk's columns are reduced in the spectrogram epilogue (no dB rows)
+            e = cudaMemsetAsync(s.d_out, 0, (size_t)nc * q.nfft * sizeof(float), s.stream);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "clear pooling accumulator"); break; }
+            rc = engine->launch_spectrogram(s.d_in, ns, r, prec, s.d_out, s.stream, 5 + (int)(c % kSlots),
+                                            reduce == SA_REDUCE_MAX ? 1 : 2, frames_per_column);
+            if (rc) break;
+            rc = launch_canvas_power(engine, ca, q, (const float*)s.d_out, (int)c0, (int)nc, s.stream);
+            continue;
+        }
         rc = engine->launch_spectrogram(s.d_in, ns, r, prec, s.d_out, s.stream, 5 + (int)(c % kSlots));
         if (rc) break;
         rc = launch_canvas(engine, ca, (const float*)s.d_out, (int)c0, (int)nc, s.stream);

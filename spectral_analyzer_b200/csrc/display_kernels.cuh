@@ -82,6 +82,36 @@ canvas_kernel(const CanvasArgs a) {
     a.out[(size_t)(a.canvas_h - 1 - f) * a.canvas_w + a.col0 + col] = px;      // :1288 y flipped
 }
 
+// Second stage of the fused pooling: acc[col][bin] holds max / sum over the column's frames of |X|^2 (spectrogram
+// epilogue, pool_mode); pixel (col, f) reduces the bins [bin(f), bin(f+1)) of its column, takes the level once and
+// colours it.  One thread per pixel, consecutive threads = consecutive pixel rows (adjacent bin ranges: coalesced).
+struct CanvasPowerArgs {
+    const float* acc;       // [ncols][nfft]
+    uint32_t*    out;
+    int nfft, canvas_w, canvas_h, col0, ncols;
+    int reduce, cmap, db_mode;
+    float inv_count;        // MEAN: 1 / frames per column
+    float inv_range, cmap_bias;
+};
+
+__global__ void __launch_bounds__(256)
+canvas_power_kernel(const CanvasPowerArgs a) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    const int col = blockIdx.y;
+    if (f >= a.canvas_h) return;
+    const int b0 = (int)((double)f / (double)a.canvas_h * (double)a.nfft);          // MainController.java:1280
+    int b1 = (int)((double)(f + 1) / (double)a.canvas_h * (double)a.nfft);
+    if (b1 <= b0) b1 = b0 + 1;
+    if (b1 > a.nfft) b1 = a.nfft;
+    const float* r = a.acc + (size_t)col * a.nfft;
+    float p = 0.f;
+    if (a.reduce == REDUCE_MAX) { for (int b = b0; b < b1; b++) p = fmaxf(p, r[b]); }
+    else { for (int b = b0; b < b1; b++) p += r[b]; p *= a.inv_count / (float)(b1 - b0); }
+    const float db = a.db_mode == DBM_MAG_1E10 ? 6.02059991327962f * log2f(sqrtf(p) + 1e-10f) : 3.01029995663981f * log2f(p + 1e-20f);
+    const uint32_t px = a.cmap == 1 ? colormap_px<1>(db, a.inv_range, a.cmap_bias) : colormap_px<0>(db, a.inv_range, a.cmap_bias);
+    a.out[(size_t)(a.canvas_h - 1 - f) * a.canvas_w + a.col0 + col] = px;            // :1288 y flipped
+}
+
 // ---------------- N3 ----------------
 enum { PACK_F32 = 0, PACK_I16 = 1 };
 

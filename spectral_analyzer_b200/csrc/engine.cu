@@ -556,7 +556,7 @@ int check_spec_params(const sa_spectrogram_params* p, int* prec_out) {
 
 // Launches the fused spectrogram kernel on device-resident samples.
 int Engine::launch_spectrogram(const void* d_iq, uint64_t n_samples, const sa_spectrogram_params& p, int prec,
-                               void* d_out, cudaStream_t stream, int ws) {
+                               void* d_out, cudaStream_t stream, int ws, int pool_mode, uint64_t pool_fpc) {
     if (p.n_frames == 0) return SA_OK;
     const int dk = dtype_kind(p.dtype);
     const int win = (prec == SA_PREC_F64) ? 1 : (p.window != SA_WIN_RECT ? 1 : 0);
@@ -576,6 +576,16 @@ int Engine::launch_spectrogram(const void* d_iq, uint64_t n_samples, const sa_sp
         a.inv_range = (float)(1.0 / (p.max_db - p.min_db));
         a.cmap_bias = (float)(-(conv + p.min_db) / (p.max_db - p.min_db));
         a.cmap = p.colormap;
+    }
+    if (pool_mode) {
+        if (!can_pool(p, prec) || strict_zero(p)) return set_error(SA_ERR_UNSUPPORTED, "fused pooling covers the in-SM transforms only");
+        a.pool_mode = pool_mode;
+        a.pool_fpc = (long long)std::max<uint64_t>(1, pool_fpc);
+        a.pool_magic = a.pool_fpc > 1 ? (unsigned long long)((((unsigned __int128)1 << 64) + (unsigned __int128)(a.pool_fpc - 1)) / (unsigned __int128)a.pool_fpc) : 0ull;
+        // |X|^2 whose level equals eof_fill_db: (10^(dB/20) - 1e-10)^2, or 10^(dB/10) - 1e-20 in power mode
+        const double lin = p.db_mode == SA_DB_MAG_1E10 ? std::max(0.0, std::pow(10.0, p.eof_fill_db / 20.0) - 1e-10)
+                                                       : 0.0;
+        a.pool_eof = (float)(p.db_mode == SA_DB_MAG_1E10 ? lin * lin : std::max(0.0, std::pow(10.0, p.eof_fill_db / 10.0) - 1e-20));
     }
     if (strict_zero(p)) {                  // no sample is ever read
         for (uint64_t f0 = 0; f0 < p.n_frames; f0 += 65535u * 1024u) {
@@ -604,7 +614,8 @@ int Engine::launch_spectrogram(const void* d_iq, uint64_t n_samples, const sa_sp
     // 4096: two radix-64 passes (one exchange) for cf32 / ci16 input; cu8 / ci8 keep the 3-pass kernel (measured)
     static const char* r64_env = getenv("SA_R64");
     const bool use_r64 = r64_env ? (strcmp(r64_env, "all") == 0) : (dk == DK_CF32 || dk == DK_CI16);
-    if (!k && aligned && use_r64 && prec == SA_PREC_F32 && p.nfft == 4096) k = find_spec_kernel(prec, 4096, dk, win, 4);
+    // (the radix-64 kernel has its own store code: pooled launches take the small-radix-first kernel)
+    if (!k && aligned && use_r64 && !pool_mode && prec == SA_PREC_F32 && p.nfft == 4096) k = find_spec_kernel(prec, 4096, dk, win, 4);
     if (!k && aligned && !no_mid) {                                                        // small-radix-first plan
         // the asynchronously staged variant where it measured faster on B200 (tools/mid_pf_matrix.py): 2048 (8 frames
         // per CTA) and 16384 (one frame owns the SM) gain 6-19 %, 4096 (4 frames per CTA) 0-10 %, 8192 loses up to 19 %.

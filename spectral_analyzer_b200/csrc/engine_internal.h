@@ -129,8 +129,11 @@ struct Engine {
     // host pipeline passes 5 + slot so that chunks in flight on different streams never share a workspace)
     int launch_spectrogram_large(const void* d_iq, uint64_t n_samples, const sa_spectrogram_params& p, int prec,
                                  const SpecArgs& base, void* d_out, cudaStream_t stream, int ws);
+    // pool_mode != 0: instead of rows, |X|^2 is reduced (1 max, 2 sum) over the pool_fpc frames of each canvas column into
+    // d_out = float[n_frames / pool_fpc][nfft], which the caller has zeroed (display.cu); transforms up to 16384 points
     int launch_spectrogram(const void* d_iq, uint64_t n_samples, const sa_spectrogram_params& p, int prec,
-                           void* d_out, cudaStream_t stream, int ws = 2);
+                           void* d_out, cudaStream_t stream, int ws = 2, int pool_mode = 0, uint64_t pool_fpc = 1);
+    static bool can_pool(const sa_spectrogram_params& p, int prec) { return p.nfft <= 16384 && !(prec == SA_PREC_F64 && p.nfft > 8192); }
     int spectrogram_host(const HostSource& src, uint64_t iq_bytes, const sa_spectrogram_params& p, int prec, void* out);
 };
 

@@ -35,7 +35,25 @@ struct SpecArgs {
     float       cmap_bias;     // -(conv + min_db) * inv_range, conv = 10*log10(fs/N) + 20*log10(N) (:1273-1274)
     float       inv_range;     // 1/(max_db - min_db), :929
     int         cmap;
+    // display pooling fused into the epilogue (sa_render_canvas with MAX / MEAN): instead of a dB row per frame, |X|^2 is
+    // reduced over the pool_fpc frames of a canvas column into out = float[columns][N] (fft-shifted bins, zero-initialised)
+    int         pool_mode;     // 0: rows; 1: max; 2: sum
+    float       pool_eof;      // |X|^2 whose level is eof_fill (frames past the end of the buffer)
+    long long   pool_fpc;      // frames per canvas column
+    unsigned long long pool_magic;   // ceil(2^64 / pool_fpc) (0 for pool_fpc == 1): column = umul64hi(frame, magic), exact
+                                     // for frame * pool_fpc < 2^64 -- no 64-bit division (F2I / I2F sequences) in the kernels
 };
+__device__ __forceinline__ long long pool_column(const SpecArgs& a, long long frame) {
+    return a.pool_magic ? (long long)__umul64hi((unsigned long long)frame, a.pool_magic) : frame;
+}
+
+// One reduction per bin and frame, 32 consecutive bins per warp instruction: the L2 atomic units see one 128-byte line
+// per instruction, the same number of transactions as the row stores they replace, and the accumulator (columns x N
+// floats, a few MB) never leaves L2.  |X|^2 >= 0, so the unsigned order of the bit patterns is the float order.
+__device__ __forceinline__ void pool_red(float* p, float v, int mode) {
+    if (mode == 1) asm volatile("red.global.max.u32 [%0], %1;" ::"l"(p), "r"(__float_as_uint(v)) : "memory");
+    else asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
 
 #ifndef SA_F64_FAST_DB
 #define SA_F64_FAST_DB 1        // table-driven FP64 dB epilogue (0: library log10 / sqrt)
@@ -171,6 +189,12 @@ template <int DK> __host__ __device__ constexpr int bytes_per_iq_kind() {
 template <typename T, int N>
 __device__ __forceinline__ void store_fill(const SpecArgs& a, const long long frame, const int t) {
     constexpr int P = Geo<T, N>::P, TPF = Geo<T, N>::TPF;
+    if (a.pool_mode) {
+        float* o = reinterpret_cast<float*>(a.out) + (size_t)pool_column(a, frame) * N;
+#pragma unroll
+        for (int q = 0; q < P; q++) pool_red(&o[t + TPF * q], a.pool_eof, a.pool_mode);
+        return;
+    }
     const size_t row = (size_t)frame * N;
     if (a.out_kind == OUT_F32_DB) {
         float* o = reinterpret_cast<float*>(a.out) + row;
@@ -238,6 +262,14 @@ template <typename T, int N>
 __device__ __forceinline__ void store_row(const SpecArgs& a, const long long frame, const int t,
                                           const cpx<T> (&v)[Plan<T, N>::P], const double* ltab = nullptr) {
     constexpr int P = Geo<T, N>::P, TPF = Geo<T, N>::TPF;
+    if (a.pool_mode) {          // |X|^2 only: the logarithm is taken once per pixel by canvas_power_kernel
+        float* o = reinterpret_cast<float*>(a.out) + (size_t)pool_column(a, frame) * N;
+        const int kp = (t + N / 2) & (N - 1);
+#pragma unroll
+        for (int q = 0; q < P; q++)
+            pool_red(&o[(kp + TPF * q) & (N - 1)], (float)fma_t(v[q].x, v[q].x, v[q].y * v[q].y), a.pool_mode);
+        return;
+    }
     T db[P];
     if (a.db_mode == DBM_MAG_1E10) bins_to_db<T, P, DBM_MAG_1E10>(v, db, ltab);
     else bins_to_db<T, P, DBM_POWER>(v, db, ltab);
