@@ -278,3 +278,41 @@ def test_golden_analysis(engine):
     psd = engine.psd_welch(g["dc"], 1e6 / 4, 2048)
     strong = g["psd"][1] > g["psd"][1].max() - 60
     assert np.abs(psd[1] - g["psd"][1])[strong].max() < PSD_TOL_DB
+
+
+def test_analysis_edge_cases(engine, tmp_path):
+    """Empty and degenerate requests of the new entry points: no annotations, annotations without output, valid mode on a
+    span shorter than the filter, PSD-only batches with rows that cannot hold a transform, empty file requests."""
+    raw = synth.recording(50_000, "ci16_le", seed=33)
+    iq, psd = engine.downconvert_psd_batch(raw, "ci16_le", 1e6, [], psd_nfft=256)
+    assert iq == [] and psd.shape == (0, 256)
+    # count < down: no output sample; PSD row all NaN; neighbours unaffected
+    anns = [(100, 7, 0.1, 16, False), (200, 40_000, -0.2, 16, False), (0, 0, 0.0, 4, True), (5, 1000, 0.3, 4, False)]
+    iq, psd = engine.downconvert_psd_batch(raw, "ci16_le", 1e6, anns, psd_nfft=256)
+    assert iq[0].shape == (2, 0) and iq[2].shape == (2, 0) and np.isnan(psd[0]).all() and np.isnan(psd[2]).all()
+    ref1 = co.downconvert(raw, "ci16_le", 200, 40_000, -0.2, 16, False)
+    assert rel_err(iq[1], ref1) < DC_TOL and np.isfinite(psd[1]).all()
+    ref3 = co.downconvert(raw, "ci16_le", 5, 1000, 0.3, 4, False)
+    assert iq[3].shape == (2, 250) and rel_err(iq[3], ref3) < DC_TOL
+    rp = co.psd_welch(ref3, 1e6 / 4, 250)                        # 250 < 256: one window of 250 points, rest NaN
+    top = rp[1] > rp[1].max() - 40
+    assert np.abs(psd[3][:250] - rp[1])[top].max() < 5e-3 and np.isnan(psd[3][250:]).all()
+    _, psd_only = engine.downconvert_psd_batch(raw, "ci16_le", 1e6, anns, psd_nfft=256, want_iq=False)
+    assert np.array_equal(np.isnan(psd), np.isnan(psd_only)) and np.array_equal(psd[1], psd_only[1])
+    # valid mode on a span shorter than the filter: zero outputs, not an error
+    engine.set_analysis_config(delay="valid")
+    try:
+        assert engine.downconvert_length(100, 16) == 0
+        assert engine.downconvert(raw, "ci16_le", 0, 100, 0.1, 16).shape == (2, 0)
+        assert engine.downconvert(raw, "ci16_le", 0, 129, 0.1, 16).shape == (2, 1)       # exactly L = 129 samples: one output
+    finally:
+        engine.reset_analysis_config()
+    # file entry point: zero frames is a no-op, an offset past the end is an error, EOF-only requests are fill rows
+    path = tmp_path / "r.sigmf-data"
+    raw.tofile(path)
+    assert engine.spectrogram_file(str(path), "ci16_le", 1024, 0).shape == (0, 1024)
+    with pytest.raises(EngineError) as ei:
+        engine.spectrogram_file(str(path), "ci16_le", 1024, 1, data_offset=10**9)
+    assert ei.value.code == 3
+    rows = engine.spectrogram_file(str(path), "ci16_le", 1024, 3, start_sample=49_500)
+    assert (rows == -150.0).all()
