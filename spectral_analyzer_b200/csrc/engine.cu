@@ -402,13 +402,99 @@ int Engine::launch_spectrogram_large(const void* d_iq, uint64_t n_samples, const
             return SA_OK;
         }
     }
+    // Fused persistent kernel, opt-in (SA_LARGE_FUSED=1): both steps in one launch, work items drawn from a ticket counter,
+    // workspace = an L2-persisting ring of frames (DRAM traffic ~ the algorithmic bytes).  Measured on B200: config 5 0.84-0.86 ms
+    // against 0.78 ms for the two kernels below, FP32 65536 1.08-1.30 against 0.69 ms (without the persisting window 1.25 /
+    // 1.52 ms): the per-item device-wide fence, the ticket round trip and two CTAs per SM cost more than the saved
+    // traffic buys (profiles/r02_c5_onchip_ablation.txt).
+    {
+        const char* fused_env = getenv("SA_LARGE_FUSED");
+        const bool fused_on = fused_env ? atoi(fused_env) != 0 : false;
+        const char* ring_env = getenv("SA_LARGE_RING");
+        const char* delay_env = getenv("SA_LARGE_DELAY");
+        if (k->fn_fused && fused_on) {
+            int ring = ring_env ? atoi(ring_env) : (int)std::max<uint64_t>(24, (40ull << 20) / per_frame);
+            int delay = delay_env ? atoi(delay_env) : 12;
+            if (delay < 1) delay = 1;
+            if (ring < delay + 12) ring = delay + 12;
+            if (!l2_persist_set) {
+                cudaDeviceProp prop;
+                if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+                    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize);
+                    l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+                }
+                cudaGetLastError();
+                l2_persist_set = true;
+            }
+            const size_t ring_bytes = ((size_t)ring * per_frame + 255) & ~(size_t)255;
+            const size_t ctr_bytes = (16 + 2 * (size_t)p.n_frames * sizeof(int) + 255) & ~(size_t)255;
+            rc = ensure_scratch(ws, ring_bytes + ctr_bytes);
+            if (rc) return rc;
+            char* base_ws = (char*)scratch[ws];
+            e = cudaMemsetAsync(base_ws + ring_bytes, 0, ctr_bytes, stream);
+            if (e != cudaSuccess) return cuda_fail(e, "clear four-step counters");
+            LargeFusedArgs fa;
+            memset(&fa, 0, sizeof(fa));
+            fa.a = a;
+            fa.a.ws = base_ws;
+            fa.a.frame0 = 0;
+            fa.ticket = (unsigned long long*)(base_ws + ring_bytes);
+            fa.cols_done = (int*)(base_ws + ring_bytes + 16);
+            fa.rows_done = fa.cols_done + p.n_frames;
+            fa.ring = ring; fa.delay = delay;
+            int bps_f = 0;
+            rc = kernel_grid(k->fn_fused, k->cta_cols, k->smem_fused, &bps_f);
+            if (rc) return rc;
+            const long long n_items = ((long long)p.n_frames + delay) * (k->n2 / kLargeC + k->n1 / kLargeC);
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+            attr[0].val.accessPolicyWindow.base_ptr = base_ws;
+            attr[0].val.accessPolicyWindow.num_bytes = std::min<size_t>(ring_bytes, l2_window_max);
+            attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
+            attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.stream = stream;
+            const char* pers_env = getenv("SA_LARGE_PERSIST");
+            const bool pers = l2_window_max > 0 && !(pers_env && atoi(pers_env) == 0);
+            cfg.attrs = attr; cfg.numAttrs = pers ? 1 : 0;
+            cfg.gridDim = dim3((unsigned)std::min<long long>(n_items, (long long)bps_f * num_sms));
+            cfg.blockDim = dim3(k->cta_cols);
+            cfg.dynamicSmemBytes = k->smem_fused;
+            void* fargs[] = { &fa };
+            e = cudaLaunchKernelExC(&cfg, k->fn_fused, fargs);
+            if (e != cudaSuccess) return cuda_fail(e, "launch large_fused_kernel");
+            launches++;
+            static const char* const dkn[] = { "cf32", "ci16", "c8", "cf64" };
+            char nm[160];
+            snprintf(nm, sizeof(nm), "large_fused_kernel<%s,%dx%d,%s,%s> (ring %d, delay %d)", prec == SA_PREC_F64 ? "double" : "float",
+                     k->n1, k->n2, dkn[dk], win ? "window" : "rect", ring, delay);
+            last_kernel = nm;
+            return SA_OK;
+        }
+    }
     // Two workspaces, two streams: even chunks run on the caller's stream, odd chunks on a helper stream forked
     // from it, so that one chunk's column pass fills the SMs the other chunk's row pass leaves idle in its last
     // wave, and workspaces small enough to stay in L2 no longer mean under-filled grids (SA_LARGE_DUAL=0 disables).
     static const char* dual_env = getenv("SA_LARGE_DUAL");
     static const bool dual_on = dual_env ? atoi(dual_env) != 0 : kLargeDualDefault;
+    // SA_LARGE_PERSIST=1: the workspace is declared L2-persisting for the two kernels (launch attribute access policy
+    // window, hit ratio 1, everything else streaming), so that the column kernel's A[k1][n2] stays in L2 until the row
+    // kernel has read it instead of making a DRAM round trip; needs a workspace well below the persisting carve-out
+    static const char* persist_env = getenv("SA_LARGE_PERSIST");
+    static const bool persist_on = persist_env ? atoi(persist_env) != 0 : false;
     static const uint64_t ws_mb = getenv("SA_LARGE_WS_MB") ? (uint64_t)atoi(getenv("SA_LARGE_WS_MB"))
-                                                            : (dual_on ? kLargeDualWsMb : 512);
+                                                            : (persist_on ? 32 : (dual_on ? kLargeDualWsMb : 512));
+    if (persist_on && !l2_persist_set) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize);
+            l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+        }
+        cudaGetLastError();
+        l2_persist_set = true;
+    }
     const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(p.n_frames, (ws_mb << 20) / per_frame));
     const bool dual = dual_on && p.n_frames > chunk;
     const int ai = (ws == 2) ? 0 : ws - 4;                 // helper index: device API 0, host-pipeline slots 1..3
@@ -436,6 +522,26 @@ int Engine::launch_spectrogram_large(const void* d_iq, uint64_t n_samples, const
         cudaStream_t st = odd ? large_aux[ai] : stream;
         a.ws = scratch[odd ? 8 + ai : ws];
         a.frame0 = (long long)f0;
+        if (persist_on && l2_window_max > 0) {
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+            attr[0].val.accessPolicyWindow.base_ptr = a.ws;
+            attr[0].val.accessPolicyWindow.num_bytes = std::min<size_t>((size_t)nf * per_frame, l2_window_max);
+            attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
+            attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
+            cfg.gridDim = dim3(k->n2 / kLargeC, nf); cfg.blockDim = dim3(k->cta_cols); cfg.dynamicSmemBytes = k->smem_cols;
+            e = cudaLaunchKernelExC(&cfg, k->fn_cols, args);
+            if (e != cudaSuccess) return cuda_fail(e, "launch large_cols_kernel");
+            cfg.gridDim = dim3(k->n1 / kLargeC, nf); cfg.blockDim = dim3(k->cta_rows); cfg.dynamicSmemBytes = k->smem_rows;
+            e = cudaLaunchKernelExC(&cfg, k->fn_rows, args);
+            if (e != cudaSuccess) return cuda_fail(e, "launch large_rows_kernel");
+            launches += 2;
+            continue;
+        }
         e = cudaLaunchKernel(k->fn_cols, dim3(k->n2 / kLargeC, nf), dim3(k->cta_cols), args, k->smem_cols, st);
         if (e != cudaSuccess) return cuda_fail(e, "launch large_cols_kernel");
         e = cudaLaunchKernel(k->fn_rows, dim3(k->n1 / kLargeC, nf), dim3(k->cta_rows), args, k->smem_rows, st);

@@ -106,6 +106,7 @@ struct Engine {
     size_t scratch_cap[kScratch] = {};
     cudaStream_t large_aux[4] = {};                  // helper stream per four-step caller (device API, slots 0..2)
     cudaEvent_t large_ev[4][2] = {};                 // fork / join events of that helper stream
+    bool l2_persist_set = false; size_t l2_window_max = 0;   // persisting-L2 carve-out for the four-step workspace
     AnalysisProfile profile;                         // sa_set_analysis_config
     cudaStream_t dc_aux = nullptr;                   // annotation batches alternate between the caller's stream and this one
     cudaEvent_t dc_ev[2] = {};                       // fork / join

@@ -153,6 +153,81 @@ large_rows_kernel(const LargeArgs a) {
                                blockIdx.x, smem_raw, ltab);
 }
 
+// ---- fused persistent variant: both steps in ONE launch, workspace = a ring of frames that stays in L2 ----
+// The two-kernel path writes the whole chunk's A[k1][n2] to DRAM and reads it back (2.2x the algorithmic traffic; the
+// column kernel runs at 85 % of the HBM bandwidth for ITS bytes).  Chunks small enough for L2 do not help as separate
+// launches (32 launches of 512 CTAs: ramp and tail of every launch, 1.12 ms instead of 0.78), with or without an
+// L2-persisting window.  Here the CTAs of one persistent grid draw work items from a ticket counter in an order that
+// interleaves the column groups of frame f with the row groups of frame f - delay; a row item waits (acquire load of a
+// per-frame counter) until the 16 column items of its frame have published their part of A, a column item until the rows
+// of the frame that used its ring slot `ring` frames ago are done.  Every wait targets items with smaller tickets, which
+// resident CTAs hold or have finished (grid = resident CTAs), so the scheme cannot deadlock; the ring (ring x N elements)
+// is declared L2-persisting for the launch.
+struct LargeFusedArgs {
+    LargeArgs a;                 // a.ws: ring of `ring` frames
+    unsigned long long* ticket;  // zeroed before the launch
+    int* cols_done;              // [n_frames], zeroed
+    int* rows_done;              // [n_frames], zeroed
+    int ring, delay;
+};
+
+__device__ __forceinline__ int ld_acquire(const int* p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+// thread 0 waits for *p >= want, the CTA follows; traps instead of hanging if the producer never arrives
+__device__ __forceinline__ void wait_counter(const int* p, int want) {
+    if (threadIdx.x == 0) {
+        unsigned spins = 0;
+        while (ld_acquire(p) < want) {
+            __nanosleep(64);
+            if (++spins > (1u << 24)) __trap();
+        }
+    }
+    __syncthreads();
+}
+
+template <typename T, int N1, int N2, int DK, bool WIN>
+__global__ void __launch_bounds__(kLargeC * Geo<T, N1>::TPF, 2)
+large_fused_kernel(const LargeFusedArgs fa) {
+    static_assert(Geo<T, N1>::TPF == Geo<T, N2>::TPF, "both steps use the same CTA size");
+    constexpr int N = N1 * N2, C = kLargeC, CG = N2 / C, RG = N1 / C;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ long long s_item;
+    const double* ltab = nullptr;
+    if constexpr (sizeof(T) == 8 && SA_F64_FAST_DB) {
+        __shared__ double s_ltab[128];
+        f64_ltab_init(s_ltab);
+        ltab = s_ltab;
+    }
+    const LargeArgs& a = fa.a;
+    const long long n_items = (a.s.n_frames + fa.delay) * (CG + RG);
+    cpx<T>* ring = reinterpret_cast<cpx<T>*>(a.ws);
+    for (;;) {
+        __syncthreads();                                      // s_item and the shared-memory buffers of the last item are free
+        if (threadIdx.x == 0) s_item = (long long)atomicAdd(fa.ticket, 1ull);
+        __syncthreads();
+        const long long item = s_item;
+        if (item >= n_items) break;
+        const long long slot = item / (CG + RG);
+        const int sub = (int)(item % (CG + RG));
+        if (sub < CG) {                                       // column group `sub` of frame `slot`
+            const long long f = slot;
+            if (f >= a.s.n_frames) continue;
+            if (f >= fa.ring) wait_counter(&fa.rows_done[f - fa.ring], RG);
+            large_cols_body<T, N1, N2, DK, WIN>(a, a.frame0 + f, ring + (size_t)(f % fa.ring) * N, sub, smem_raw);
+            __threadfence();                                  // this thread's part of A is visible device-wide ...
+            __syncthreads();
+            if (threadIdx.x == 0) atomicAdd(&fa.cols_done[f], 1);      // ... before the group is published
+        } else {                                              // row group of frame slot - delay
+            const long long f = slot - fa.delay;
+            if (f < 0) continue;
+            wait_counter(&fa.cols_done[f], CG);
+            large_rows_body<T, N1, N2>(a, a.frame0 + f, ring + (size_t)(f % fa.ring) * N, sub - CG, smem_raw, ltab);
+            __threadfence();
+            __syncthreads();                                  // every thread has read its part of the ring slot
+            if (threadIdx.x == 0) atomicAdd(&fa.rows_done[f], 1);
+        }
+    }
+}
+
 // ---- on-chip variant (N = 256 x 256): one thread-block cluster of kLargeCluster CTAs per frame ----
 // The frame never leaves the chip between the column step and the row step.  CTA `rank` of the cluster owns the
 // 32 columns n2 = 32 rank .. 32 rank + 31 in the column step and the 32 rows k1 = 32 rank .. + 31 in the row step:
@@ -380,8 +455,8 @@ large_onchip_kernel(const LargeArgs a, const __grid_constant__ CUtensorMap tmap)
 }
 
 struct LargeKernelInfo {
-    const void* fn_cols; const void* fn_rows; const void* fn_cluster;
-    size_t smem_cluster;
+    const void* fn_cols; const void* fn_rows; const void* fn_cluster; const void* fn_fused;
+    size_t smem_cluster, smem_fused;
     int cta_cluster;
     int prec, n, n1, n2, dk, win;
     int cta_cols, cta_rows;
@@ -403,6 +478,11 @@ LargeKernelInfo make_large_info(int prec) {
     const size_t tile = (size_t)N2 * (kLargeC + 1) * sizeof(T);
     k.smem_rows = ex > tile ? ex : tile;
     k.fn_cluster = nullptr; k.smem_cluster = 0; k.cta_cluster = 0;
+    k.fn_fused = nullptr; k.smem_fused = 0;
+    if constexpr (Geo<T, N1>::TPF == Geo<T, N2>::TPF) {
+        k.fn_fused = (const void*)&large_fused_kernel<T, N1, N2, DK, WIN>;
+        k.smem_fused = k.smem_cols > k.smem_rows ? k.smem_cols : k.smem_rows;
+    }
     // on-chip cluster kernel: 256 x 256 with the raw element as wide as the complex working type
     if constexpr (N1 == 256 && N2 == 256 && sizeof(typename Loader<T, DK>::raw_t) == sizeof(cpx<T>)) {
         k.fn_cluster = (const void*)&large_onchip_kernel<T, DK, WIN>;

@@ -408,6 +408,15 @@ def test_onchip_cluster_four_step(engine, monkeypatch, dt, prec, kind):
     assert engine.last_kernel.startswith("large_cols_kernel+large_rows_kernel")
     # same arithmetic in the same order (the workspace round trip is the only difference): bit-identical
     assert np.array_equal(got, two)
+    # third variant, opt-in as well: both steps in one persistent launch, ring of frames in L2 (a short ring and delay so
+    # that slots are reused and row items really wait for their columns)
+    monkeypatch.setenv("SA_LARGE_FUSED", "1")
+    monkeypatch.setenv("SA_LARGE_RING", "14")
+    monkeypatch.setenv("SA_LARGE_DELAY", "2")
+    fused = engine.spectrogram(raw, dt, nfft, frames, hop=hop, window="hann", precision=prec, out_kind=kind)
+    assert engine.last_kernel.startswith("large_fused_kernel")
+    assert np.array_equal(got, fused)
+    monkeypatch.delenv("SA_LARGE_FUSED")
     # rect window on the FP32 path (no window multiply instantiated) and an unaligned start (two-kernel path again)
     monkeypatch.setenv("SA_LARGE_ONCHIP", "1")
     if prec == "f32":
