@@ -113,25 +113,33 @@ __device__ __forceinline__ void sts64(uint32_t addr, float x, float y) {
 
 // One register batch of a tile: U coalesced loads per thread (sample i0 + tid + 256 u of the tile), all issued before
 // the first is consumed.  Samples outside the annotation ([lo, hi) in tile coordinates) are not read.
-template <int DK, int U>
-__device__ __forceinline__ void dc_load_batch(const DcArgs& a, const DcAnn& an, typename DcRaw<DK>::raw_t (&raw)[U],
-                                              const long long nlo, const int i0, const int lo, const int hi) {
+// INTERIOR (tile-uniform): every staged sample of the tile lies inside the annotation: one range test (tile end) per
+// sample instead of two, and no zeroing select in the staging step.
+template <int DK, int U, bool INTERIOR>
+__device__ __forceinline__ void dc_load_batch_impl(const DcArgs& a, const DcAnn& an, typename DcRaw<DK>::raw_t (&raw)[U],
+                                                   const long long nlo, const int i0, const int lo, const int hi) {
     using R = DcRaw<DK>;
     const long long s = an.start_sample + nlo + i0 + threadIdx.x;
 #pragma unroll
     for (int u = 0; u < U; u++) {
         const int ii = i0 + (int)threadIdx.x + u * kDcThreads;
         raw[u] = typename R::raw_t();
-        if (ii >= lo && ii < hi) raw[u] = R::ld(a.lp.base, s + u * kDcThreads);
+        if (INTERIOR ? (ii < hi) : (ii >= lo && ii < hi)) raw[u] = R::ld(a.lp.base, s + u * kDcThreads);
     }
+}
+template <int DK, int U>
+__device__ __forceinline__ void dc_load_batch(const DcArgs& a, const DcAnn& an, typename DcRaw<DK>::raw_t (&raw)[U],
+                                              const long long nlo, const int i0, const int n_stage, const int lo, const int hi) {
+    if (lo == 0 && hi == n_stage) dc_load_batch_impl<DK, U, true>(a, an, raw, nlo, i0, lo, hi);
+    else dc_load_batch_impl<DK, U, false>(a, an, raw, nlo, i0, lo, hi);
 }
 
 // Decodes and mixes a register batch into the staged tile: stage[i + (i / D) * pad].  The NCO phasor of the batch
 // is seeded from the exact 64-bit phase and advances 256 samples per step by one packed complex multiply.
-template <int DK, bool SWAP, int U>
-__device__ __forceinline__ void dc_stage_batch(const DcArgs& a, const DcAnn& an, const typename DcRaw<DK>::raw_t (&raw)[U],
-                                               float2* __restrict__ stage, const long long nlo, const int i0,
-                                               const int n_stage, const int lo, const int hi, const int pad) {
+template <int DK, bool SWAP, int U, bool INTERIOR>
+__device__ __forceinline__ void dc_stage_batch_impl(const DcArgs& a, const DcAnn& an, const typename DcRaw<DK>::raw_t (&raw)[U],
+                                                    float2* __restrict__ stage, const long long nlo, const int i0,
+                                                    const int n_stage, const int lo, const int hi, const int pad) {
     using LD = typename DcRaw<DK>::LD;
     const float2 wstep = nco_phasor(an.phase_step * (unsigned long long)kDcThreads);
     const pk2 W = pack2(wstep.x, wstep.y), iW = pack2(-wstep.y, wstep.x);
@@ -147,12 +155,21 @@ __device__ __forceinline__ void dc_stage_batch(const DcArgs& a, const DcAnn& an,
         unpack2(P, px, py);
         // y = d * P = d.x (P.x, P.y) + d.y (-P.y, P.x)
         pk2 Y = fma2(pack2(d.y, d.y), pack2(-py, px), mul2(pack2(d.x, d.x), P));
-        if (ii < lo || ii >= hi) Y = pack2(0.f, 0.f);             // zero history / zero tail of the filter
+        if (!INTERIOR && (ii < lo || ii >= hi)) Y = pack2(0.f, 0.f);             // zero history / zero tail of the filter
         float yx, yy;
         unpack2(Y, yx, yy);
         if (ii < n_stage) sts64(stage_s + 8u * (unsigned)(ii + (int)__umulhi((unsigned)ii, qmagic)), yx, yy);
         if (u + 1 < U) P = fma2(pack2(py, py), iW, mul2(pack2(px, px), W));
     }
+}
+template <int DK, bool SWAP, int U>
+__device__ __forceinline__ void dc_stage_batch(const DcArgs& a, const DcAnn& an, const typename DcRaw<DK>::raw_t (&raw)[U],
+                                               float2* __restrict__ stage, const long long nlo, const int i0,
+                                               const int n_stage, const int lo, const int hi, const int pad) {
+    if (lo == 0 && hi == n_stage)
+        dc_stage_batch_impl<DK, SWAP, U, true>(a, an, raw, stage, nlo, i0, n_stage, lo, hi, pad);
+    else
+        dc_stage_batch_impl<DK, SWAP, U, false>(a, an, raw, stage, nlo, i0, n_stage, lo, hi, pad);
 }
 
 constexpr int kDcUnrollMax = 16;      // loads in flight per thread of the non-pipelined variant (16-byte pairs: 8)
@@ -200,7 +217,7 @@ downconvert_kernel(const DcArgs a, const __grid_constant__ DcTapParams tp) {
     long long nlo;
     geom(tile, nbt, nblk, n_stage, nlo, lo, hi);
     raw_t raw[U];
-    if constexpr (PIPE) dc_load_batch<DK, U>(a, an, raw, nlo, 0, lo, hi);
+    if constexpr (PIPE) dc_load_batch<DK, U>(a, an, raw, nlo, 0, n_stage, lo, hi);
     for (; tile < tile_end; tile++) {
         const long long m0 = tile * an.nb;
         // ---- stage: decode + mix once into shared memory
@@ -209,7 +226,7 @@ downconvert_kernel(const DcArgs a, const __grid_constant__ DcTapParams tp) {
             else           dc_stage_batch<DK, false, U>(a, an, raw, stage, nlo, 0, n_stage, lo, hi, pad);
         } else {
             for (int i0 = 0; i0 < n_stage; i0 += kDcThreads * U) {
-                dc_load_batch<DK, U>(a, an, raw, nlo, i0, lo, hi);
+                dc_load_batch<DK, U>(a, an, raw, nlo, i0, n_stage, lo, hi);
                 if (a.lp.swap) dc_stage_batch<DK, true, U>(a, an, raw, stage, nlo, i0, n_stage, lo, hi, pad);
                 else           dc_stage_batch<DK, false, U>(a, an, raw, stage, nlo, i0, n_stage, lo, hi, pad);
             }
@@ -219,7 +236,7 @@ downconvert_kernel(const DcArgs a, const __grid_constant__ DcTapParams tp) {
         if constexpr (PIPE) {           // next tile's samples fly under this tile's arithmetic
             if (tile + 1 < tile_end) {
                 geom(tile + 1, nbt, nblk, n_stage, nlo, lo, hi);
-                dc_load_batch<DK, U>(a, an, raw, nlo, 0, lo, hi);
+                dc_load_batch<DK, U>(a, an, raw, nlo, 0, n_stage, lo, hi);
             }
         }
         const int stage_phys = c_nstage + c_nstage / D + 2;
