@@ -66,19 +66,23 @@ class CopyPool {
 public:
     explicit CopyPool(int workers);
     ~CopyPool();
+    struct Group { size_t outstanding = 0; };                    // one asynchronous copy (start / wait)
     void copy(void* dst, const void* src, size_t bytes);         // returns when every part has been copied
     // same, the source being bytes [off, off + bytes) of an open file (parallel pread); false on a short read / error
     bool read(void* dst, int fd, uint64_t off, size_t bytes);
+    // asynchronous memcpy: every part goes to the workers, the caller carries on (e.g. with the next chunk's copy-in) and
+    // waits later; `g` must stay alive until wait() returns
+    void start(void* dst, const void* src, size_t bytes, Group* g);
+    void wait(Group* g);
 private:
     void worker();
     void run(void* dst, const void* src, int fd, uint64_t off, size_t bytes);
-    struct Job { char* dst; const char* src; size_t bytes; int fd; uint64_t off; };
+    struct Job { char* dst; const char* src; size_t bytes; int fd; uint64_t off; Group* group; };
     std::atomic<bool> io_error_{false};
     std::vector<std::thread> threads_;
     std::mutex mu_;
     std::condition_variable cv_, done_cv_;
     std::vector<Job> queue_;
-    size_t outstanding_ = 0;
     bool stop_ = false;
 };
 
