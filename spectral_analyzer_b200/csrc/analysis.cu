@@ -316,18 +316,19 @@ static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, i
     const uint64_t batch_mb = batch_env && atoi(batch_env) > 0 ? (uint64_t)atoi(batch_env) : 128;
     const uint64_t scr_cap_elems = (batch_mb << 20) / sizeof(float2);
     std::vector<std::pair<uint32_t, uint32_t>> batches;
-    if (want_psd) {
+    {
+        const uint32_t max_per_batch = 65535;                // annotations are grid.y of the launches
         uint32_t b0 = 0;
         uint64_t acc = 0;
         for (uint32_t i = 0; i < n_ann; i++) {
-            if (i > b0 && acc + (uint64_t)plan[i].m_out > scr_cap_elems) { batches.push_back({b0, i}); b0 = i; acc = 0; }
+            if (i > b0 && ((want_psd && acc + (uint64_t)plan[i].m_out > scr_cap_elems) || i - b0 >= max_per_batch)) {
+                batches.push_back({b0, i}); b0 = i; acc = 0;
+            }
             plan[i].scr_off = (long long)acc;
             acc += (uint64_t)plan[i].m_out;
-            scr_total = std::max(scr_total, acc);
+            if (want_psd) scr_total = std::max(scr_total, acc);
         }
         batches.push_back({b0, n_ann});
-    } else {
-        batches.push_back({0, n_ann});
     }
     const bool dual = want_psd && batches.size() > 1;
     int rc = SA_OK;

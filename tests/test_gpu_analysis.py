@@ -316,3 +316,15 @@ def test_analysis_edge_cases(engine, tmp_path):
     assert ei.value.code == 3
     rows = engine.spectrogram_file(str(path), "ci16_le", 1024, 3, start_sample=49_500)
     assert (rows == -150.0).all()
+
+
+def test_batch_of_more_annotations_than_one_launch_holds(engine):
+    """70 000 tiny annotations: more than the 65 535 a launch can index (grid.y); the batch is cut, results are the same
+    as for the first and the last annotation alone."""
+    raw = synth.recording(80_000, "cu8", seed=5)
+    anns = [(i, 64, 0.01 * (i % 7), 4, False) for i in range(70_000)]
+    iq, _ = engine.downconvert_psd_batch(raw, "cu8", 1e6, anns, want_psd=False)
+    assert len(iq) == 70_000 and all(z.shape == (2, 16) for z in (iq[0], iq[-1]))
+    for i in (0, 65_534, 65_535, 69_999):
+        ref = co.downconvert(raw, "cu8", *anns[i][:4], False)
+        assert np.abs(iq[i] - ref).max() <= DC_TOL * max(np.abs(ref).max(), 0.5)
