@@ -9,6 +9,9 @@
 #pragma once
 #include "decode.cuh"
 
+#ifndef SA_POOL_EPILOGUE
+#define SA_POOL_EPILOGUE 1      // 0: compile the fused display pooling out of the epilogues (A/B of its cost on the row path)
+#endif
 #ifndef SA_STORE_STREAMING
 #define SA_STORE_STREAMING 0
 #endif
@@ -189,7 +192,7 @@ template <int DK> __host__ __device__ constexpr int bytes_per_iq_kind() {
 template <typename T, int N>
 __device__ __forceinline__ void store_fill(const SpecArgs& a, const long long frame, const int t) {
     constexpr int P = Geo<T, N>::P, TPF = Geo<T, N>::TPF;
-    if (a.pool_mode) {
+    if (SA_POOL_EPILOGUE && a.pool_mode) {
         float* o = reinterpret_cast<float*>(a.out) + (size_t)pool_column(a, frame) * N;
 #pragma unroll
         for (int q = 0; q < P; q++) pool_red(&o[t + TPF * q], a.pool_eof, a.pool_mode);
@@ -262,7 +265,7 @@ template <typename T, int N>
 __device__ __forceinline__ void store_row(const SpecArgs& a, const long long frame, const int t,
                                           const cpx<T> (&v)[Plan<T, N>::P], const double* ltab = nullptr) {
     constexpr int P = Geo<T, N>::P, TPF = Geo<T, N>::TPF;
-    if (a.pool_mode) {          // |X|^2 only: the logarithm is taken once per pixel by canvas_power_kernel
+    if (SA_POOL_EPILOGUE && a.pool_mode) {          // |X|^2 only: the logarithm is taken once per pixel by canvas_power_kernel
         float* o = reinterpret_cast<float*>(a.out) + (size_t)pool_column(a, frame) * N;
         const int kp = (t + N / 2) & (N - 1);
 #pragma unroll
