@@ -57,5 +57,39 @@ if not only or only == "canvas":
         px = eng.render_canvas(raw, "cf32_le", 1024, 13, 200, 2.4e6, frames_per_column=3, reduce=red, colormap="Heatmap")
         assert px.shape == (200, 13, 4) and (px[..., 3] == 255).all()
         n_checked += 1
+if not only or only == "profile":
+    # round 2: any-length PSD (direct DFT kernel, FP32 and FP64), FP64 Welch, caller taps / delay / length rules, PSD-only
+    # batch, strict decodes, file ingest
+    import tempfile
+    raw = synth.recording(30000, "ci16_le", seed=8)
+    iq = co.downconvert(raw, "ci16_le", 0, 28000, 0.1, 4, False)
+    for prec, tol in (("f32", 1e-3), ("f64", 1e-8)):
+        eng.set_analysis_config(psd_precision=prec, psd_detrend="constant", psd_scaling="spectrum")
+        cfg = co.analysis_cfg(scaling="spectrum", detrend="constant")
+        for nf in (777, 1024):
+            got = eng.psd_welch(iq, 250e3, nf)
+            ref = co.psd_welch(iq, 250e3, nf, cfg=cfg)
+            top = ref[1] > ref[1].max() - 40
+            assert np.abs(got[1] - ref[1])[top].max() < tol, (prec, nf)
+            n_checked += 1
+    taps = np.hanning(41) / np.hanning(41).sum()
+    eng.set_analysis_config(taps=taps, delay="same", length="ceil")
+    got = eng.downconvert(raw, "ci16_le", 7, 20001, -0.2, 8)
+    ref = co.downconvert_ex(raw, "ci16_le", 7, 20001, -0.2, 8, False, co.analysis_cfg(taps=taps, delay="same", length="ceil"))
+    assert got.shape == ref.shape and np.abs(got - ref).max() < 1e-5
+    eng.set_analysis_config(strict_reference=True)
+    raw32 = synth.recording(8000, "cf32_le", seed=9)            # an unknown datatype is read as cf32 (strict reference)
+    got = eng.downconvert(raw32, "ri16_le", 0, 7000, 0.05, 4)
+    ref = co.downconvert_ex(raw32, "ri16_le", 0, 7000, 0.05, 4, False, co.analysis_cfg(strict_reference=True))
+    assert np.abs(got - ref).max() <= 1e-5 * max(np.abs(ref).max(), 0.5)
+    eng.reset_analysis_config()
+    _, psd = eng.downconvert_psd_batch(raw, "ci16_le", 1e6, [(0, 20000, 0.1, 4, False), (100, 900, 0.2, 4, False)], psd_nfft=1024, want_iq=False)
+    assert np.isfinite(psd[0]).all() and np.isnan(psd[1][225:]).all()
+    with tempfile.NamedTemporaryFile(suffix=".sigmf-data") as f:
+        f.write(b"\0" * 44 + raw.tobytes())
+        f.flush()
+        a = eng.spectrogram_file(f.name, "ci16_le", 1024, 20, hop=512, window="hann", data_offset=44)
+    assert np.array_equal(a, eng.spectrogram(raw, "ci16_le", 1024, 20, hop=512, window="hann"))
+    n_checked += 4
 eng.close()
 print("sanitize smoke ok: %d checks" % n_checked)
