@@ -58,9 +58,16 @@ def spectrogram_case(eng, name, datatype, n_samples, nfft, hop, window, out_kind
     ms = timed(lambda: eng.spectrogram_device(raw.data_ptr() + byte_offset, n_samples * bps, p, out.data_ptr(), out.numel(), stream), steps)
     alg = n_samples * bps + frames * nfft * obytes
     peak, kind_p = hbm_peak()
+    # the FP32 (FP64) pipe beside the HBM roofline: 5 nfft log2(nfft) / hop + 6 flop per input sample
+    # against 148 SMs x 128 (64) FMA lanes x 2 flop at 1965 MHz -- for the integer inputs and the large transforms
+    # the arithmetic, not the bytes, sets the time
+    import math
+    flops = frames * hop * (5.0 * nfft * math.log2(nfft) / hop + 6.0)
+    pipe_peak = 148 * (64 if kind == "cf64" or kw.get("precision") == "f64" else 128) * 2 * 1.965e9
     res = {"config": name, "datatype": datatype, "samples": n_samples, "nfft": nfft, "hop": hop, "window": window,
            "out": out_kind, "ms": round(ms, 4), "Msamples_per_s": round(frames * hop / ms / 1e3, 1),
            "alg_bytes": alg, "GBps": round(alg / ms / 1e6, 1), "roofline_frac": round(alg / ms / 1e6 / peak, 4),
+           "fft_flop_pipe_frac": round(flops / (ms * 1e-3) / pipe_peak, 4),
            "peak_kind": kind_p, "kernel": eng.last_kernel}
     del raw, out
     torch.cuda.empty_cache()

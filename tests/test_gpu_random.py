@@ -90,3 +90,73 @@ def test_random_batch_mixed_decimations(engine):
             top = rp > rp.max() - 40
             assert np.abs(p[:nf] - rp)[top].max() < 5e-3
         assert np.isnan(p[nf:]).all()
+
+
+def profile_cases():
+    """Random analysis profiles: tap counts around the 8*down+1 boundary between the staged and the warp-per-output
+    kernel, every delay x length rule, spans shorter than the filter, starts at 0 and ends at the end of the buffer."""
+    rng = np.random.default_rng(4242)
+    out = []
+    for i in range(48):
+        down = int([rng.integers(1, 9), rng.integers(9, 33), rng.integers(33, 200), rng.integers(200, 700)][i % 4])
+        ntaps = [None, int(rng.integers(1, 8 * down + 2)), 8 * down + 1, int(rng.integers(8 * down + 2, 8 * down + 300))][int(rng.integers(4))]
+        delay = ["causal", "same", "valid"][int(rng.integers(3))]
+        length = ["floor", "ceil"][int(rng.integers(2))]
+        dt = DTYPES[int(rng.integers(len(DTYPES)))] if i % 6 else "cf64_le"
+        count = int(rng.integers(1, 40 * down + 3000)) if i % 9 else int(rng.integers(1, 3 * down + 5))
+        start = 0 if i % 4 == 0 else int(rng.integers(0, 2000))
+        out.append((dt, down, ntaps, delay, length, start, count, float(rng.uniform(-0.5, 0.5))))
+    return out
+
+
+@pytest.mark.parametrize("dt,down,ntaps,delay,length,start,count,f", profile_cases())
+def test_random_analysis_profiles_match_oracle(engine, dt, down, ntaps, delay, length, start, count, f):
+    raw = synth.recording(start + count, dt, seed=down + count)                 # the annotation ends at the end of the buffer
+    taps = None
+    if ntaps:
+        taps = np.random.default_rng(ntaps).standard_normal(ntaps)
+        taps /= np.abs(taps).sum()
+    cfg = co.analysis_cfg(taps=taps, delay=delay, length=length)
+    engine.set_analysis_config(taps=taps, delay=delay, length=length)
+    try:
+        for fast in (False, True):
+            ref = co.downconvert_ex(raw, dt, start, count, f, down, fast, cfg)
+            got = engine.downconvert(raw, dt, start, count, f, down, fast)
+            assert got.shape == ref.shape, (fast, got.shape, ref.shape)
+            if ref.size:
+                assert np.abs(got - ref).max() <= 1e-5 * max(np.abs(ref).max(), 0.5), fast
+    finally:
+        engine.reset_analysis_config()
+
+
+def psd_cases():
+    rng = np.random.default_rng(99)
+    out = []
+    for i in range(24):
+        nfft = int([rng.integers(1, 64), rng.integers(64, 1200), 2 ** int(rng.integers(6, 14)), rng.integers(1200, 9000)][i % 4])
+        segs = int(rng.integers(1, 6))
+        hop = max(1, int(nfft * rng.uniform(0.1, 1.2)))
+        n = nfft + (segs - 1) * hop + int(rng.integers(0, hop))
+        out.append((nfft, hop, n, WINDOWS[int(rng.integers(len(WINDOWS)))], ["density", "spectrum"][int(rng.integers(2))],
+                    [None, "constant"][int(rng.integers(2))], ["f32", "f64"][i % 2]))
+    return out
+
+
+@pytest.mark.parametrize("nfft,hop,n,window,scaling,detrend,prec", psd_cases())
+def test_random_psd_requests_match_oracle(engine, nfft, hop, n, window, scaling, detrend, prec):
+    rng = np.random.default_rng(nfft + n)
+    x = (0.4 - 0.3j) + 0.5 * np.exp(2j * np.pi * 0.123 * np.arange(n)) + 0.05 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    iq = np.stack([x.real, x.imag])
+    ref = co.psd_welch(iq, 48e3, nfft, hop=hop, window=window, cfg=co.analysis_cfg(scaling=scaling, detrend=detrend))
+    engine.set_analysis_config(psd_scaling=scaling, psd_detrend=detrend, psd_precision=prec)
+    try:
+        got = engine.psd_welch(iq, 48e3, nfft, hop=hop, window=window)
+    finally:
+        engine.reset_analysis_config()
+    assert got.shape == (2, nfft) and np.allclose(got[0], ref[0], rtol=0, atol=1e-9)
+    ok = np.isfinite(ref[1])
+    assert np.array_equal(np.isfinite(got[1]), ok)
+    if ok.any():
+        top = ok & (ref[1] > np.nanmax(ref[1][ok]) - (60 if prec == "f64" else 40))
+        tol = 1e-8 if prec == "f64" else 2e-3
+        assert np.abs(got[1] - ref[1])[top].max() < tol
