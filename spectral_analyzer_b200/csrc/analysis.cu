@@ -80,11 +80,12 @@ const void* dc_kernel(int dk, int which) {
     }
 }
 
-size_t dc_smem_bytes(int down, int nb, int fast) {
+size_t dc_smem_bytes(int down, int nb, int fast, bool pipe) {
     const int nblk = nb + (fast ? 0 : 7);
     const size_t n_stage = fast ? (size_t)nb * down : (size_t)nblk * down + 1;
     const size_t stage_phys = n_stage + n_stage / down + 2;
-    return ((stage_phys + 1) & ~(size_t)1) * sizeof(float2) + (fast ? 0 : (size_t)nblk * 8 * sizeof(float2));
+    return ((stage_phys + 1) & ~(size_t)1) * sizeof(float2) + (fast ? 0 : (size_t)nblk * 8 * sizeof(float2)) +
+           (pipe ? (size_t)dc_tap_smem_bytes(down) : 0);
 }
 
 int validate_anns(const sa_annotation* anns, uint32_t n_ann, uint64_t n_samples, uint64_t extra) {
@@ -302,7 +303,13 @@ static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, i
             a.nb = 0;                       // marks the warp-per-output kernel
         } else if (pipe_ok && !a.fast && D <= 32) {
             // pipelined variant: the whole tile is one register batch (<= 17 x 256 staged samples)
-            const int nblk = std::max(8, std::min(kDcThreads, (kDcPipeLoads * kDcThreads - 1) / D));
+            // blocks per tile: the staged samples fill the register batch (n_stage + D - 1 <= 17 x 256) and the tile
+            // (staged samples + 8 partial sums per block) stays within a third of the SM's shared memory; a thread
+            // takes several blocks when the decimation is small (D = 2: 256 -> 768 blocks per tile)
+            const int by_batch = (kDcPipeLoads * kDcThreads - D) / D;
+            const int by_smem = (int)((size_t)(74 * 1024 - dc_tap_smem_bytes(D) - 64) / (8 * (size_t)(D + 1) + 64));
+            int nblk = std::max(8, std::min(by_batch, by_smem));
+            if (nblk > kDcThreads) nblk -= nblk % kDcThreads;        // whole rounds of one block per thread
             a.nb = nblk - 7;
             piped[i] = 1;
         } else {
@@ -471,9 +478,12 @@ static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, i
                     tp.down = D;
                     memcpy(tp.ht, h + (std::max<size_t>((size_t)first.n_taps, 8 * (size_t)D + 1)), sizeof(float) * 8 * (size_t)D);
                 }
-                const size_t smem = dc_smem_bytes(D, first.nb, first.fast);
+                const size_t smem = dc_smem_bytes(D, first.nb, first.fast, pipe);
                 const void* fn = dc_kernel(dk, pipe ? 3 : (ptaps ? 1 : 0));
-                if (pipe) da.tiles_per_cta = kDcPipeTiles;
+                if (pipe) {
+                    static const char* te = getenv("SA_DC_TILES");
+                    da.tiles_per_cta = te && atoi(te) > 0 ? atoi(te) : kDcPipeTiles;
+                }
                 const long long ctas = (tiles + da.tiles_per_cta - 1) / da.tiles_per_cta;
                 if (ctas > 0) {
                     size_t& have = eng->dc_smem_set[fn];

@@ -57,10 +57,17 @@ struct DcTapParams {
 };
 
 constexpr int kDcThreads = 256;
+#ifndef SA_DC_PIPE_CTAS
+#define SA_DC_PIPE_CTAS 3
+#endif
+#ifndef SA_DC_SWP
+#define SA_DC_SWP 0
+#endif
 constexpr int kDcStage = 8192;       // staged samples per tile (shared memory budget)
 constexpr int kDcMaxDown = 512;      // larger decimations take the warp-per-output kernel
 constexpr int kDcPipeLoads = 17;     // pipelined variant: the whole tile (<= 17 x 256 samples) is one register batch
 constexpr int kDcPipeTiles = 8;      // consecutive tiles of one annotation per CTA (pipelined variant)
+__host__ __device__ constexpr int dc_tap_smem_bytes(int down) { return (8 * down * (int)sizeof(float) + 15) & ~15; }   // pipelined variant
 
 // The reference's cf64 stride bug, reproduced only with strict_reference (ExtractDownConvertService.java:60-67,79-81):
 // IQ pair i is read as the two doubles at byte offset 8 i (re = d[i], im = d[i+1]).
@@ -107,12 +114,23 @@ __device__ __forceinline__ float2 nco_phasor(unsigned long long phase) {
     return make_float2(c, -s);
 }
 
+__device__ __forceinline__ float2 lds64(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ void sts64(uint32_t addr, float x, float y) {
     asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(x), "f"(y) : "memory");
 }
 
 // One register batch of a tile: U coalesced loads per thread (sample i0 + tid + 256 u of the tile), all issued before
-// the first is consumed.  Samples outside the annotation ([lo, hi) in tile coordinates) are not read.
+// the first is consumed.  i0 starts at -qoff (below), so that a half-warp's 16 samples never straddle a pad element
+// when D is a multiple of 16 (conflict-free staging stores); the lanes left of sample 0 idle.  Samples outside the annotation ([lo, hi) in tile coordinates) are not read.
 // INTERIOR (tile-uniform): every staged sample of the tile lies inside the annotation: one range test (tile end) per
 // sample instead of two, and no zeroing select in the staging step.
 template <int DK, int U, bool INTERIOR>
@@ -124,7 +142,7 @@ __device__ __forceinline__ void dc_load_batch_impl(const DcArgs& a, const DcAnn&
     for (int u = 0; u < U; u++) {
         const int ii = i0 + (int)threadIdx.x + u * kDcThreads;
         raw[u] = typename R::raw_t();      // (skipping this for interior tiles measured SLOWER: C3 1.66 -> 1.74 ms on one box)
-        if (INTERIOR ? (ii < hi) : (ii >= lo && ii < hi)) raw[u] = R::ld(a.lp.base, s + u * kDcThreads);
+        if (INTERIOR ? ((unsigned)ii < (unsigned)hi) : (ii >= lo && ii < hi)) raw[u] = R::ld(a.lp.base, s + u * kDcThreads);
     }
 }
 template <int DK, int U>
@@ -134,12 +152,15 @@ __device__ __forceinline__ void dc_load_batch(const DcArgs& a, const DcAnn& an, 
     else dc_load_batch_impl<DK, U, false>(a, an, raw, nlo, i0, lo, hi);
 }
 
-// Decodes and mixes a register batch into the staged tile: stage[i + (i / D) * pad].  The NCO phasor of the batch
+// Decodes and mixes a register batch into the staged tile: stage[i + ((i + qoff) / D) * pad].  qoff = D - 1 (FIR tiles)
+// puts the pad element of an even D AFTER the samples i = 0 mod D, so the D samples y[(b+1)D - r], r = 0..D-1, that
+// input block b multiplies are contiguous (one address stream, no first-row special case in the tap loop) while
+// y[jD] stays at j (D + pad); qoff = 0 (box-car tiles) keeps y[jD .. jD + D) contiguous.  The NCO phasor of the batch
 // is seeded from the exact 64-bit phase and advances 256 samples per step by one packed complex multiply.
 template <int DK, bool SWAP, int U, bool INTERIOR>
 __device__ __forceinline__ void dc_stage_batch_impl(const DcArgs& a, const DcAnn& an, const typename DcRaw<DK>::raw_t (&raw)[U],
                                                     float2* __restrict__ stage, const long long nlo, const int i0,
-                                                    const int n_stage, const int lo, const int hi, const int pad) {
+                                                    const int n_stage, const int lo, const int hi, const int pad, const int qoff) {
     using LD = typename DcRaw<DK>::LD;
     const float2 wstep = nco_phasor(an.phase_step * (unsigned long long)kDcThreads);
     const pk2 W = pack2(wstep.x, wstep.y), iW = pack2(-wstep.y, wstep.x);
@@ -158,18 +179,18 @@ __device__ __forceinline__ void dc_stage_batch_impl(const DcArgs& a, const DcAnn
         if (!INTERIOR && (ii < lo || ii >= hi)) Y = pack2(0.f, 0.f);             // zero history / zero tail of the filter
         float yx, yy;
         unpack2(Y, yx, yy);
-        if (ii < n_stage) sts64(stage_s + 8u * (unsigned)(ii + (int)__umulhi((unsigned)ii, qmagic)), yx, yy);
+        if ((unsigned)ii < (unsigned)n_stage) sts64(stage_s + 8u * (unsigned)(ii + (int)__umulhi((unsigned)(ii + qoff), qmagic)), yx, yy);
         if (u + 1 < U) P = fma2(pack2(py, py), iW, mul2(pack2(px, px), W));
     }
 }
 template <int DK, bool SWAP, int U>
 __device__ __forceinline__ void dc_stage_batch(const DcArgs& a, const DcAnn& an, const typename DcRaw<DK>::raw_t (&raw)[U],
                                                float2* __restrict__ stage, const long long nlo, const int i0,
-                                               const int n_stage, const int lo, const int hi, const int pad) {
+                                               const int n_stage, const int lo, const int hi, const int pad, const int qoff) {
     if (lo == 0 && hi == n_stage)
-        dc_stage_batch_impl<DK, SWAP, U, true>(a, an, raw, stage, nlo, i0, n_stage, lo, hi, pad);
+        dc_stage_batch_impl<DK, SWAP, U, true>(a, an, raw, stage, nlo, i0, n_stage, lo, hi, pad, qoff);
     else
-        dc_stage_batch_impl<DK, SWAP, U, false>(a, an, raw, stage, nlo, i0, n_stage, lo, hi, pad);
+        dc_stage_batch_impl<DK, SWAP, U, false>(a, an, raw, stage, nlo, i0, n_stage, lo, hi, pad, qoff);
 }
 
 constexpr int kDcUnrollMax = 16;      // loads in flight per thread of the non-pipelined variant (16-byte pairs: 8)
@@ -184,7 +205,7 @@ constexpr int kDcUnrollMax = 16;      // loads in flight per thread of the non-p
 // from a vector register only, so the taps still travel LDCU -> MOV -> register pair: 19 instructions per tap row
 // against 13 for the run-time loop, whose LDC.64 lands the tap pairs in vector registers directly.)
 template <int DK, bool PTAPS, bool PIPE>
-__global__ void __launch_bounds__(kDcThreads, PIPE ? 3 : 4)
+__global__ void __launch_bounds__(kDcThreads, PIPE ? SA_DC_PIPE_CTAS : 4)
 downconvert_kernel(const DcArgs a, const __grid_constant__ DcTapParams tp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using raw_t = typename DcRaw<DK>::raw_t;
@@ -197,11 +218,21 @@ downconvert_kernel(const DcArgs a, const __grid_constant__ DcTapParams tp) {
     const long long tile_end = min(n_tiles, tile + a.tiles_per_cta);
     if (tile >= tile_end) return;
     const int pad = (D & 1) ? 0 : 1;                  // odd stride between blocks: conflict-free LDS.64
-    float2* stage = reinterpret_cast<float2*>(smem_raw);
+    const int qoff = an.fast ? 0 : D - 1;             // where the pad element sits (dc_stage_batch)
     const int halo = an.fast ? 0 : 7;
     const float* h = a.taps + an.taps_off;
     const float* ht = h + 8 * D + 1;
     const float h_last = PTAPS ? tp.h_last : h[8 * D];
+    // PIPE: the transposed tap rows sit in front of the staged tile (two broadcast LDS.128 per tap row instead of four
+    // LDC.64 from the parameter bank); they become visible with the barrier that follows the first staging step
+    const int tap_bytes = PIPE ? dc_tap_smem_bytes(D) : 0;
+    const uint32_t taps_s = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    if constexpr (PIPE) {
+        float* tsm = reinterpret_cast<float*>(smem_raw);
+        for (int i = threadIdx.x; i < 8 * D; i += kDcThreads) tsm[i] = __ldg(&ht[i]);
+    }
+    float2* stage = reinterpret_cast<float2*>(smem_raw + tap_bytes);
+    const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
 
     // geometry of a tile (the last one of an annotation may be short)
     auto geom = [&](long long tl, int& nbt, int& nblk, int& n_stage, long long& nlo, int& lo, int& hi) {
@@ -217,18 +248,18 @@ downconvert_kernel(const DcArgs a, const __grid_constant__ DcTapParams tp) {
     long long nlo;
     geom(tile, nbt, nblk, n_stage, nlo, lo, hi);
     raw_t raw[U];
-    if constexpr (PIPE) dc_load_batch<DK, U>(a, an, raw, nlo, 0, n_stage, lo, hi);
+    if constexpr (PIPE) dc_load_batch<DK, U>(a, an, raw, nlo, -qoff, n_stage, lo, hi);
     for (; tile < tile_end; tile++) {
         const long long m0 = tile * an.nb;
         // ---- stage: decode + mix once into shared memory
         if constexpr (PIPE) {
-            if (a.lp.swap) dc_stage_batch<DK, true, U>(a, an, raw, stage, nlo, 0, n_stage, lo, hi, pad);
-            else           dc_stage_batch<DK, false, U>(a, an, raw, stage, nlo, 0, n_stage, lo, hi, pad);
+            if (a.lp.swap) dc_stage_batch<DK, true, U>(a, an, raw, stage, nlo, -qoff, n_stage, lo, hi, pad, qoff);
+            else           dc_stage_batch<DK, false, U>(a, an, raw, stage, nlo, -qoff, n_stage, lo, hi, pad, qoff);
         } else {
-            for (int i0 = 0; i0 < n_stage; i0 += kDcThreads * U) {
+            for (int i0 = -qoff; i0 < n_stage; i0 += kDcThreads * U) {
                 dc_load_batch<DK, U>(a, an, raw, nlo, i0, n_stage, lo, hi);
-                if (a.lp.swap) dc_stage_batch<DK, true, U>(a, an, raw, stage, nlo, i0, n_stage, lo, hi, pad);
-                else           dc_stage_batch<DK, false, U>(a, an, raw, stage, nlo, i0, n_stage, lo, hi, pad);
+                if (a.lp.swap) dc_stage_batch<DK, true, U>(a, an, raw, stage, nlo, i0, n_stage, lo, hi, pad, qoff);
+                else           dc_stage_batch<DK, false, U>(a, an, raw, stage, nlo, i0, n_stage, lo, hi, pad, qoff);
             }
         }
         __syncthreads();
@@ -236,7 +267,7 @@ downconvert_kernel(const DcArgs a, const __grid_constant__ DcTapParams tp) {
         if constexpr (PIPE) {           // next tile's samples fly under this tile's arithmetic
             if (tile + 1 < tile_end) {
                 geom(tile + 1, nbt, nblk, n_stage, nlo, lo, hi);
-                dc_load_batch<DK, U>(a, an, raw, nlo, 0, n_stage, lo, hi);
+                dc_load_batch<DK, U>(a, an, raw, nlo, -qoff, n_stage, lo, hi);
             }
         }
         const int stage_phys = c_nstage + c_nstage / D + 2;
@@ -260,20 +291,33 @@ downconvert_kernel(const DcArgs a, const __grid_constant__ DcTapParams tp) {
                 pk2 ax[4], ay[4];
 #pragma unroll
                 for (int p = 0; p < 4; p++) { ax[p] = pack2(0.f, 0.f); ay[p] = pack2(0.f, 0.f); }
-                // block b (local) holds staged indices (b+1)*D - r, r = 0..D-1
-                const float2* s_hi = stage + (b + 1) * (D + pad);       // r = 0 sits here (next block's slot 0)
-                const float2* s_lo = stage + b * (D + pad) + D;         // r > 0: b*(D+pad) + D - r
+                // block b (local) multiplies y[(b+1)D - r], r = 0..D-1: staged at (b+1)(D+pad) - r
+                const uint32_t s_top = stage_s + 8u * (unsigned)((b + 1) * (D + pad));
                 const float4* t4 = reinterpret_cast<const float4*>(ht);
                 // (unrolling this loop by 4 to amortise its uniform-datapath control, ~4 of 52 instructions per input sample,
                 // measured slower: C3 1.66 -> 1.74 ms)
+                float2 s_n;
+                float4 ta_n, tb_n;
+                if constexpr (PIPE && SA_DC_SWP) { s_n = lds64(s_top); ta_n = lds128(taps_s); tb_n = lds128(taps_s + 16u); }
                 for (int r = 0; r < D; r++) {
-                    const float2 s = (r == 0) ? s_hi[0] : s_lo[-r];
+                    float2 s;
                     float4 ta, tb;
-                    if constexpr (PTAPS) {
-                        ta = make_float4(tp.ht[8 * r], tp.ht[8 * r + 1], tp.ht[8 * r + 2], tp.ht[8 * r + 3]);
-                        tb = make_float4(tp.ht[8 * r + 4], tp.ht[8 * r + 5], tp.ht[8 * r + 6], tp.ht[8 * r + 7]);
+                    if constexpr (PIPE && SA_DC_SWP) {
+                        // software pipeline: row r + 1 is in flight under row r's arithmetic (the read past the last row
+                        // lands in the block below / the first staged sample: valid shared memory, value unused)
+                        s = s_n; ta = ta_n; tb = tb_n;
+                        s_n = lds64(s_top - 8u * (unsigned)(r + 1));
+                        ta_n = lds128(taps_s + 32u * (unsigned)(r + 1)); tb_n = lds128(taps_s + 32u * (unsigned)(r + 1) + 16u);
                     } else {
-                        ta = __ldg(&t4[2 * r]); tb = __ldg(&t4[2 * r + 1]);
+                        s = lds64(s_top - 8u * (unsigned)r);
+                        if constexpr (PIPE) {
+                            ta = lds128(taps_s + 32u * (unsigned)r); tb = lds128(taps_s + 32u * (unsigned)r + 16u);
+                        } else if constexpr (PTAPS) {
+                            ta = make_float4(tp.ht[8 * r], tp.ht[8 * r + 1], tp.ht[8 * r + 2], tp.ht[8 * r + 3]);
+                            tb = make_float4(tp.ht[8 * r + 4], tp.ht[8 * r + 5], tp.ht[8 * r + 6], tp.ht[8 * r + 7]);
+                        } else {
+                            ta = __ldg(&t4[2 * r]); tb = __ldg(&t4[2 * r + 1]);
+                        }
                     }
                     const pk2 sx = pack2(s.x, s.x), sy = pack2(s.y, s.y);
                     const pk2 t01 = pack2(ta.x, ta.y), t23 = pack2(ta.z, ta.w), t45 = pack2(tb.x, tb.y), t67 = pack2(tb.z, tb.w);

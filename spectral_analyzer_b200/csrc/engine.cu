@@ -738,6 +738,13 @@ int Engine::launch_spectrogram(const void* d_iq, uint64_t n_samples, const sa_sp
     const bool use_r64 = r64_env ? (strcmp(r64_env, "all") == 0) : (dk == DK_CF32 || dk == DK_CI16);
     // (the radix-64 kernel has its own store code: pooled launches take the small-radix-first kernel)
     if (!k && aligned && use_r64 && !pool_mode && prec == SA_PREC_F32 && p.nfft == 4096) k = find_spec_kernel(prec, 4096, dk, win, 4);
+    // 2048: two warp-private 1024-point transforms + a radix-2 combine.  Opt-in (SA_SPLIT=1): measured against the
+    // three-pass kernel on cu8 input it executes the same 43.8 instructions per point with 29 % fewer shared-memory
+    // wavefronts and runs 2.02 vs 2.00 ms per 2^30 samples (f32 dB), 4.81 vs 4.51 ms per 2^31 (RGBA): both kernels
+    // wait on the FMA pipe, not on shared memory
+    const char* split_env = getenv("SA_SPLIT");
+    const bool use_split = split_env ? atoi(split_env) != 0 : false;
+    if (!k && aligned && use_split && !pool_mode && prec == SA_PREC_F32 && p.nfft == 2048) k = find_spec_kernel(prec, 2048, dk, win, 5);
     if (!k && aligned && !no_mid) {                                                        // small-radix-first plan
         // the asynchronously staged variant where it measured faster on B200 (tools/mid_pf_matrix.py): 2048 (8 frames
         // per CTA) and 16384 (one frame owns the SM) gain 6-19 %, 4096 (4 frames per CTA) 0-10 %, 8192 loses up to 19 %.
@@ -772,7 +779,7 @@ int Engine::launch_spectrogram(const void* d_iq, uint64_t n_samples, const sa_sp
     launches++;
     {
         static const char* const fam[] = { "spectrogram_kernel", "spectrogram_tma_kernel", "spectrogram_mid_kernel",
-                                           "spectrogram_mid_kernel(prefetch)", "spectrogram_r64_kernel" };
+                                           "spectrogram_mid_kernel(prefetch)", "spectrogram_r64_kernel", "spectrogram_split_kernel" };
         static const char* const dkn[] = { "cf32", "ci16", "c8", "cf64" };
         char nm[128];
         snprintf(nm, sizeof(nm), "%s<%s,%d,%s,%s>", fam[k->tma], prec == SA_PREC_F64 ? "double" : "float", k->n, dkn[k->dk],

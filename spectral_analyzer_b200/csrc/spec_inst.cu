@@ -3,6 +3,7 @@
 #include "spectrogram_tma_kernel.cuh"
 #include "spectrogram_mid_kernel.cuh"
 #include "spectrogram_r64_kernel.cuh"
+#include "spectrogram_split_kernel.cuh"
 
 #ifndef SA_INST_PREC
 #error "compile with -DSA_INST_PREC=1|2 -DSA_INST_N=<nfft>"
@@ -44,6 +45,15 @@ struct Registrar {
         register_spec_kernel(make_spec_mid_info<SA_INST_N, DK_CI16, true, true>());
         register_spec_kernel(make_spec_mid_info<SA_INST_N, DK_C8, false, true>());
         register_spec_kernel(make_spec_mid_info<SA_INST_N, DK_C8, true, true>());
+#endif
+#if SA_INST_N == 2048
+        // two warp-private 1024-point transforms + one radix-2 combine (16-byte aligned frames)
+        register_spec_kernel(make_spec_split_info<DK_CF32, false>());
+        register_spec_kernel(make_spec_split_info<DK_CF32, true>());
+        register_spec_kernel(make_spec_split_info<DK_CI16, false>());
+        register_spec_kernel(make_spec_split_info<DK_CI16, true>());
+        register_spec_kernel(make_spec_split_info<DK_C8, false>());
+        register_spec_kernel(make_spec_split_info<DK_C8, true>());
 #endif
 #if SA_INST_N == 4096
         // two-pass radix-64 plan (default for cf32 / ci16 input with 16-byte aligned frames)

@@ -426,3 +426,33 @@ def test_onchip_cluster_four_step(engine, monkeypatch, dt, prec, kind):
         g3 = engine.spectrogram(raw, dt, nfft, 3, hop=nfft + 1, precision=prec, out_kind=kind)     # odd hop: frames 8-byte aligned only
         assert engine.last_kernel.startswith("large_cols_kernel+large_rows_kernel")
         check_db_parity(g3[1:2], co.spectrogram(raw, dt, nfft + 1, nfft, nfft, "rect", 1))
+
+
+@pytest.mark.parametrize("dt", ["cf32_le", "cf32_be", "ci16_le", "ci16_be", "cu8", "ci8"])
+@pytest.mark.parametrize("win,hop", [("hann", 1024), ("rect", 2048)])
+def test_split_2048_kernel(engine, monkeypatch, dt, win, hop):
+    """Opt-in alternative for nfft 2048 (SA_SPLIT=1): two warp-private 1024-point transforms of the even / odd samples and
+    a radix-2 combine (spectrogram_split_kernel.cuh).  More frames than one pass of the grid, two trailing EOF rows;
+    against the oracle, against the default three-pass kernel, and through the RGBA and FP64-row epilogues."""
+    nfft, frames = 2048, 1500
+    raw = synth.recording((frames - 3) * hop + nfft, dt, seed=77)
+    monkeypatch.setenv("SA_SPLIT", "1")
+    got = engine.spectrogram(raw, dt, nfft, frames, hop=hop, window=win)
+    assert engine.last_kernel.startswith("spectrogram_split_kernel<float,2048,")
+    assert (got[-2:] == -150.0).all()
+    for f in (0, 1, 777, frames - 3):
+        check_db_parity(got[f:f + 1], co.spectrogram(raw, dt, f * hop, nfft, hop, win, 1))
+    g64 = engine.spectrogram(raw, dt, nfft, 40, hop=hop, window=win, out_kind="f64")
+    assert np.array_equal(g64, got[:40].astype(np.float64))
+    rgba = engine.spectrogram(raw, dt, nfft, 40, hop=hop, window=win, out_kind="rgba8", colormap="Heatmap", sample_rate=2.4e6)
+    odd = engine.spectrogram(raw, dt, nfft, 5, hop=hop + 1, window=win)                    # frames not 16-byte aligned
+    assert not engine.last_kernel.startswith("spectrogram_split_kernel")
+    monkeypatch.setenv("SA_SPLIT", "0")
+    three = engine.spectrogram(raw, dt, nfft, frames, hop=hop, window=win)
+    assert engine.last_kernel.startswith("spectrogram_mid_kernel")
+    strong = three > three.max(axis=1, keepdims=True) - 40
+    assert np.abs(three - got)[strong].max() < 1e-4       # two factorizations, same answer to FP32 rounding
+    rgba3 = engine.spectrogram(raw, dt, nfft, 40, hop=hop, window=win, out_kind="rgba8", colormap="Heatmap", sample_rate=2.4e6)
+    d = np.abs(rgba.astype(np.int32) - rgba3.astype(np.int32))
+    assert d.max() <= 255 and (d > 1).mean() < 1e-3       # +-1 LSB apart from pixels on a Heatmap breakpoint
+    check_db_parity(odd[:1], co.spectrogram(raw, dt, 0, nfft, hop + 1, win, 1))
