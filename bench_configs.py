@@ -102,7 +102,8 @@ def annotation_case(eng, n_samples, n_ann, count, down, steps, want_iq=True):
                       % (n_ann, count.bit_length() - 1, down, "" if want_iq else ", PSD only (no decimated IQ written)"),
             "annotations": n_ann, "count": count, "down": down, "psd_nfft": 8192,
             "ms": round(ms, 4), "Msamples_per_s": round(n_ann * count / ms / 1e3, 1), "alg_bytes": alg,
-            "GBps": round(alg / ms / 1e6, 1), "roofline_frac": round(alg / ms / 1e6 / peak, 4), "peak_kind": kind_p}
+            "GBps": round(alg / ms / 1e6, 1), "roofline_frac": round(alg / ms / 1e6 / peak, 4), "peak_kind": kind_p,
+            "kernel": eng.last_kernel}
 
 
 def canvas_case(eng, n_samples, nfft, hop, W, H, reduce, steps, host=True):

@@ -226,6 +226,9 @@ static int welch_launch(Engine* eng, const WelchLaunch& wl, const WelchSig* d_si
         e = cudaLaunchKernel(wk->fin, dim3((n + 255) / 256, n_sig), dim3(256), fargs, 0, stream);
         if (e != cudaSuccess) return cuda_fail(e, "launch welch_finalize_kernel");
         eng->launches++;
+        char nm[96];
+        snprintf(nm, sizeof(nm), "welch_accum_kernel<%s,%d>", wl.prec == SA_PREC_F64 ? "double" : "float", wk->n);
+        eng->last_kernel = nm;
     } else {
         const void* fn = wl.prec == SA_PREC_F64 ? (const void*)&psd_direct_kernel<double> : (const void*)&psd_direct_kernel<float>;
         int bps = 0;
@@ -236,6 +239,7 @@ static int welch_launch(Engine* eng, const WelchLaunch& wl, const WelchSig* d_si
         e = cudaLaunchKernel(fn, dim3((nfft + 255) / 256, n_sig), dim3(256), dargs, wl.direct_smem, stream);
         if (e != cudaSuccess) return cuda_fail(e, "launch psd_direct_kernel");
         eng->launches++;
+        eng->last_kernel = wl.prec == SA_PREC_F64 ? "psd_direct_kernel<double>" : "psd_direct_kernel<float>";
     }
     // rows -> their destinations (contiguous runs collapse into one copy)
     for (uint32_t i = 0; i < n_sig && e == cudaSuccess && !contiguous;) {
@@ -445,6 +449,8 @@ static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, i
     DcTapParams tp;                      // copied into the launch by cudaLaunchKernel (kernel-parameter bank)
     tp.h_last = 0.f; tp.down = 0;
     void* args[] = { &da, &tp };
+    const char* dc_name = "";            // family of the last downconverter launch (sa_last_kernel_name)
+    bool any_welch = false;
     uint32_t pos = 0;                    // position in `sorted`
     size_t sig_pos = 0;                  // position in the uploaded WelchSig array
     for (size_t bi = 0; bi < batches.size(); bi++) {
@@ -465,6 +471,7 @@ static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, i
                     e = cudaLaunchKernel(dc_kernel(dk, 2), dim3((unsigned)tiles, g1 - g0), dim3(256), args, 0, s);
                     if (e != cudaSuccess) return cuda_fail(e, "launch downconvert_wide_kernel");
                     eng->launches++;
+                    dc_name = "downconvert_wide_kernel";
                 }
             } else {
                 long long tiles = 0;
@@ -495,6 +502,7 @@ static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, i
                     e = cudaLaunchKernel(fn, dim3((unsigned)ctas, g1 - g0), dim3(kDcThreads), args, smem, s);
                     if (e != cudaSuccess) return cuda_fail(e, "launch downconvert_kernel");
                     eng->launches++;
+                    dc_name = pipe ? "downconvert_kernel(pipelined)" : "downconvert_kernel";
                 }
             }
             g0 = g1;
@@ -509,10 +517,12 @@ static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, i
             for (auto& wl : welch[bi]) {
                 rc = welch_launch(eng, wl, d_sigs + sig_pos, s, par);
                 if (rc) return rc;
+                if (!wl.sigs.empty()) any_welch = true;
                 sig_pos += wl.sigs.size();
             }
         }
     }
+    eng->last_kernel = any_welch ? std::string(dc_name) + "+" + eng->last_kernel : std::string(dc_name);
     if (dual) {
         e = cudaEventRecord(eng->dc_ev[1], eng->dc_aux);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, eng->dc_ev[1], 0);
