@@ -57,6 +57,10 @@ struct DcTapParams {
 };
 
 constexpr int kDcThreads = 256;
+// Ablation switches of the pipelined downconverter (measured on C3, 500 x 2^20 cf32 samples, D 16, same box):
+//   default (3 CTAs/SM, 80 registers, tap loop as written)        1.661 ms
+//   SA_DC_SWP=1 (next tap row's loads issued under this row's FMAs)  1.712 ms  -- needs > 85 registers: spills
+//   SA_DC_SWP=1 SA_DC_PIPE_CTAS=2 (127 registers, no spills)        1.618 ms for cf32, but 2-5 % slower for ci16 / cu8
 #ifndef SA_DC_PIPE_CTAS
 #define SA_DC_PIPE_CTAS 3
 #endif
