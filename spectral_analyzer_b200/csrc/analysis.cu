@@ -34,7 +34,7 @@ void lowpass_taps(int down, std::vector<double>& h) {
     for (int k = 0; k < nt; k++) h[k] /= sum;
 }
 
-struct WelchKernel { const void* fn; const void* fin; int prec, n, cta, fpc; size_t smem; int p, np, radix[4]; };
+struct WelchKernel { const void* fn; const void* fin; int prec, n, cta, fpc; size_t smem; int p, np, radix[4]; int mid; };
 
 template <typename T, int N> WelchKernel make_welch(int prec) {
     using G = Geo<T, N>;
@@ -45,10 +45,27 @@ template <typename T, int N> WelchKernel make_welch(int prec) {
     k.prec = prec;
     k.n = N; k.cta = G::CTA; k.fpc = G::FPC; k.smem = G::SMEM_BYTES + G::TW_BYTES; k.p = G::P; k.np = PL::NP;
     for (int i = 0; i < 4; i++) k.radix[i] = PL::radix(i);
+    k.mid = 0;
+    return k;
+}
+// FP32 2048 .. 16384: the small-radix-first plan (welch_accum_mid_kernel)
+template <int N> WelchKernel make_welch_mid() {
+    using G = MidGeo<N>;
+    WelchKernel k;
+    k.fn = (const void*)&welch_accum_mid_kernel<N>;
+    k.fin = (const void*)&welch_finalize_kernel<float>;
+    k.prec = 1;
+    k.n = N; k.cta = G::CTA; k.fpc = G::FPC; k.smem = G::EX_BYTES + G::T1_BYTES + G::WIN_BYTES; k.p = 32; k.np = 3;
+    k.radix[0] = G::R0; k.radix[1] = 32; k.radix[2] = 32; k.radix[3] = 1;
+    k.mid = 1;
     return k;
 }
 
 const WelchKernel* find_welch(int prec, int n) {
+    static const bool no_mid = getenv("SA_WELCH_MID") && atoi(getenv("SA_WELCH_MID")) == 0;     // A/B: the general plan
+    static const WelchKernel mid_tab[] = { make_welch_mid<2048>(), make_welch_mid<4096>(), make_welch_mid<8192>(), make_welch_mid<16384>() };
+    if (prec == 1 && !no_mid)
+        for (const auto& k : mid_tab) if (k.n == n) return &k;
     static const WelchKernel tab[] = {
         make_welch<float, 64>(1), make_welch<float, 128>(1), make_welch<float, 256>(1), make_welch<float, 512>(1),
         make_welch<float, 1024>(1), make_welch<float, 2048>(1), make_welch<float, 4096>(1), make_welch<float, 8192>(1),
@@ -208,7 +225,13 @@ static int welch_launch(Engine* eng, const WelchLaunch& wl, const WelchSig* d_si
         memset(&ki, 0, sizeof(ki));
         ki.prec = wl.prec; ki.n = wk->n; ki.p = wk->p; ki.np = wk->np;
         for (int i = 0; i < 4; i++) ki.radix[i] = wk->radix[i];
-        rc = eng->twiddle_table(ki, &wa.twiddle);
+        if (wk->mid) {
+            rc = eng->mid_t1_table(wk->n, &wa.twiddle);
+            if (rc) return rc;
+            rc = eng->root_table(wk->n, wl.prec, &wa.aux);
+        } else {
+            rc = eng->twiddle_table(ki, &wa.twiddle);
+        }
         if (rc) return rc;
         rc = eng->window_table(wl.window, (int)nfft, wl.prec, &wa.window);
         if (rc) return rc;
@@ -227,7 +250,8 @@ static int welch_launch(Engine* eng, const WelchLaunch& wl, const WelchSig* d_si
         if (e != cudaSuccess) return cuda_fail(e, "launch welch_finalize_kernel");
         eng->launches++;
         char nm[96];
-        snprintf(nm, sizeof(nm), "welch_accum_kernel<%s,%d>", wl.prec == SA_PREC_F64 ? "double" : "float", wk->n);
+        snprintf(nm, sizeof(nm), "%s<%s,%d>", wk->mid ? "welch_accum_mid_kernel" : "welch_accum_kernel",
+                 wl.prec == SA_PREC_F64 ? "double" : "float", wk->n);
         eng->last_kernel = nm;
     } else {
         const void* fn = wl.prec == SA_PREC_F64 ? (const void*)&psd_direct_kernel<double> : (const void*)&psd_direct_kernel<float>;
@@ -332,11 +356,11 @@ static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, i
         uint32_t b0 = 0;
         uint64_t acc = 0;
         for (uint32_t i = 0; i < n_ann; i++) {
-            if (i > b0 && ((want_psd && acc + (uint64_t)plan[i].m_out > scr_cap_elems) || i - b0 >= max_per_batch)) {
+            if (i > b0 && ((want_psd && acc + (uint64_t)plan[i].m_out + 1 > scr_cap_elems) || i - b0 >= max_per_batch)) {
                 batches.push_back({b0, i}); b0 = i; acc = 0;
             }
             plan[i].scr_off = (long long)acc;
-            acc += (uint64_t)plan[i].m_out;
+            acc += ((uint64_t)plan[i].m_out + 1) & ~(uint64_t)1;       // rows start 16-byte aligned (128-bit loads of the Welch kernel)
             if (want_psd) scr_total = std::max(scr_total, acc);
         }
         batches.push_back({b0, n_ann});

@@ -16,6 +16,7 @@
 //           AnalysisDialogController.java:304-307, passes nfft = signal length)
 #pragma once
 #include "decode.cuh"
+#include "spectrogram_mid_kernel.cuh"
 
 namespace sa {
 
@@ -57,16 +58,22 @@ struct DcTapParams {
 };
 
 constexpr int kDcThreads = 256;
-// Ablation switches of the pipelined downconverter (measured on C3, 500 x 2^20 cf32 samples, D 16, same box):
-//   default (3 CTAs/SM, 80 registers, tap loop as written)        1.661 ms
-//   SA_DC_SWP=1 (next tap row's loads issued under this row's FMAs)  1.712 ms  -- needs > 85 registers: spills
-//   SA_DC_SWP=1 SA_DC_PIPE_CTAS=2 (127 registers, no spills)        1.618 ms for cf32, but 2-5 % slower for ci16 / cu8
+// Shape of the pipelined downconverter per input type (measured on C3, 500 x 2^20 samples, D 16, and over D = 2..32 with
+// tools/dc_matrix.py, same box):
+//   3 CTAs/SM, 80 registers, tap loop as written                      cf32 1.661 ms
+//   + next tap row's loads issued under this row's FMAs (SWP)          cf32 1.712 ms  -- needs > 85 registers: spills
+//   SWP at 2 CTAs/SM (127 registers, no spills)                        cf32 1.618 ms (1.5-4 % faster at every D);
+//                                                                      ci16 / cu8 2-6 % SLOWER at every D
+// cf32 holds 34 registers of raw samples in flight per thread, the integer types 17: cf32 takes the 2-CTA software-pipelined
+// shape, the others stay at 3 CTAs.  -DSA_DC_SWP=0|1 / -DSA_DC_PIPE_CTAS=n force one shape for all types.
 #ifndef SA_DC_PIPE_CTAS
-#define SA_DC_PIPE_CTAS 3
+#define SA_DC_PIPE_CTAS 0       // 0: per type
 #endif
 #ifndef SA_DC_SWP
-#define SA_DC_SWP 0
+#define SA_DC_SWP -1            // -1: per type
 #endif
+template <int DK> __host__ __device__ constexpr bool dc_swp() { return SA_DC_SWP < 0 ? DK == DK_CF32 : SA_DC_SWP != 0; }
+template <int DK> __host__ __device__ constexpr int dc_pipe_ctas() { return SA_DC_PIPE_CTAS > 0 ? SA_DC_PIPE_CTAS : (DK == DK_CF32 ? 2 : 3); }
 constexpr int kDcStage = 8192;       // staged samples per tile (shared memory budget)
 constexpr int kDcMaxDown = 512;      // larger decimations take the warp-per-output kernel
 constexpr int kDcPipeLoads = 17;     // pipelined variant: the whole tile (<= 17 x 256 samples) is one register batch
@@ -209,7 +216,7 @@ constexpr int kDcUnrollMax = 16;      // loads in flight per thread of the non-p
 // from a vector register only, so the taps still travel LDCU -> MOV -> register pair: 19 instructions per tap row
 // against 13 for the run-time loop, whose LDC.64 lands the tap pairs in vector registers directly.)
 template <int DK, bool PTAPS, bool PIPE>
-__global__ void __launch_bounds__(kDcThreads, PIPE ? SA_DC_PIPE_CTAS : 4)
+__global__ void __launch_bounds__(kDcThreads, PIPE ? dc_pipe_ctas<DK>() : 4)
 downconvert_kernel(const DcArgs a, const __grid_constant__ DcTapParams tp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using raw_t = typename DcRaw<DK>::raw_t;
@@ -302,11 +309,11 @@ downconvert_kernel(const DcArgs a, const __grid_constant__ DcTapParams tp) {
                 // measured slower: C3 1.66 -> 1.74 ms)
                 float2 s_n;
                 float4 ta_n, tb_n;
-                if constexpr (PIPE && SA_DC_SWP) { s_n = lds64(s_top); ta_n = lds128(taps_s); tb_n = lds128(taps_s + 16u); }
+                if constexpr (PIPE && dc_swp<DK>()) { s_n = lds64(s_top); ta_n = lds128(taps_s); tb_n = lds128(taps_s + 16u); }
                 for (int r = 0; r < D; r++) {
                     float2 s;
                     float4 ta, tb;
-                    if constexpr (PIPE && SA_DC_SWP) {
+                    if constexpr (PIPE && dc_swp<DK>()) {
                         // software pipeline: row r + 1 is in flight under row r's arithmetic (the read past the last row
                         // lands in the block below / the first staged sample: valid shared memory, value unused)
                         s = s_n; ta = ta_n; tb = tb_n;
@@ -399,6 +406,7 @@ struct WelchArgs {
     long long hop;
     const void* window;    // T[N]
     const void* twiddle;
+    const void* aux;       // welch_accum_mid_kernel: roots W_N^j (twiddle = its pass-1 pair table)
     void* partial;         // T [sig][slot][N], slot = split * FPC + frame slot
     int nsplit;
     int detrend;           // 1: subtract the segment's mean before the window
@@ -485,6 +493,83 @@ welch_accum_kernel(const WelchArgs a) {
         }
     }
     T* part = reinterpret_cast<T*>(a.partial) + (((size_t)blockIdx.y * a.nsplit + blockIdx.x) * FPC + fl) * N;
+#pragma unroll
+    for (int q = 0; q < P; q++) part[t + TPF * q] = acc[q];
+}
+
+// FP32 segments of 2048 .. 16384 points on the small-radix-first plan of spectrogram_mid_kernel.cuh (R0 x 32 x 32, pass-1
+// twiddles from a tiny shared-memory table, pass-2 twiddles by the register recurrence, window folded into the first
+// butterfly stage) instead of the general plan's two table-driven passes: thread t owns S = 32 / R0 CONSECUTIVE samples of
+// each of the R0 slices of a segment -- 128-bit loads from the downconverter's FP32 rows when they are 16-byte aligned.
+template <int N>
+__global__ void __launch_bounds__(MidGeo<N>::CTA, MidGeo<N>::MINB)
+welch_accum_mid_kernel(const WelchArgs a) {
+    using G = MidGeo<N>;
+    constexpr int P = 32, R0 = G::R0, S = G::S, TPF = G::TPF, FPC = G::FPC;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ float2 red[32];
+    const int fl = threadIdx.x / TPF, t = threadIdx.x % TPF;
+    float2* sm = reinterpret_cast<float2*>(smem_raw) + (size_t)fl * G::SM_ELEMS;
+    TwPair<float>* t1 = reinterpret_cast<TwPair<float>*>(smem_raw + G::EX_BYTES);
+    float* wsm = reinterpret_cast<float*>(smem_raw + G::EX_BYTES + G::T1_BYTES);
+    mid_setup_tables<N, true>(a.twiddle, a.window, t1, wsm);
+    __syncthreads();
+    const float* win = wsm + t * G::WROW;
+    TwSeed<float> seed;
+    {
+        const float2* root = reinterpret_cast<const float2*>(a.aux);
+        seed.om = __ldg(&root[t]);
+        seed.oh = __ldg(&root[(16 * t) & (N - 1)]);
+        seed.q_lo = seed.om; seed.q_hi = seed.om;
+    }
+    const TwPair<float>* t1_row = t1 + (t % R0);
+    const WelchSig sg = a.sigs[blockIdx.y];
+    // 128-bit loads: FP32 rows whose every slice start is 16-byte aligned (S t is even for every plan; hop and row start must be)
+    const bool vec = sg.f32 && ((reinterpret_cast<uintptr_t>(sg.f32) & 15) == 0) && ((a.hop & 1) == 0);
+    float acc[P];
+#pragma unroll
+    for (int q = 0; q < P; q++) acc[q] = 0.f;
+    const long long stride = (long long)a.nsplit * FPC;
+    const long long iters = (sg.nseg + stride - 1) / stride;
+    for (long long it = 0; it < iters; it++) {
+        const long long seg = it * stride + (long long)blockIdx.x * FPC + fl;
+        const bool valid = seg < sg.nseg;
+        float2 v[P];
+        if (valid) {
+            const long long s0 = seg * a.hop + (long long)S * t;
+            if (vec) {
+#pragma unroll
+                for (int m = 0; m < R0; m++) {
+                    const float4* p = reinterpret_cast<const float4*>(sg.f32 + s0 + (long long)m * (N / R0));
+#pragma unroll
+                    for (int i = 0; i < S; i += 2) {
+                        const float4 x = __ldg(p + i / 2);
+                        v[i + S * m] = make_float2(x.x, x.y);
+                        v[i + 1 + S * m] = make_float2(x.z, x.w);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int m = 0; m < R0; m++)
+#pragma unroll
+                    for (int i = 0; i < S; i++) v[i + S * m] = welch_load<float>(sg, s0 + (long long)m * (N / R0) + i);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < P; q++) v[q] = make_float2(0.f, 0.f);
+        }
+        if (a.detrend) {                 // launch-uniform
+            const float2 m = frame_mean<float, TPF, P, G::CTA>(v, red);
+#pragma unroll
+            for (int q = 0; q < P; q++) { v[q].x -= m.x; v[q].y -= m.y; }
+        }
+        mid_fft<N, true>(v, t, fl, sm, win, t1_row, seed);
+        if (valid) {
+#pragma unroll
+            for (int q = 0; q < P; q++) acc[q] += __fmaf_rn(v[q].x, v[q].x, v[q].y * v[q].y);
+        }
+    }
+    float* part = reinterpret_cast<float*>(a.partial) + (((size_t)blockIdx.y * a.nsplit + blockIdx.x) * FPC + fl) * N;
 #pragma unroll
     for (int q = 0; q < P; q++) part[t + TPF * q] = acc[q];
 }

@@ -240,7 +240,7 @@ def test_psd_only_batch_matches_the_batch_with_rows(engine):
     _, psd_a = engine.downconvert_psd_batch(raw, "ci16_le", 1e6, anns, psd_nfft=4096, want_iq=True)
     none, psd_b = engine.downconvert_psd_batch(raw, "ci16_le", 1e6, anns, psd_nfft=4096, want_iq=False)
     assert none is None and np.array_equal(psd_a, psd_b)
-    assert engine.last_kernel == "downconvert_kernel(pipelined)+welch_accum_kernel<float,4096>"     # sa_last_kernel_name
+    assert engine.last_kernel == "downconvert_kernel(pipelined)+welch_accum_mid_kernel<float,4096>"     # sa_last_kernel_name
     ref = co.psd_welch(co.downconvert(raw, "ci16_le", *anns[7][:4], False), 1e6 / 4, 4096)
     strong = ref[1] > ref[1].max() - 40
     assert np.abs(psd_b[7] - ref[1])[strong].max() < 5e-3

@@ -61,10 +61,15 @@ def test_register_and_stack_budgets():
     worst = max(res.items(), key=lambda kv: kv[1]["STACK"])
     assert worst[1]["STACK"] <= 256, worst
     # downconverter: 64 registers -> 4 CTAs of 256 threads per SM; the pipelined variant (template flag PIPE, "ELb1ELb1E")
-    # carries the next tile's 17 raw samples in registers: <= 85 registers -> 3 CTAs per SM
+    # carries the next tile's 17 raw samples in registers: <= 85 registers -> 3 CTAs per SM; its cf32 instance ("ILi0E")
+    # is software-pipelined at 2 CTAs per SM (<= 128 registers, no spills)
     dc = {k: v for k, v in res.items() if "downconvert_kernel" in k}
     assert dc and any("ELb1ELb1E" in k for k in dc)
-    assert all(v["REG"] <= (85 if "ELb1ELb1E" in k else 64) and v["STACK"] <= 64 for k, v in dc.items()), dc
+    def budget(k):
+        if "ELb1ELb1E" not in k:
+            return 64, 64
+        return (128, 0) if "kernelILi0E" in k else (85, 64)
+    assert all(v["REG"] <= budget(k)[0] and v["STACK"] <= budget(k)[1] for k, v in dc.items()), dc
 
 
 def count(text, pattern):
