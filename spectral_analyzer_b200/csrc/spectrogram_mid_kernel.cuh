@@ -333,6 +333,9 @@ SpecKernelInfo make_spec_mid_info() {
     k.prec = 1; k.n = N; k.dk = DK; k.win = WIN ? 1 : 0;
     k.cta = G::CTA; k.fpc = G::FPC; k.minb = G::MINB;
     k.smem = G::EX_BYTES + G::T1_BYTES + (WIN ? G::WIN_BYTES : 0);
+#ifdef SA_MID_SMEM_PAD          // occupancy ablation: pad the request so that fewer CTAs fit an SM
+    if (k.smem < (size_t)SA_MID_SMEM_PAD) k.smem = (size_t)SA_MID_SMEM_PAD;
+#endif
     k.p = 32; k.np = 3; k.tma = PF ? 3 : 2;
     k.radix[0] = G::R0; k.radix[1] = 32; k.radix[2] = 32; k.radix[3] = 1;
     return k;
