@@ -181,8 +181,9 @@ SA_API int32_t sa_spectrogram_device(sa_engine* engine, const void* d_iq, uint64
  * into its pinned ring with several threads: no mapped buffer, no page-fault + memcpy hop.  out: host. */
 SA_API int32_t sa_spectrogram_file(sa_engine* engine, const char* path, uint64_t data_offset, uint64_t data_bytes,
                                    const sa_spectrogram_params* params, void* out, uint64_t out_bytes);
-/* name of the kernel the engine's last spectrogram launch selected, e.g.
- * "spectrogram_tma_kernel<float,1024,cf32,window>" (thread-local copy, never NULL) */
+/* name of the kernel family the engine's last launch selected, e.g.
+ * "spectrogram_tma_kernel<float,1024,cf32,window>", or for the analysis calls
+ * "downconvert_kernel(pipelined)+welch_accum_mid_kernel<float,8192>" (thread-local copy, never NULL) */
 SA_API const char* sa_last_kernel_name(sa_engine* engine);
 /* SpectralService.computeMagnitudes (SpectralService.java:33-85), kept for API compatibility:
  * one frame at byte offset start_byte, rect window, 20*log10(|X|+1e-10), fft-shifted, FP64 out. */
