@@ -258,6 +258,7 @@ downconvert_kernel(const DcArgs a, const __grid_constant__ DcTapParams tp) {
     int nbt, nblk, n_stage, lo, hi;
     long long nlo;
     geom(tile, nbt, nblk, n_stage, nlo, lo, hi);
+    const int nst0 = n_stage, phys0 = n_stage + n_stage / D + 2;
     raw_t raw[U];
     if constexpr (PIPE) dc_load_batch<DK, U>(a, an, raw, nlo, -qoff, n_stage, lo, hi);
     for (; tile < tile_end; tile++) {
@@ -281,7 +282,7 @@ downconvert_kernel(const DcArgs a, const __grid_constant__ DcTapParams tp) {
                 dc_load_batch<DK, U>(a, an, raw, nlo, -qoff, n_stage, lo, hi);
             }
         }
-        const int stage_phys = c_nstage + c_nstage / D + 2;
+        const int stage_phys = (c_nstage == nst0) ? phys0 : c_nstage + c_nstage / D + 2;      // one division per CTA, not per tile
         float2* csm_t = stage + ((stage_phys + 1) & ~1);               // C_p[b] at csm_t[p * nblk + b]
         double* out_re = a.out ? a.out + an.out_off + m0 : nullptr;
         double* out_im = a.out ? out_re + an.m_out : nullptr;
