@@ -512,8 +512,12 @@ static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, i
                 const size_t smem = dc_smem_bytes(D, first.nb, first.fast, pipe);
                 const void* fn = dc_kernel(dk, pipe ? 3 : (ptaps ? 1 : 0));
                 if (pipe) {
+                    // consecutive tiles per CTA: 8, or 16 when the launch still fills the GPU many times over (C3: 1.544 ->
+                    // 1.524 ms; 4 / 33 tiles per CTA measured slower); SA_DC_TILES overrides
                     static const char* te = getenv("SA_DC_TILES");
-                    da.tiles_per_cta = te && atoi(te) > 0 ? atoi(te) : kDcPipeTiles;
+                    const long long group_tiles = tiles * (long long)(g1 - g0);
+                    da.tiles_per_cta = te && atoi(te) > 0 ? atoi(te)
+                                     : (group_tiles >= 16LL * 2 * kDcPipeTiles * eng->num_sms ? 2 * kDcPipeTiles : kDcPipeTiles);
                 }
                 const long long ctas = (tiles + da.tiles_per_cta - 1) / da.tiles_per_cta;
                 if (ctas > 0) {
