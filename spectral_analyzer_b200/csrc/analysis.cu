@@ -97,6 +97,30 @@ const void* dc_kernel(int dk, int which) {
     }
 }
 
+// row-per-thread kernel (cf32, little-endian, power-of-two decimation): nullptr when there is none for this factor.
+// mode 0: taps and NCO phasors as shared-memory tables, FFMA2; mode 1: taps as constant-bank immediates, NCO recurrence
+template <int D> const void* dc_rows_kernel_of(int mode, size_t* smem) {
+    *smem = DcRowsGeo<D>::SMEM;
+    return mode == 0 ? (const void*)&downconvert_rows_kernel<D, 0> : (const void*)&downconvert_rows_kernel<D, 1>;
+}
+const void* dc_rows_kernel(int down, int mode, size_t* smem) {
+    switch (down) {
+        case 8:  return dc_rows_kernel_of<8>(mode, smem);
+        case 16: return dc_rows_kernel_of<16>(mode, smem);
+        case 32: return dc_rows_kernel_of<32>(mode, smem);
+        default: *smem = 0; return nullptr;
+    }
+}
+// kernel-parameter tap block of the row kernel (the layout of DcRowsTaps<D>): g[sg][i][p] = h[(p+1)D - i - sg], h[0], h[8D]
+static void dc_rows_taps(const float* h, int D, std::vector<float>& out) {
+    out.assign((size_t)2 * D * 8 + 4, 0.f);
+    for (int sg = 0; sg < 2; sg++)
+        for (int i = 0; i < D; i++)
+            for (int p = 0; p < 8; p++) out[((size_t)sg * D + i) * 8 + p] = h[(p + 1) * D - i - sg];
+    out[(size_t)2 * D * 8] = h[0];
+    out[(size_t)2 * D * 8 + 1] = h[8 * D];
+}
+
 size_t dc_smem_bytes(int down, int nb, int fast, bool pipe) {
     const int nblk = nb + (fast ? 0 : 7);
     const size_t n_stage = fast ? (size_t)nb * down : (size_t)nblk * down + 1;
@@ -296,7 +320,10 @@ static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, i
     std::vector<DcAnn> plan(n_ann);
     std::vector<float> taps;
     std::map<int, int> taps_off;
-    std::vector<char> piped(n_ann, 0);
+    std::vector<char> piped(n_ann, 0), rowsk(n_ann, 0);
+    // row-per-thread kernel: 16-byte cp.async of raw cf32 pairs, so little-endian cf32 from a 16-byte aligned base
+    static const char* rows_env = getenv("SA_DC_ROWS");
+    const bool rows_ok = (rows_env ? atoi(rows_env) != 0 : true) && dk == DK_CF32 && !big_endian && ((uintptr_t)d_iq & 15) == 0;
     uint64_t scr_total = 0;
     for (uint32_t i = 0; i < n_ann; i++) {
         DcAnn& a = plan[i];
@@ -327,8 +354,12 @@ static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, i
         a.taps_off = taps_off[D];
         a.qmagic = D > 1 ? (unsigned)(((1ull << 32) + (unsigned long long)D - 1) / (unsigned long long)D) : 0u;
         const bool wide = (a.fast ? (D > kDcStage / 8) : (D > kDcMaxDown)) || (!a.fast && L > 8 * D + 1);
+        size_t rows_smem = 0;
         if (wide) {
             a.nb = 0;                       // marks the warp-per-output kernel
+        } else if (rows_ok && !a.fast && dc_rows_kernel(D, 1, &rows_smem)) {
+            a.nb = kDcRowsOut;
+            rowsk[i] = 1;
         } else if (pipe_ok && !a.fast && D <= 32) {
             // pipelined variant: the whole tile is one register batch (<= 17 x 256 staged samples)
             // blocks per tile: the staged samples fill the register batch (n_stage + D - 1 <= 17 x 256) and the tile
@@ -376,7 +407,7 @@ static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, i
     sorted.reserve(n_ann);
     std::vector<uint32_t> order;
     order.reserve(n_ann);
-    auto key = [&](uint32_t i) { return std::make_tuple(plan[i].nb == 0 ? 2 : (piped[i] ? 0 : 1), plan[i].fast, plan[i].down); };
+    auto key = [&](uint32_t i) { return std::make_tuple(plan[i].nb == 0 ? 2 : (rowsk[i] ? 3 : (piped[i] ? 0 : 1)), plan[i].fast, plan[i].down); };
     for (auto& b : batches) {
         std::vector<uint32_t> o;
         for (uint32_t i = b.first; i < b.second; i++) o.push_back(i);
@@ -496,6 +527,31 @@ static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, i
                     if (e != cudaSuccess) return cuda_fail(e, "launch downconvert_wide_kernel");
                     eng->launches++;
                     dc_name = "downconvert_wide_kernel";
+                }
+            } else if (rowsk[order[g0]]) {     // row-per-thread kernel
+                long long tiles = 0;
+                for (uint32_t i = g0; i < g1; i++) tiles = std::max<long long>(tiles, (sorted[i].m_out + first.nb - 1) / first.nb);
+                size_t smem = 0;
+                static const char* me = getenv("SA_DC_ROWS_MODE");
+                const void* fn = dc_rows_kernel(first.down, me ? atoi(me) : 1, &smem);
+                std::vector<float> rt;
+                dc_rows_taps(taps.data() + first.taps_off, first.down, rt);
+                void* rargs[] = { &da, rt.data() };
+                static const char* te = getenv("SA_DC_ROWS_TILES");
+                const long long group_tiles = tiles * (long long)(g1 - g0);
+                da.tiles_per_cta = te && atoi(te) > 0 ? atoi(te) : (group_tiles >= 16LL * 16 * eng->num_sms ? 16 : 4);
+                const long long ctas = (tiles + da.tiles_per_cta - 1) / da.tiles_per_cta;
+                if (ctas > 0) {
+                    size_t& have = eng->dc_smem_set[fn];
+                    if (have < smem) {
+                        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                        if (e != cudaSuccess) return cuda_fail(e, "downconvert smem attribute");
+                        have = smem;
+                    }
+                    e = cudaLaunchKernel(fn, dim3((unsigned)ctas, g1 - g0), dim3(kDcRowsThreads), rargs, smem, s);
+                    if (e != cudaSuccess) return cuda_fail(e, "launch downconvert_rows_kernel");
+                    eng->launches++;
+                    dc_name = "downconvert_rows_kernel";
                 }
             } else {
                 long long tiles = 0;

@@ -125,6 +125,14 @@ __device__ __forceinline__ float2 nco_phasor(unsigned long long phase) {
     return make_float2(c, -s);
 }
 
+// the same evaluated in FP64 from the full 64-bit phase and rounded once: for phasors that are multiplied up in a
+// recurrence, where the 4e-7 absolute error of the fast sincos (and of a 24-bit angle) would grow with the step count
+__device__ __forceinline__ float2 nco_phasor_acc(unsigned long long phase) {
+    double s, c;
+    sincospi((double)(long long)phase * (1.0 / 9223372036854775808.0), &s, &c);
+    return make_float2((float)c, (float)-s);
+}
+
 __device__ __forceinline__ float2 lds64(uint32_t addr) {
     float2 v;
     asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
@@ -389,6 +397,227 @@ downconvert_wide_kernel(const DcArgs a) {
             a.out[an.out_off + an.m_out + m] = (double)zi;
         }
         if (a.scratch) a.scratch[an.scr_off + m] = make_float2(zr, zi);
+    }
+}
+
+// ---------------- row-per-thread downconverter (cf32, even power-of-two decimation) ----------------
+// The staged kernel above spends two thirds of its instructions moving samples (register batch -> decode -> NCO
+// recurrence -> padded shared-memory store -> LDS.64 per tap row).  Here the RAW tile goes global -> shared memory
+// with 16-byte cp.async (no registers, no per-sample address arithmetic: a thread's D/2 chunks differ by immediates),
+// and thread b owns ROW b = D consecutive raw samples, which it reads back as 128-bit loads (rows are D/2 | 1 chunks
+// apart: an odd stride, so the 8 lanes of a quarter-warp hit 8 different 16-byte bank groups).  The NCO is split
+//     e^{-i th (n_b + i)} = P_b T[i],   T[i] = e^{-i th i} (shared-memory table, D entries, exact 64-bit phase),
+// so there is no recurrence: the row is mixed with the lane-uniform T[i], filtered into the 8 polyphase partial sums
+//     S_p[b] = sum_i h[(p+1)D - i - sg] x[b][i] T[i]      (taps G[i][p], lane-uniform 128-bit broadcasts)
+// and the row's own phasor P_b (one sincos per row from the exact phase) multiplies the 8 sums once.
+// cp.async needs 16-byte aligned sources, i.e. rows that start on an even sample of the recording.  sg = parity of
+// (start_sample + in_off) picks one of two equivalent decompositions of z[m] = sum_k h[k] y[q - k], q = mD + in_off:
+//   sg = 0: rows START at q - (p+1)D: taps k = 1..8D from rows j..j+7, lone tap h[0] on the first sample of row j+8
+//   sg = 1: rows END   at q - pD    : taps k = 0..8D-1 from rows j+1..j+8, lone tap h[8D] on the last sample of row j
+// (j = output index within the tile, 248 outputs per 256 rows).  Samples outside the annotation are zeroed in the
+// tiles that touch its ends; chunks outside the recording are not read (cp.async src-size 0 / 8).
+constexpr int kDcRowsThreads = 256;
+constexpr int kDcRowsOut = kDcRowsThreads - 8;
+template <int D> struct DcRowsGeo {
+    static_assert(D >= 4 && D <= 32 && (D & (D - 1)) == 0, "row kernel: power-of-two decimation, 4..32");
+    static constexpr int CPR = D / 2;                    // 16-byte chunks (2 cf32 samples) per row
+    static constexpr int RS = CPR | 1;                   // row stride in chunks (odd)
+    static constexpr int RAW_BYTES = kDcRowsThreads * RS * 16;
+    static constexpr int CSM_BYTES = 9 * kDcRowsThreads * 8;
+    static constexpr int G_BYTES = D * 32;               // G[i][p]
+    static constexpr int T_BYTES = D * 16;               // (T.x, T.y, -T.y, T.x)
+    static constexpr int SMEM = 128 + RAW_BYTES + CSM_BYTES + G_BYTES + T_BYTES;
+    static constexpr int MINB = SMEM <= 56 * 1024 ? 4 : (SMEM <= 75 * 1024 ? 3 : 2);
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16_partial(uint32_t dst, const void* src, int bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+
+template <int D, bool INTERIOR>
+__device__ __forceinline__ void dc_rows_fir(const uint32_t row_s, const uint32_t g_s, const uint32_t t_s, const long long n_row,
+                                            const long long count, pk2 (&ax)[4], pk2 (&ay)[4], float2& y_first, float2& y_last) {
+#pragma unroll
+    for (int c = 0; c < D / 2; c++) {
+        float4 x = lds128(row_s + 16u * (unsigned)c);
+        if constexpr (!INTERIOR) {
+            const long long n = n_row + 2 * c;
+            if (n < 0 || n >= count) { x.x = 0.f; x.y = 0.f; }
+            if (n + 1 < 0 || n + 1 >= count) { x.z = 0.f; x.w = 0.f; }
+        }
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+            const int i = 2 * c + hh;
+            const float xr = hh ? x.z : x.x, xi = hh ? x.w : x.y;
+            const float4 tt = lds128(t_s + 16u * (unsigned)i);
+            const pk2 y = fma2(pack2(xi, xi), pack2(tt.z, tt.w), mul2(pack2(xr, xr), pack2(tt.x, tt.y)));
+            float yr, yi;
+            unpack2(y, yr, yi);
+            if (i == 0) y_first = make_float2(yr, yi);
+            if (i == D - 1) y_last = make_float2(yr, yi);
+            const float4 ga = lds128(g_s + 32u * (unsigned)i), gb = lds128(g_s + 32u * (unsigned)i + 16u);
+            const pk2 sx = pack2(yr, yr), sy = pack2(yi, yi);
+            const pk2 g01 = pack2(ga.x, ga.y), g23 = pack2(ga.z, ga.w), g45 = pack2(gb.x, gb.y), g67 = pack2(gb.z, gb.w);
+            ax[0] = fma2(g01, sx, ax[0]); ay[0] = fma2(g01, sy, ay[0]);
+            ax[1] = fma2(g23, sx, ax[1]); ay[1] = fma2(g23, sy, ay[1]);
+            ax[2] = fma2(g45, sx, ax[2]); ay[2] = fma2(g45, sy, ay[2]);
+            ax[3] = fma2(g67, sx, ax[3]); ay[3] = fma2(g67, sy, ay[3]);
+        }
+    }
+}
+
+// Variant with NO table loads in the tap loop (MODE 1).  MODE 0 above is bound by the shared-memory pipe (ncu: MIO
+// throttle + short scoreboard, LSU wavefronts 62 %: a lane-uniform LDS.128 still costs two wavefronts, and a sample
+// needs three of them).  Here the taps are immediates of the kernel-parameter constant bank (`FFMA R, R, c[0][imm], R`:
+// scalar FFMA instead of FFMA2, because FFMA2 cannot take a constant operand) and the NCO is a per-row recurrence
+// P_{i+1} = P_i W seeded with the row's exact phase (15 steps), so the only shared-memory reads are the raw row itself.
+template <int D> struct DcRowsTaps {
+    float g[2][D][8];                 // g[sg][i][p] = h[(p+1)D - i - sg]
+    float lone[2];                    // h[0], h[8D]
+    float pad_[2];
+};
+
+template <int D, bool INTERIOR, int SG>
+__device__ __forceinline__ void dc_rows_fir_c(const DcRowsTaps<D>& tp, const uint32_t row_s, const long long n_row, const long long count,
+                                              float2 P, const float2 W, float (&sr)[8], float (&si)[8], float2& y_lone) {
+#pragma unroll
+    for (int c = 0; c < D / 2; c++) {
+        float4 x = lds128(row_s + 16u * (unsigned)c);
+        if constexpr (!INTERIOR) {
+            const long long n = n_row + 2 * c;
+            if (n < 0 || n >= count) { x.x = 0.f; x.y = 0.f; }
+            if (n + 1 < 0 || n + 1 >= count) { x.z = 0.f; x.w = 0.f; }
+        }
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+            const int i = 2 * c + hh;
+            const float xr = hh ? x.z : x.x, xi = hh ? x.w : x.y;
+            const float yr = __fmaf_rn(xr, P.x, -xi * P.y), yi = __fmaf_rn(xr, P.y, xi * P.x);
+            if (i == (SG ? D - 1 : 0)) y_lone = make_float2(yr, yi);
+            if (i + 1 < D) P = make_float2(__fmaf_rn(P.x, W.x, -P.y * W.y), __fmaf_rn(P.x, W.y, P.y * W.x));
+#pragma unroll
+            for (int p = 0; p < 8; p++) {
+                sr[p] = __fmaf_rn(tp.g[SG][i][p], yr, sr[p]);
+                si[p] = __fmaf_rn(tp.g[SG][i][p], yi, si[p]);
+            }
+        }
+    }
+}
+
+template <int D, int MODE>
+__global__ void __launch_bounds__(kDcRowsThreads, DcRowsGeo<D>::MINB)
+downconvert_rows_kernel(const DcArgs a, const __grid_constant__ DcRowsTaps<D> tp) {
+    using G = DcRowsGeo<D>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const DcAnn an = a.anns[a.ann_base + blockIdx.y];
+    constexpr int NB = kDcRowsOut, NT = kDcRowsThreads;
+    const long long n_tiles = (an.m_out + NB - 1) / NB;
+    long long tile = (long long)blockIdx.x * a.tiles_per_cta;
+    const long long tile_end = min(n_tiles, tile + a.tiles_per_cta);
+    if (tile >= tile_end) return;
+    const int t = threadIdx.x;
+    const uint32_t smem_s = ((uint32_t)__cvta_generic_to_shared(smem_raw) + 127u) & ~127u;
+    const uint32_t raw_s = smem_s, csm_s = raw_s + G::RAW_BYTES, g_s = csm_s + G::CSM_BYTES, t_s = g_s + G::G_BYTES;
+    const int sg = (int)((an.start_sample + an.in_off) & 1);
+    float h_lone;
+    float2 W = make_float2(1.f, 0.f);
+    if constexpr (MODE == 0) {
+        // tables of this annotation: taps of the chosen decomposition, NCO phasors of the D positions of a row
+        const float* h = a.taps + an.taps_off;
+        for (int idx = t; idx < 8 * D; idx += NT) {
+            const int i = idx >> 3, p = idx & 7;
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(g_s + 4u * (unsigned)idx), "f"(__ldg(&h[(p + 1) * D - i - sg])) : "memory");
+        }
+        if (t < D) {
+            const float2 T = nco_phasor(an.phase_step * (unsigned long long)t);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(t_s + 16u * (unsigned)t), "f"(T.x), "f"(T.y), "f"(-T.y), "f"(T.x) : "memory");
+        }
+        h_lone = __ldg(&h[sg ? 8 * D : 0]);
+    } else {
+        h_lone = tp.lone[sg];
+        W = nco_phasor_acc(an.phase_step);
+    }
+    const int lone_row = sg ? 0 : 8;                          // row (relative to j) that holds the lone sample
+
+    // this thread's chunks of a tile: chunk g = t + NT k, row g / CPR, position g % CPR
+    const uint32_t dst0 = raw_s + 16u * (unsigned)((t / G::CPR) * G::RS + (t % G::CPR));
+    constexpr uint32_t kDstStep = (NT / G::CPR) * G::RS * 16;
+    auto tile_n0 = [&](long long tl) { return (tl * NB - 8 - sg) * D + an.in_off + sg; };       // sample of row 0 (annotation-relative)
+    auto issue = [&](long long tl) {
+        const long long s0 = an.start_sample + tile_n0(tl);                                     // even by construction
+        const char* src = reinterpret_cast<const char*>(a.lp.base) + 8 * s0 + 16 * (long long)t;
+        if (s0 >= 0 && s0 + (long long)NT * D <= a.n_samples) {
+#pragma unroll
+            for (int k = 0; k < G::CPR; k++) cp_async16(dst0 + kDstStep * k, src + (size_t)NT * 16 * k);
+        } else {
+#pragma unroll
+            for (int k = 0; k < G::CPR; k++) {
+                const long long s = s0 + 2 * ((long long)t + NT * k);
+                const int bytes = s < 0 ? 0 : (int)max(0LL, min(2LL, a.n_samples - s)) * 8;
+                cp_async16_partial(dst0 + kDstStep * k, bytes ? (const void*)(src + (size_t)NT * 16 * k) : a.lp.base, bytes);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue(tile);
+    const uint32_t row_s = raw_s + (unsigned)(t * G::RS * 16);
+    for (; tile < tile_end; tile++) {
+        const long long m0 = tile * NB;
+        const int nbt = (int)min((long long)NB, an.m_out - m0);
+        const long long n0 = tile_n0(tile);
+        const long long n_row = n0 + (long long)t * D;
+        const bool interior = n0 >= 0 && n0 + (long long)NT * D <= an.count;
+        const float2 P = nco_phasor(an.phase_step * (unsigned long long)n_row);     // phasor of the row's first sample
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                    // the tile has landed; C_p of the previous tile has been consumed
+        if constexpr (MODE == 0) {
+            pk2 ax[4], ay[4];
+#pragma unroll
+            for (int p = 0; p < 4; p++) { ax[p] = pack2(0.f, 0.f); ay[p] = pack2(0.f, 0.f); }
+            float2 y_first = make_float2(0.f, 0.f), y_last = y_first;
+            if (interior) dc_rows_fir<D, true>(row_s, g_s, t_s, n_row, an.count, ax, ay, y_first, y_last);
+            else          dc_rows_fir<D, false>(row_s, g_s, t_s, n_row, an.count, ax, ay, y_first, y_last);
+            // C_p[b] = P_b S_p[b]
+            const pk2 Px = pack2(P.x, P.x), Py = pack2(P.y, P.y), nPy = pack2(-P.y, -P.y);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const pk2 re = fma2(ay[k], nPy, mul2(ax[k], Px)), im = fma2(ay[k], Px, mul2(ax[k], Py));
+                float r0, r1, i0, i1;
+                unpack2(re, r0, r1); unpack2(im, i0, i1);
+                sts64(csm_s + 8u * (unsigned)((2 * k) * NT + t), r0, i0);
+                sts64(csm_s + 8u * (unsigned)((2 * k + 1) * NT + t), r1, i1);
+            }
+            const float2 yl = sg ? y_last : y_first;
+            const float lr = h_lone * yl.x, li = h_lone * yl.y;
+            sts64(csm_s + 8u * (unsigned)(8 * NT + t), lr * P.x - li * P.y, lr * P.y + li * P.x);
+        } else {
+            float sr[8], si[8];
+#pragma unroll
+            for (int p = 0; p < 8; p++) { sr[p] = 0.f; si[p] = 0.f; }
+            float2 yl = make_float2(0.f, 0.f);
+            if (sg) {
+                if (interior) dc_rows_fir_c<D, true, 1>(tp, row_s, n_row, an.count, P, W, sr, si, yl);
+                else          dc_rows_fir_c<D, false, 1>(tp, row_s, n_row, an.count, P, W, sr, si, yl);
+            } else {
+                if (interior) dc_rows_fir_c<D, true, 0>(tp, row_s, n_row, an.count, P, W, sr, si, yl);
+                else          dc_rows_fir_c<D, false, 0>(tp, row_s, n_row, an.count, P, W, sr, si, yl);
+            }
+#pragma unroll
+            for (int p = 0; p < 8; p++) sts64(csm_s + 8u * (unsigned)(p * NT + t), sr[p], si[p]);
+            sts64(csm_s + 8u * (unsigned)(8 * NT + t), h_lone * yl.x, h_lone * yl.y);
+        }
+        __syncthreads();                                    // C_p complete; the raw tile is free
+        if (tile + 1 < tile_end) issue(tile + 1);           // next tile flies under the combine step and the stores
+        if (t < nbt) {
+            float2 z = lds64(csm_s + 8u * (unsigned)(8 * NT + t + lone_row));
+#pragma unroll
+            for (int p = 0; p < 8; p++) { const float2 c = lds64(csm_s + 8u * (unsigned)(p * NT + t + sg + 7 - p)); z.x += c.x; z.y += c.y; }
+            if (a.out) { double* o = a.out + an.out_off + m0 + t; o[0] = (double)z.x; o[an.m_out] = (double)z.y; }
+            if (a.scratch) a.scratch[an.scr_off + m0 + t] = z;
+        }
     }
 }
 

@@ -329,3 +329,96 @@ def test_batch_of_more_annotations_than_one_launch_holds(engine):
     for i in (0, 65_534, 65_535, 69_999):
         ref = co.downconvert(raw, "cu8", *anns[i][:4], False)
         assert np.abs(iq[i] - ref).max() <= DC_TOL * max(np.abs(ref).max(), 0.5)
+
+
+@pytest.mark.parametrize("down", [8, 16, 32])
+@pytest.mark.parametrize("start,delay", [(0, "causal"), (1, "causal"), (122, "same"), (123, "same"), (4096, "valid"), (4097, "valid")])
+def test_row_kernel_alignment_edges_and_tiles(engine, down, start, delay):
+    """cf32 / power-of-two decimation takes the row-per-thread kernel (16-byte cp.async of raw rows): both parities of
+    (start + delay shift) -- the two decompositions of the tap sum --, an annotation that begins at sample 0 of the
+    recording and one that ends at its last sample (chunks outside the recording are not read), zero history / zero
+    tail inside a longer recording, several tiles per CTA, a count that is not a multiple of down."""
+    count = 2 * 248 * down * 5 + 3 * down + 5            # a little over 10 tiles
+    for tail in (0, 1, 333):                             # annotation ends at the end of the buffer / before it
+        raw = synth.recording(start + count + tail, "cf32_le", seed=21 + tail)
+        cfg = co.analysis_cfg(delay=delay, length="ceil")
+        ref = co.downconvert_ex(raw, "cf32_le", start, count, -0.3217, down, False, cfg)
+        engine.set_analysis_config(delay=delay, length="ceil")
+        try:
+            got = engine.downconvert(raw, "cf32_le", start, count, -0.3217, down, False)
+            name = engine.last_kernel
+        finally:
+            engine.reset_analysis_config()
+        assert got.shape == ref.shape
+        assert np.abs(got - ref).max() <= DC_TOL * max(np.abs(ref).max(), 0.5), (tail, name)
+        if os.environ.get("SA_DC_ROWS", "1") != "0":
+            assert "downconvert_rows_kernel" in name
+
+
+@pytest.mark.parametrize("count", [1, 15, 16, 17, 100, 248 * 16, 248 * 16 + 1, 5000])
+def test_row_kernel_short_annotations(engine, count):
+    """Annotations shorter than one tile, shorter than the filter, down to one sample; caller taps shorter than 8D+1."""
+    raw = synth.recording(9000, "cf32_le", seed=33)
+    taps = np.hamming(65) / np.hamming(65).sum()
+    for tp in (None, taps):
+        for start in (0, 2001, 9000 - count):
+            cfg = co.analysis_cfg(taps=tp, delay="same", length="ceil")
+            ref = co.downconvert_ex(raw, "cf32_le", start, count, 0.0613, 16, False, cfg)
+            engine.set_analysis_config(taps=tp, delay="same", length="ceil")
+            try:
+                got = engine.downconvert(raw, "cf32_le", start, count, 0.0613, 16, False)
+            finally:
+                engine.reset_analysis_config()
+            assert got.shape == ref.shape
+            assert np.abs(got - ref).max() <= DC_TOL * max(np.abs(ref).max(), 0.5), (start, tp is None)
+
+
+def test_row_kernel_device_path_odd_starts_and_recording_ends(engine):
+    """The device-resident batch call keeps the caller's sample offsets (the host call packs every span at an even
+    offset): odd and even starts, annotations touching sample 0 and the last sample of the recording, mixed
+    decimation factors in one call, each against the oracle."""
+    import ctypes as C
+    import torch
+    from spectral_analyzer_b200 import _capi
+    n = 300001
+    raw = synth.recording(n, "cf32_le", seed=17)
+    d_raw = torch.from_numpy(np.frombuffer(raw, np.uint8).copy()).cuda()
+    specs = [(0, 100000, 16), (1, 100001, 16), (12345, 77777, 16), (200000, 100001, 16), (199999, 100002, 8),
+             (3, 299998, 32), (150001, 40000, 16), (150002, 40000, 16)]
+    anns = (_capi.Annotation * len(specs))()
+    offs = (C.c_uint64 * len(specs))()
+    total = 0
+    for i, (s, c, d) in enumerate(specs):
+        anns[i] = _capi.Annotation(s, c, 0.05 + 0.031 * i, d, 0)
+        offs[i] = total
+        total += 2 * (c // d)
+    d_iq = torch.empty(total, dtype=torch.float64, device="cuda")
+    _capi.check(_capi.lib().sa_downconvert_psd_batch_device(
+        engine.handle, d_raw.data_ptr(), d_raw.numel(), 0, 0, 1.0e6, anns, len(specs), 0, 0, 1, d_iq.data_ptr(), offs,
+        None, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    got_all = d_iq.cpu().numpy()
+    for i, (s, c, d) in enumerate(specs):
+        ref = co.downconvert(raw, "cf32_le", s, c, 0.05 + 0.031 * i, d, False)
+        got = got_all[offs[i]:offs[i] + 2 * (c // d)].reshape(2, c // d)
+        assert rel_err(got, ref) < DC_TOL, (i, s, c, d)
+
+
+@pytest.mark.parametrize("ntaps,delay", [(127, "same"), (128, "valid"), (129, "same"), (31, "same")])
+def test_row_kernel_odd_delay_shift(engine, ntaps, delay):
+    """The host call packs spans at even offsets, so the parity of the delay shift alone picks the decomposition:
+    (L-1)/2 = 63 and L-1 = 127 are odd (rows end at the output's sample), 64 and 15 exercise the other one."""
+    down, count = 16, 50003
+    raw = synth.recording(count + 10, "cf32_le", seed=41)
+    k = np.arange(ntaps) - (ntaps - 1) / 2
+    taps = np.sinc(k / down) * np.hamming(ntaps)
+    taps /= taps.sum()
+    cfg = co.analysis_cfg(taps=taps, delay=delay, length="floor")
+    ref = co.downconvert_ex(raw, "cf32_le", 5, count, -0.0917, down, False, cfg)
+    engine.set_analysis_config(taps=taps, delay=delay, length="floor")
+    try:
+        got = engine.downconvert(raw, "cf32_le", 5, count, -0.0917, down, False)
+    finally:
+        engine.reset_analysis_config()
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= DC_TOL * max(np.abs(ref).max(), 0.5)
