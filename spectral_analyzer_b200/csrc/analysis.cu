@@ -99,15 +99,38 @@ const void* dc_kernel(int dk, int which) {
 
 // row-per-thread kernel (cf32, little-endian, power-of-two decimation): nullptr when there is none for this factor.
 // mode 0: taps and NCO phasors as shared-memory tables, FFMA2; mode 1: taps as constant-bank immediates, NCO recurrence
-template <int D> const void* dc_rows_kernel_of(int mode, size_t* smem) {
-    *smem = DcRowsGeo<D>::SMEM;
-    return mode == 0 ? (const void*)&downconvert_rows_kernel<D, 0> : (const void*)&downconvert_rows_kernel<D, 1>;
+struct DcRowsShape { int mode, nt, nbuf; };
+// Shape of the row kernel, measured on B200 (C3 = 500 x 2^20 samples at D 16 incl. Welch; tools/dc_matrix.py for 8 / 32):
+//   rows per tile x raw buffers     C3          D 8        D 16       D 32
+//   256 x 1                          1.413 ms    0.827      0.621      0.479
+//   256 x 2                          1.407       0.805      0.617      0.580
+//   128 x 1                          1.464       0.793      0.634      0.457
+//   128 x 2                          1.325       0.784      0.581      0.507
+// (small tiles double-buffered: every CTA always has a tile in flight and the load / tap-loop phases of the resident
+// CTAs no longer line up; at D 32 two buffers cost too many CTAs).  SA_DC_ROWS_NT / SA_DC_ROWS_NBUF / SA_DC_ROWS_MODE override.
+static DcRowsShape dc_rows_shape(int down) {
+    static const char* me = getenv("SA_DC_ROWS_MODE");
+    static const char* ne = getenv("SA_DC_ROWS_NT");
+    static const char* be = getenv("SA_DC_ROWS_NBUF");
+    DcRowsShape sh = { me ? atoi(me) : 1, ne ? atoi(ne) : 128, be ? atoi(be) : (down >= 32 ? 1 : 2) };
+    if (sh.nt != 256) sh.nt = 128;
+    if (sh.nbuf != 1) sh.nbuf = 2;
+    if (sh.mode == 0) { sh.nt = 256; sh.nbuf = 1; }        // the table variant exists in the first shape only (ablation record)
+    return sh;
 }
-const void* dc_rows_kernel(int down, int mode, size_t* smem) {
+template <int D> const void* dc_rows_kernel_of(const DcRowsShape& sh, size_t* smem) {
+    if (sh.mode == 0) { *smem = DcRowsGeo<D, 256, 1>::SMEM; return (const void*)&downconvert_rows_kernel<D, 0, 256, 1>; }
+    if (sh.nt == 256 && sh.nbuf == 1) { *smem = DcRowsGeo<D, 256, 1>::SMEM; return (const void*)&downconvert_rows_kernel<D, 1, 256, 1>; }
+    if (sh.nt == 256 && sh.nbuf == 2) { *smem = DcRowsGeo<D, 256, 2>::SMEM; return (const void*)&downconvert_rows_kernel<D, 1, 256, 2>; }
+    if (sh.nt == 128 && sh.nbuf == 1) { *smem = DcRowsGeo<D, 128, 1>::SMEM; return (const void*)&downconvert_rows_kernel<D, 1, 128, 1>; }
+    *smem = DcRowsGeo<D, 128, 2>::SMEM; return (const void*)&downconvert_rows_kernel<D, 1, 128, 2>;
+}
+const void* dc_rows_kernel(int down, const DcRowsShape& sh, size_t* smem) {
     switch (down) {
-        case 8:  return dc_rows_kernel_of<8>(mode, smem);
-        case 16: return dc_rows_kernel_of<16>(mode, smem);
-        case 32: return dc_rows_kernel_of<32>(mode, smem);
+        case 4:  return dc_rows_kernel_of<4>(sh, smem);
+        case 8:  return dc_rows_kernel_of<8>(sh, smem);
+        case 16: return dc_rows_kernel_of<16>(sh, smem);
+        case 32: return dc_rows_kernel_of<32>(sh, smem);
         default: *smem = 0; return nullptr;
     }
 }
@@ -357,8 +380,8 @@ static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, i
         size_t rows_smem = 0;
         if (wide) {
             a.nb = 0;                       // marks the warp-per-output kernel
-        } else if (rows_ok && !a.fast && dc_rows_kernel(D, 1, &rows_smem)) {
-            a.nb = kDcRowsOut;
+        } else if (rows_ok && !a.fast && dc_rows_kernel(D, dc_rows_shape(D), &rows_smem)) {
+            a.nb = dc_rows_shape(D).nt - 8;
             rowsk[i] = 1;
         } else if (pipe_ok && !a.fast && D <= 32) {
             // pipelined variant: the whole tile is one register batch (<= 17 x 256 staged samples)
@@ -532,8 +555,8 @@ static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, i
                 long long tiles = 0;
                 for (uint32_t i = g0; i < g1; i++) tiles = std::max<long long>(tiles, (sorted[i].m_out + first.nb - 1) / first.nb);
                 size_t smem = 0;
-                static const char* me = getenv("SA_DC_ROWS_MODE");
-                const void* fn = dc_rows_kernel(first.down, me ? atoi(me) : 1, &smem);
+                const DcRowsShape rows_shape = dc_rows_shape(first.down);
+                const void* fn = dc_rows_kernel(first.down, rows_shape, &smem);
                 std::vector<float> rt;
                 dc_rows_taps(taps.data() + first.taps_off, first.down, rt);
                 void* rargs[] = { &da, rt.data() };
@@ -548,7 +571,7 @@ static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, i
                         if (e != cudaSuccess) return cuda_fail(e, "downconvert smem attribute");
                         have = smem;
                     }
-                    e = cudaLaunchKernel(fn, dim3((unsigned)ctas, g1 - g0), dim3(kDcRowsThreads), rargs, smem, s);
+                    e = cudaLaunchKernel(fn, dim3((unsigned)ctas, g1 - g0), dim3(rows_shape.nt), rargs, smem, s);
                     if (e != cudaSuccess) return cuda_fail(e, "launch downconvert_rows_kernel");
                     eng->launches++;
                     dc_name = "downconvert_rows_kernel";

@@ -416,18 +416,20 @@ downconvert_wide_kernel(const DcArgs a) {
 //   sg = 1: rows END   at q - pD    : taps k = 0..8D-1 from rows j+1..j+8, lone tap h[8D] on the last sample of row j
 // (j = output index within the tile, 248 outputs per 256 rows).  Samples outside the annotation are zeroed in the
 // tiles that touch its ends; chunks outside the recording are not read (cp.async src-size 0 / 8).
-constexpr int kDcRowsThreads = 256;
-constexpr int kDcRowsOut = kDcRowsThreads - 8;
-template <int D> struct DcRowsGeo {
+template <int D, int NT = 256, int NBUF = 1> struct DcRowsGeo {
     static_assert(D >= 4 && D <= 32 && (D & (D - 1)) == 0, "row kernel: power-of-two decimation, 4..32");
+    static_assert(NT % (D / 2) == 0 && (NBUF == 1 || NBUF == 2), "row kernel geometry");
     static constexpr int CPR = D / 2;                    // 16-byte chunks (2 cf32 samples) per row
     static constexpr int RS = CPR | 1;                   // row stride in chunks (odd)
-    static constexpr int RAW_BYTES = kDcRowsThreads * RS * 16;
-    static constexpr int CSM_BYTES = 9 * kDcRowsThreads * 8;
+    static constexpr int RAW_BYTES = NT * RS * 16;       // one raw tile: NT rows
+    static constexpr int CSM_BYTES = 9 * NT * 8;
     static constexpr int G_BYTES = D * 32;               // G[i][p]
     static constexpr int T_BYTES = D * 16;               // (T.x, T.y, -T.y, T.x)
-    static constexpr int SMEM = 128 + RAW_BYTES + CSM_BYTES + G_BYTES + T_BYTES;
-    static constexpr int MINB = SMEM <= 56 * 1024 ? 4 : (SMEM <= 75 * 1024 ? 3 : 2);
+    static constexpr int SMEM = 128 + NBUF * RAW_BYTES + CSM_BYTES + G_BYTES + T_BYTES;
+    static constexpr int BY_SMEM = (227 * 1024) / (SMEM + 1024);
+    static constexpr int BY_WARPS = 2048 / NT;
+    static constexpr int BY_REGS = 65536 / (NT * 64);    // aim: 64 registers per thread at most when that raises occupancy
+    static constexpr int MINB = BY_SMEM < BY_WARPS ? (BY_SMEM < BY_REGS ? BY_SMEM : BY_REGS) : (BY_WARPS < BY_REGS ? BY_WARPS : BY_REGS);
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
@@ -507,20 +509,20 @@ __device__ __forceinline__ void dc_rows_fir_c(const DcRowsTaps<D>& tp, const uin
     }
 }
 
-template <int D, int MODE>
-__global__ void __launch_bounds__(kDcRowsThreads, DcRowsGeo<D>::MINB)
+template <int D, int MODE, int NT, int NBUF>
+__global__ void __launch_bounds__(NT, DcRowsGeo<D, NT, NBUF>::MINB)
 downconvert_rows_kernel(const DcArgs a, const __grid_constant__ DcRowsTaps<D> tp) {
-    using G = DcRowsGeo<D>;
+    using G = DcRowsGeo<D, NT, NBUF>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const DcAnn an = a.anns[a.ann_base + blockIdx.y];
-    constexpr int NB = kDcRowsOut, NT = kDcRowsThreads;
+    constexpr int NB = NT - 8;
     const long long n_tiles = (an.m_out + NB - 1) / NB;
     long long tile = (long long)blockIdx.x * a.tiles_per_cta;
     const long long tile_end = min(n_tiles, tile + a.tiles_per_cta);
     if (tile >= tile_end) return;
     const int t = threadIdx.x;
     const uint32_t smem_s = ((uint32_t)__cvta_generic_to_shared(smem_raw) + 127u) & ~127u;
-    const uint32_t raw_s = smem_s, csm_s = raw_s + G::RAW_BYTES, g_s = csm_s + G::CSM_BYTES, t_s = g_s + G::G_BYTES;
+    const uint32_t raw_s = smem_s, csm_s = raw_s + NBUF * G::RAW_BYTES, g_s = csm_s + G::CSM_BYTES, t_s = g_s + G::G_BYTES;
     const int sg = (int)((an.start_sample + an.in_off) & 1);
     float h_lone;
     float2 W = make_float2(1.f, 0.f);
@@ -543,10 +545,10 @@ downconvert_rows_kernel(const DcArgs a, const __grid_constant__ DcRowsTaps<D> tp
     const int lone_row = sg ? 0 : 8;                          // row (relative to j) that holds the lone sample
 
     // this thread's chunks of a tile: chunk g = t + NT k, row g / CPR, position g % CPR
-    const uint32_t dst0 = raw_s + 16u * (unsigned)((t / G::CPR) * G::RS + (t % G::CPR));
+    const uint32_t dst_t = raw_s + 16u * (unsigned)((t / G::CPR) * G::RS + (t % G::CPR));
     constexpr uint32_t kDstStep = (NT / G::CPR) * G::RS * 16;
     auto tile_n0 = [&](long long tl) { return (tl * NB - 8 - sg) * D + an.in_off + sg; };       // sample of row 0 (annotation-relative)
-    auto issue = [&](long long tl) {
+    auto issue = [&](long long tl, uint32_t dst0) {
         const long long s0 = an.start_sample + tile_n0(tl);                                     // even by construction
         const char* src = reinterpret_cast<const char*>(a.lp.base) + 8 * s0 + 16 * (long long)t;
         if (s0 >= 0 && s0 + (long long)NT * D <= a.n_samples) {
@@ -562,9 +564,10 @@ downconvert_rows_kernel(const DcArgs a, const __grid_constant__ DcRowsTaps<D> tp
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    issue(tile);
-    const uint32_t row_s = raw_s + (unsigned)(t * G::RS * 16);
+    issue(tile, dst_t);
+    uint32_t buf = 0;                                       // byte offset of the current raw tile (NBUF == 2)
     for (; tile < tile_end; tile++) {
+        const uint32_t row_s = raw_s + buf + (unsigned)(t * G::RS * 16);
         const long long m0 = tile * NB;
         const int nbt = (int)min((long long)NB, an.m_out - m0);
         const long long n0 = tile_n0(tile);
@@ -573,6 +576,10 @@ downconvert_rows_kernel(const DcArgs a, const __grid_constant__ DcRowsTaps<D> tp
         const float2 P = nco_phasor(an.phase_step * (unsigned long long)n_row);     // phasor of the row's first sample
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();                                    // the tile has landed; C_p of the previous tile has been consumed
+        if constexpr (NBUF == 2) {                          // the next tile flies under this tile's tap loop
+            buf ^= (uint32_t)G::RAW_BYTES;
+            if (tile + 1 < tile_end) issue(tile + 1, dst_t + buf);
+        }
         if constexpr (MODE == 0) {
             pk2 ax[4], ay[4];
 #pragma unroll
@@ -610,7 +617,7 @@ downconvert_rows_kernel(const DcArgs a, const __grid_constant__ DcRowsTaps<D> tp
             sts64(csm_s + 8u * (unsigned)(8 * NT + t), h_lone * yl.x, h_lone * yl.y);
         }
         __syncthreads();                                    // C_p complete; the raw tile is free
-        if (tile + 1 < tile_end) issue(tile + 1);           // next tile flies under the combine step and the stores
+        if constexpr (NBUF == 1) { if (tile + 1 < tile_end) issue(tile + 1, dst_t); }   // next tile flies under the combine step and the stores
         if (t < nbt) {
             float2 z = lds64(csm_s + 8u * (unsigned)(8 * NT + t + lone_row));
 #pragma unroll
