@@ -49,13 +49,14 @@ template <typename T, int N> WelchKernel make_welch(int prec) {
     return k;
 }
 // FP32 2048 .. 16384: the small-radix-first plan (welch_accum_mid_kernel)
-template <int N> WelchKernel make_welch_mid() {
+template <int N, int CTA_ = MidGeo<N>::CTA> WelchKernel make_welch_mid() {
     using G = MidGeo<N>;
     WelchKernel k;
-    k.fn = (const void*)&welch_accum_mid_kernel<N>;
+    k.fn = (const void*)&welch_accum_mid_kernel<N, CTA_>;
     k.fin = (const void*)&welch_finalize_kernel<float>;
     k.prec = 1;
-    k.n = N; k.cta = G::CTA; k.fpc = G::FPC; k.smem = G::EX_BYTES + G::T1_BYTES + G::WIN_BYTES; k.p = 32; k.np = 3;
+    k.n = N; k.cta = CTA_; k.fpc = CTA_ / G::TPF;
+    k.smem = (size_t)k.fpc * G::SM_ELEMS * sizeof(float2) + G::T1_BYTES + G::WIN_BYTES; k.p = 32; k.np = 3;
     k.radix[0] = G::R0; k.radix[1] = 32; k.radix[2] = 32; k.radix[3] = 1;
     k.mid = 1;
     return k;
@@ -64,6 +65,11 @@ template <int N> WelchKernel make_welch_mid() {
 const WelchKernel* find_welch(int prec, int n) {
     static const bool no_mid = getenv("SA_WELCH_MID") && atoi(getenv("SA_WELCH_MID")) == 0;     // A/B: the general plan
     static const WelchKernel mid_tab[] = { make_welch_mid<2048>(), make_welch_mid<4096>(), make_welch_mid<8192>(), make_welch_mid<16384>() };
+    // SA_WELCH_CTA=256: one segment per CTA for 8192 points (256 threads, 32 K registers), small enough to share an SM with
+    // the row-per-thread downconverter's CTAs when the batches are pipelined (run_batch_device); measured no faster
+    static const bool small_cta = getenv("SA_WELCH_CTA") && atoi(getenv("SA_WELCH_CTA")) == 256;
+    static const WelchKernel mid_8192_small = make_welch_mid<8192, 256>();
+    if (prec == 1 && !no_mid && n == 8192 && small_cta) return &mid_8192_small;
     if (prec == 1 && !no_mid)
         for (const auto& k : mid_tab) if (k.n == n) return &k;
     static const WelchKernel tab[] = {
@@ -504,11 +510,25 @@ static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, i
     if (e == cudaSuccess) e = cudaEventRecord(eng->plan_ev, stream);
     if (e != cudaSuccess) return cuda_fail(e, "upload annotation plan");
 
+    // Two schedules for more than one batch:
+    //   alternate (default): batch b runs downconverter and Welch on stream b & 1;
+    //   pipelined (SA_DC_SCHED=1): every downconverter launch on the caller's stream, every Welch launch on a HIGH-PRIORITY
+    //     helper stream behind an event, so that Welch of batch b could share the SMs with the downconverter of batch b + 1
+    //     (the one bound by memory, the other by issue slots; with SA_WELCH_CTA=256 the Welch CTAs are small enough to fit
+    //     beside the downconverter's).  Measured on C3 (ms; rows = schedule / Welch CTA, columns = SA_DC_BATCH_MB 16 32 64 128):
+    //       pipelined 256: 1.568 1.477 1.384 1.356     pipelined 512: 1.621 1.475 1.393 1.350
+    //       alternate 256: 1.567 1.477 1.372 1.335     alternate 512: 1.592 1.485 1.399 1.331
+    //     -- no gain from the overlap, and small batches lose to their launch tails: two 128 MB batches stay the default.
+    static const char* sched_env = getenv("SA_DC_SCHED");
+    const bool pipelined = dual && sched_env && atoi(sched_env) == 1;
     cudaStream_t st[2] = { stream, stream };
     if (dual) {
         if (!eng->dc_aux) {
-            e = cudaStreamCreateWithFlags(&eng->dc_aux, cudaStreamNonBlocking);
+            int lo = 0, hi = 0;
+            e = cudaDeviceGetStreamPriorityRange(&lo, &hi);          // hi = numerically smallest = greatest priority
+            if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&eng->dc_aux, cudaStreamNonBlocking, hi);
             for (int j = 0; j < 2 && e == cudaSuccess; j++) e = cudaEventCreateWithFlags(&eng->dc_ev[j], cudaEventDisableTiming);
+            for (int j = 0; j < 4 && e == cudaSuccess; j++) e = cudaEventCreateWithFlags(&eng->dc_pipe_ev[j], cudaEventDisableTiming);
             if (e != cudaSuccess) return cuda_fail(e, "analysis helper stream");
         }
         st[1] = eng->dc_aux;
@@ -533,7 +553,11 @@ static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, i
     size_t sig_pos = 0;                  // position in the uploaded WelchSig array
     for (size_t bi = 0; bi < batches.size(); bi++) {
         const int par = dual ? (int)(bi & 1) : 0;
-        cudaStream_t s = st[par];
+        cudaStream_t s = pipelined ? stream : st[par];
+        if (pipelined && bi >= 2) {          // the rows of parity `par` are rewritten: Welch of batch bi - 2 must have read them
+            e = cudaStreamWaitEvent(stream, eng->dc_pipe_ev[2 + par], 0);
+            if (e != cudaSuccess) return cuda_fail(e, "analysis pipeline wait");
+        }
         const uint32_t bn = batches[bi].second - batches[bi].first;
         da.scratch = want_psd ? (float2*)eng->scratch[12] + (size_t)par * scr_total : nullptr;
         for (uint32_t g0 = pos; g0 < pos + bn;) {
@@ -615,6 +639,12 @@ static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, i
             g0 = g1;
         }
         pos += bn;
+        if (pipelined) {                     // Welch of this batch: helper stream, behind the downconverter launches above
+            e = cudaEventRecord(eng->dc_pipe_ev[par], stream);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(eng->dc_aux, eng->dc_pipe_ev[par], 0);
+            if (e != cudaSuccess) return cuda_fail(e, "analysis pipeline fork");
+            s = eng->dc_aux;
+        }
         if (want_psd) {
             // NaN padding first (the short spectra are written over the row start)
             for (uint32_t i : short_rows[bi]) {
@@ -627,6 +657,10 @@ static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, i
                 if (!wl.sigs.empty()) any_welch = true;
                 sig_pos += wl.sigs.size();
             }
+        }
+        if (pipelined) {
+            e = cudaEventRecord(eng->dc_pipe_ev[2 + par], eng->dc_aux);
+            if (e != cudaSuccess) return cuda_fail(e, "analysis pipeline record");
         }
     }
     eng->last_kernel = any_welch ? std::string(dc_name) + "+" + eng->last_kernel : std::string(dc_name);

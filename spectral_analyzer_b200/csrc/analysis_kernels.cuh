@@ -738,17 +738,21 @@ welch_accum_kernel(const WelchArgs a) {
 // twiddles from a tiny shared-memory table, pass-2 twiddles by the register recurrence, window folded into the first
 // butterfly stage) instead of the general plan's two table-driven passes: thread t owns S = 32 / R0 CONSECUTIVE samples of
 // each of the R0 slices of a segment -- 128-bit loads from the downconverter's FP32 rows when they are 16-byte aligned.
-template <int N>
-__global__ void __launch_bounds__(MidGeo<N>::CTA, MidGeo<N>::MINB)
+// CTA_: threads per CTA, a multiple of the TPF threads of one segment (the spectrogram kernel's geometry, or one segment
+// per CTA so that the CTAs are small enough to share an SM with the downconverter's, see run_batch_device).
+template <int N, int CTA_>
+__global__ void __launch_bounds__(CTA_, 512 / CTA_)
 welch_accum_mid_kernel(const WelchArgs a) {
     using G = MidGeo<N>;
-    constexpr int P = 32, R0 = G::R0, S = G::S, TPF = G::TPF, FPC = G::FPC;
+    constexpr int P = 32, R0 = G::R0, S = G::S, TPF = G::TPF, FPC = CTA_ / TPF;
+    static_assert(CTA_ % TPF == 0 && FPC >= 1 && FPC <= G::FPC, "Welch CTA: whole segments, at most the spectrogram kernel's");
+    constexpr size_t EX_BYTES = (size_t)FPC * G::SM_ELEMS * sizeof(float2);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ float2 red[32];
     const int fl = threadIdx.x / TPF, t = threadIdx.x % TPF;
     float2* sm = reinterpret_cast<float2*>(smem_raw) + (size_t)fl * G::SM_ELEMS;
-    TwPair<float>* t1 = reinterpret_cast<TwPair<float>*>(smem_raw + G::EX_BYTES);
-    float* wsm = reinterpret_cast<float*>(smem_raw + G::EX_BYTES + G::T1_BYTES);
+    TwPair<float>* t1 = reinterpret_cast<TwPair<float>*>(smem_raw + EX_BYTES);
+    float* wsm = reinterpret_cast<float*>(smem_raw + EX_BYTES + G::T1_BYTES);
     mid_setup_tables<N, true>(a.twiddle, a.window, t1, wsm);
     __syncthreads();
     const float* win = wsm + t * G::WROW;
@@ -796,7 +800,7 @@ welch_accum_mid_kernel(const WelchArgs a) {
             for (int q = 0; q < P; q++) v[q] = make_float2(0.f, 0.f);
         }
         if (a.detrend) {                 // launch-uniform
-            const float2 m = frame_mean<float, TPF, P, G::CTA>(v, red);
+            const float2 m = frame_mean<float, TPF, P, CTA_>(v, red);
 #pragma unroll
             for (int q = 0; q < P; q++) { v[q].x -= m.x; v[q].y -= m.y; }
         }

@@ -960,6 +960,7 @@ Engine::~Engine() {
     if (plan_ev) cudaEventDestroy(plan_ev);
     if (dc_aux) cudaStreamDestroy(dc_aux);
     for (int j = 0; j < 2; j++) if (dc_ev[j]) cudaEventDestroy(dc_ev[j]);
+    for (int j = 0; j < 4; j++) if (dc_pipe_ev[j]) cudaEventDestroy(dc_pipe_ev[j]);
     delete copy_pool;
     for (auto& r : registered) cudaHostUnregister(const_cast<void*>(r));
     for (int i = 0; i < kScratch; i++) if (scratch[i]) cudaFree(scratch[i]);

@@ -114,6 +114,8 @@ struct Engine {
     AnalysisProfile profile;                         // sa_set_analysis_config
     cudaStream_t dc_aux = nullptr;                   // annotation batches alternate between the caller's stream and this one
     cudaEvent_t dc_ev[2] = {};                       // fork / join
+    cudaEvent_t dc_pipe_ev[4] = {};                  // pipelined batches: rows of batch parity p written [p], consumed [2 + p]
+    int dc_aux_prio = 0;                             // 1: dc_aux was created as a high-priority stream
     void* h_plan = nullptr; size_t h_plan_cap = 0;   // pinned staging of a call's annotation / tap / Welch plans
     cudaEvent_t plan_ev = nullptr;                   // the last upload from h_plan has completed
     std::map<const void*, size_t> dc_smem_set;       // dynamic shared memory limit already granted per kernel
