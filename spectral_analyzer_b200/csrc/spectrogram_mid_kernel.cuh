@@ -234,9 +234,13 @@ __device__ __forceinline__ void mid_setup_tables(const void* __restrict__ t1_glo
     constexpr int P = 32, R0 = G::R0, S = G::S;
     const float4* src = reinterpret_cast<const float4*>(t1_global);
     float4* dst = reinterpret_cast<float4*>(t1);
+    // (blockDim.x, not G::CTA: the Welch kernel also runs this plan with one segment per CTA; unroll 1 keeps the
+    // compiler from computing a trip count by integer division)
+#pragma unroll 1
     for (int i = threadIdx.x; i < 16 * R0; i += blockDim.x) dst[i] = __ldg(&src[i]);
     if constexpr (WIN) {
         const float* w = reinterpret_cast<const float*>(window);
+#pragma unroll 1
         for (int i = threadIdx.x; i < N; i += blockDim.x) {
             // sample i = m*(N/R0) + S*tt + ii  ->  register e = ii + S*m of thread tt
             const int m = i / (N / R0), rem = i % (N / R0), tt = rem / S, ii = rem % S;

@@ -88,8 +88,13 @@ if not only or only == "profile":
     got = eng.downconvert(raw, "ci16_le", 7, 20001, -0.2, 8)
     ref = co.downconvert_ex(raw, "ci16_le", 7, 20001, -0.2, 8, False, co.analysis_cfg(taps=taps, delay="same", length="ceil"))
     assert got.shape == ref.shape and np.abs(got - ref).max() < 1e-5
-    eng.set_analysis_config(strict_reference=True)
-    raw32 = synth.recording(8000, "cf32_le", seed=9)            # an unknown datatype is read as cf32 (strict reference)
+    eng.reset_analysis_config()
+    raw32 = synth.recording(8000, "cf32_le", seed=9)            # cf32 at decimation 16 / 8: the row-per-thread kernel, both parities
+    for start, down in ((0, 16), (77, 16), (1, 8), (1200, 32)):
+        got = eng.downconvert(raw32, "cf32_le", start, 6000, 0.11, down)
+        ref = co.downconvert(raw32, "cf32_le", start, 6000, 0.11, down, False)
+        assert got.shape == ref.shape and np.abs(got - ref).max() <= 1e-5 * max(np.abs(ref).max(), 0.5)
+    eng.set_analysis_config(strict_reference=True)            # an unknown datatype is read as cf32 (strict reference)
     got = eng.downconvert(raw32, "ri16_le", 0, 7000, 0.05, 4)
     ref = co.downconvert_ex(raw32, "ri16_le", 0, 7000, 0.05, 4, False, co.analysis_cfg(strict_reference=True))
     assert np.abs(got - ref).max() <= 1e-5 * max(np.abs(ref).max(), 0.5)

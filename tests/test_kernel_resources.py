@@ -97,6 +97,26 @@ def test_radix64_kernel_is_tma_staged_and_mid_kernel_uses_cp_async():
     assert count(s, r"\bF2I|\bI2F") == 0                   # integer decode and pixel rounding stay on the FMA pipe
 
 
+def test_row_downconverter_stages_by_cp_async_and_reads_taps_from_the_constant_bank():
+    """downconvert_rows_kernel<D, MODE, NT, NBUF>: the raw tile arrives by 16-byte cp.async (LDGSTS.128), the shipped
+    variant (MODE 1) has no table loads in its tap loop -- its only shared-memory loads are the raw row (D/2 LDS.128 per
+    row and tile variant), the partial sums and nothing else -- and multiplies by taps held in uniform registers loaded
+    from the kernel-parameter bank (FFMA ..., UR..)."""
+    res = get_res()
+    rows = {k: v for k, v in res.items() if "downconvert_rows_kernel" in k}
+    assert len(rows) >= 16                                   # D in {4, 8, 16, 32} x (table variant + four shapes)
+    for k, v in rows.items():
+        assert v["REG"] <= 128 and v["STACK"] <= 64, (k, v)
+    name = "_ZN2sa23downconvert_rows_kernelILi16ELi1ELi128ELi2EEEvNS_6DcArgsENS_10DcRowsTapsIXT_EEE"     # C3: D 16, 128 rows, 2 buffers
+    assert name in rows and rows[name]["STACK"] == 0, sorted(rows)
+    s = sass(name)
+    assert count(s, r"\bLDGSTS\.E\.BYPASS\.128") >= 8          # 8 chunks per thread and tile
+    assert count(s, r"\bFFMA R\d+, R\d+(\.reuse)?, UR\d+, R\d+") >= 900                 # ~16 taps x 16 samples x (2 parities x 2 edge variants); a few taps ride in vector registers
+    assert count(s, r"\bLDS\.128") == 4 * 8                   # the raw row only: 8 chunks x 4 variants of the tap loop
+    table = sass("_ZN2sa23downconvert_rows_kernelILi16ELi0ELi256ELi1EEEvNS_6DcArgsENS_10DcRowsTapsIXT_EEE")
+    assert count(table, r"\bLDS\.128") >= 2 * (8 + 3 * 16)     # the ablation variant reads taps and NCO phasors as tables
+
+
 def test_no_tensor_core_or_library_fft_code():
     out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, timeout=600).stdout
     # DESIGN section 4: no DFT-as-GEMM stage is shipped.  The ONLY kernel with tensor-core / TMEM instructions is the
