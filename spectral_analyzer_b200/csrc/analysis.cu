@@ -124,22 +124,42 @@ static DcRowsShape dc_rows_shape(int down) {
     if (sh.mode == 0) { sh.nt = 256; sh.nbuf = 1; }        // the table variant exists in the first shape only (ablation record)
     return sh;
 }
-template <int D> const void* dc_rows_kernel_of(const DcRowsShape& sh, size_t* smem) {
-    if (sh.mode == 0) { *smem = DcRowsGeo<D, 256, 1>::SMEM; return (const void*)&downconvert_rows_kernel<D, 0, 256, 1>; }
-    if (sh.nt == 256 && sh.nbuf == 1) { *smem = DcRowsGeo<D, 256, 1>::SMEM; return (const void*)&downconvert_rows_kernel<D, 1, 256, 1>; }
-    if (sh.nt == 256 && sh.nbuf == 2) { *smem = DcRowsGeo<D, 256, 2>::SMEM; return (const void*)&downconvert_rows_kernel<D, 1, 256, 2>; }
-    if (sh.nt == 128 && sh.nbuf == 1) { *smem = DcRowsGeo<D, 128, 1>::SMEM; return (const void*)&downconvert_rows_kernel<D, 1, 128, 1>; }
-    *smem = DcRowsGeo<D, 128, 2>::SMEM; return (const void*)&downconvert_rows_kernel<D, 1, 128, 2>;
+template <int DK, int D, int NT, int NBUF> const void* dc_rows_fn(size_t* smem) {
+    *smem = DcRowsGeo<D, NT, NBUF, DcRowsSpc<DK>::value>::SMEM;
+    return (const void*)&downconvert_rows_kernel<DK, D, 1, NT, NBUF>;
 }
-const void* dc_rows_kernel(int down, const DcRowsShape& sh, size_t* smem) {
+// cf32: every shape (the A/B record of dc_rows_shape) and the table variant; the integer types: the default shapes only
+template <int DK, int D> const void* dc_rows_kernel_of(const DcRowsShape& sh, size_t* smem) {
+    if constexpr (D % DcRowsSpc<DK>::value != 0) { *smem = 0; return nullptr; }
+    else if constexpr (DK == DK_CF32) {
+        if (sh.mode == 0) { *smem = DcRowsGeo<D, 256, 1>::SMEM; return (const void*)&downconvert_rows_kernel<DK_CF32, D, 0, 256, 1>; }
+        if (sh.nt == 256 && sh.nbuf == 1) return dc_rows_fn<DK, D, 256, 1>(smem);
+        if (sh.nt == 256 && sh.nbuf == 2) return dc_rows_fn<DK, D, 256, 2>(smem);
+        if (sh.nt == 128 && sh.nbuf == 1) return dc_rows_fn<DK, D, 128, 1>(smem);
+        return dc_rows_fn<DK, D, 128, 2>(smem);
+    } else {
+        return sh.nbuf == 1 ? dc_rows_fn<DK, D, 128, 1>(smem) : dc_rows_fn<DK, D, 128, 2>(smem);
+    }
+}
+template <int DK> const void* dc_rows_kernel_dk(int down, const DcRowsShape& sh, size_t* smem) {
     switch (down) {
-        case 4:  return dc_rows_kernel_of<4>(sh, smem);
-        case 8:  return dc_rows_kernel_of<8>(sh, smem);
-        case 16: return dc_rows_kernel_of<16>(sh, smem);
-        case 32: return dc_rows_kernel_of<32>(sh, smem);
+        case 4:  return dc_rows_kernel_of<DK, 4>(sh, smem);
+        case 8:  return dc_rows_kernel_of<DK, 8>(sh, smem);
+        case 16: return dc_rows_kernel_of<DK, 16>(sh, smem);
+        case 32: return dc_rows_kernel_of<DK, 32>(sh, smem);
         default: *smem = 0; return nullptr;
     }
 }
+const void* dc_rows_kernel(int dk, int down, DcRowsShape sh, size_t* smem) {
+    if (dk != DK_CF32) { sh.mode = 1; sh.nt = 128; }
+    switch (dk) {
+        case DK_CF32: return dc_rows_kernel_dk<DK_CF32>(down, sh, smem);
+        case DK_CI16: return dc_rows_kernel_dk<DK_CI16>(down, sh, smem);
+        case DK_C8:   return dc_rows_kernel_dk<DK_C8>(down, sh, smem);
+        default: *smem = 0; return nullptr;
+    }
+}
+static bool dc_rows_aligned(long long first, long long spc) { const long long r = first & (spc - 1); return r == 0 || r == spc - 1; }
 // kernel-parameter tap block of the row kernel (the layout of DcRowsTaps<D>): g[sg][i][p] = h[(p+1)D - i - sg], h[0], h[8D]
 static void dc_rows_taps(const float* h, int D, std::vector<float>& out) {
     out.assign((size_t)2 * D * 8 + 4, 0.f);
@@ -350,9 +370,10 @@ static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, i
     std::vector<float> taps;
     std::map<int, int> taps_off;
     std::vector<char> piped(n_ann, 0), rowsk(n_ann, 0);
-    // row-per-thread kernel: 16-byte cp.async of raw cf32 pairs, so little-endian cf32 from a 16-byte aligned base
+    // row-per-thread kernel: 16-byte cp.async of raw rows, so a 16-byte aligned base and rows that start on a chunk boundary
     static const char* rows_env = getenv("SA_DC_ROWS");
-    const bool rows_ok = (rows_env ? atoi(rows_env) != 0 : true) && dk == DK_CF32 && !big_endian && ((uintptr_t)d_iq & 15) == 0;
+    const bool rows_ok = (rows_env ? atoi(rows_env) != 0 : true) && (dk == DK_CF32 || dk == DK_CI16 || dk == DK_C8) && ((uintptr_t)d_iq & 15) == 0;
+    const long long rows_spc = dk == DK_CF32 ? 2 : (dk == DK_CI16 ? 4 : 8);
     uint64_t scr_total = 0;
     for (uint32_t i = 0; i < n_ann; i++) {
         DcAnn& a = plan[i];
@@ -386,7 +407,8 @@ static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, i
         size_t rows_smem = 0;
         if (wide) {
             a.nb = 0;                       // marks the warp-per-output kernel
-        } else if (rows_ok && !a.fast && dc_rows_kernel(D, dc_rows_shape(D), &rows_smem)) {
+        } else if (rows_ok && !a.fast && dc_rows_aligned(a.start_sample + a.in_off, rows_spc) && !(big_endian && dc_rows_shape(D).mode == 0) &&
+                   dc_rows_kernel(dk, D, dc_rows_shape(D), &rows_smem)) {
             a.nb = dc_rows_shape(D).nt - 8;
             rowsk[i] = 1;
         } else if (pipe_ok && !a.fast && D <= 32) {
@@ -580,7 +602,7 @@ static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, i
                 for (uint32_t i = g0; i < g1; i++) tiles = std::max<long long>(tiles, (sorted[i].m_out + first.nb - 1) / first.nb);
                 size_t smem = 0;
                 const DcRowsShape rows_shape = dc_rows_shape(first.down);
-                const void* fn = dc_rows_kernel(first.down, rows_shape, &smem);
+                const void* fn = dc_rows_kernel(dk, first.down, rows_shape, &smem);
                 std::vector<float> rt;
                 dc_rows_taps(taps.data() + first.taps_off, first.down, rt);
                 void* rargs[] = { &da, rt.data() };

@@ -416,10 +416,15 @@ downconvert_wide_kernel(const DcArgs a) {
 //   sg = 1: rows END   at q - pD    : taps k = 0..8D-1 from rows j+1..j+8, lone tap h[8D] on the last sample of row j
 // (j = output index within the tile, 248 outputs per 256 rows).  Samples outside the annotation are zeroed in the
 // tiles that touch its ends; chunks outside the recording are not read (cp.async src-size 0 / 8).
-template <int D, int NT = 256, int NBUF = 1> struct DcRowsGeo {
+// Input types: cf32 (2 samples per 16-byte chunk), ci16 (4), cu8 / ci8 (8), either byte order; the integer types are decoded
+// in the tap loop (the same exact one-FMA decodes as everywhere else).  A row must be whole chunks (D a multiple of the
+// samples per chunk) and start on a chunk boundary of the recording: (start_sample + in_off) mod SPC must be 0 (sg = 0)
+// or SPC - 1 (sg = 1); every other alignment takes the staged kernel above.
+template <int DK> struct DcRowsSpc { static constexpr int value = DK == DK_CF32 ? 2 : (DK == DK_CI16 ? 4 : 8); };
+template <int D, int NT = 256, int NBUF = 1, int SPC = 2> struct DcRowsGeo {
     static_assert(D >= 4 && D <= 32 && (D & (D - 1)) == 0, "row kernel: power-of-two decimation, 4..32");
-    static_assert(NT % (D / 2) == 0 && (NBUF == 1 || NBUF == 2), "row kernel geometry");
-    static constexpr int CPR = D / 2;                    // 16-byte chunks (2 cf32 samples) per row
+    static_assert(D % SPC == 0 && NT % (D / SPC) == 0 && (NBUF == 1 || NBUF == 2), "row kernel geometry");
+    static constexpr int CPR = D / SPC;                  // 16-byte chunks per row
     static constexpr int RS = CPR | 1;                   // row stride in chunks (odd)
     static constexpr int RAW_BYTES = NT * RS * 16;       // one raw tile: NT rows
     static constexpr int CSM_BYTES = 9 * NT * 8;
@@ -482,21 +487,39 @@ template <int D> struct DcRowsTaps {
     float pad_[2];
 };
 
-template <int D, bool INTERIOR, int SG>
-__device__ __forceinline__ void dc_rows_fir_c(const DcRowsTaps<D>& tp, const uint32_t row_s, const long long n_row, const long long count,
-                                              float2 P, const float2 W, float (&sr)[8], float (&si)[8], float2& y_lone) {
+// the SPC samples of one 16-byte chunk
+template <int DK, bool SWAP> __device__ __forceinline__ void dc_rows_decode(const LoadParams& lp, const uint4 w, float2 (&x)[DcRowsSpc<DK>::value]) {
+    const uint32_t ww[4] = { w.x, w.y, w.z, w.w };
+    if constexpr (DK == DK_CF32) {
 #pragma unroll
-    for (int c = 0; c < D / 2; c++) {
-        float4 x = lds128(row_s + 16u * (unsigned)c);
-        if constexpr (!INTERIOR) {
-            const long long n = n_row + 2 * c;
-            if (n < 0 || n >= count) { x.x = 0.f; x.y = 0.f; }
-            if (n + 1 < 0 || n + 1 >= count) { x.z = 0.f; x.w = 0.f; }
-        }
+        for (int j = 0; j < 2; j++) { const cpx<float> v = Loader<float, DK_CF32>::template decode<SWAP>(lp, make_uint2(ww[2 * j], ww[2 * j + 1])); x[j] = make_float2(v.x, v.y); }
+    } else if constexpr (DK == DK_CI16) {
 #pragma unroll
-        for (int hh = 0; hh < 2; hh++) {
-            const int i = 2 * c + hh;
-            const float xr = hh ? x.z : x.x, xi = hh ? x.w : x.y;
+        for (int j = 0; j < 4; j++) { const cpx<float> v = Loader<float, DK_CI16>::template decode<SWAP>(lp, ww[j]); x[j] = make_float2(v.x, v.y); }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) { const cpx<float> v = Loader<float, DK_C8>::template decode<SWAP>(lp, (uint16_t)(ww[j >> 1] >> (16 * (j & 1)))); x[j] = make_float2(v.x, v.y); }
+    }
+}
+
+template <int DK, bool SWAP, int D, bool INTERIOR, int SG>
+__device__ __forceinline__ void dc_rows_fir_c(const DcRowsTaps<D>& tp, const LoadParams& lp, const uint32_t row_s, const long long n_row,
+                                              const long long count, float2 P, const float2 W, float (&sr)[8], float (&si)[8], float2& y_lone) {
+    constexpr int SPC = DcRowsSpc<DK>::value;
+#pragma unroll
+    for (int c = 0; c < D / SPC; c++) {
+        uint4 raw;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w) : "r"(row_s + 16u * (unsigned)c) : "memory");
+        float2 x[SPC];
+        dc_rows_decode<DK, SWAP>(lp, raw, x);
+#pragma unroll
+        for (int hh = 0; hh < SPC; hh++) {
+            const int i = SPC * c + hh;
+            if constexpr (!INTERIOR) {
+                const long long n = n_row + i;
+                if (n < 0 || n >= count) x[hh] = make_float2(0.f, 0.f);
+            }
+            const float xr = x[hh].x, xi = x[hh].y;
             const float yr = __fmaf_rn(xr, P.x, -xi * P.y), yi = __fmaf_rn(xr, P.y, xi * P.x);
             if (i == (SG ? D - 1 : 0)) y_lone = make_float2(yr, yi);
             if (i + 1 < D) P = make_float2(__fmaf_rn(P.x, W.x, -P.y * W.y), __fmaf_rn(P.x, W.y, P.y * W.x));
@@ -509,10 +532,25 @@ __device__ __forceinline__ void dc_rows_fir_c(const DcRowsTaps<D>& tp, const uin
     }
 }
 
-template <int D, int MODE, int NT, int NBUF>
-__global__ void __launch_bounds__(NT, DcRowsGeo<D, NT, NBUF>::MINB)
+template <int DK, bool SWAP, int D>
+__device__ __forceinline__ void dc_rows_fir_pick(const DcRowsTaps<D>& tp, const LoadParams& lp, const int sg, const bool interior, const uint32_t row_s,
+                                                 const long long n_row, const long long count, const float2 P, const float2 W,
+                                                 float (&sr)[8], float (&si)[8], float2& yl) {
+    if (sg) {
+        if (interior) dc_rows_fir_c<DK, SWAP, D, true, 1>(tp, lp, row_s, n_row, count, P, W, sr, si, yl);
+        else          dc_rows_fir_c<DK, SWAP, D, false, 1>(tp, lp, row_s, n_row, count, P, W, sr, si, yl);
+    } else {
+        if (interior) dc_rows_fir_c<DK, SWAP, D, true, 0>(tp, lp, row_s, n_row, count, P, W, sr, si, yl);
+        else          dc_rows_fir_c<DK, SWAP, D, false, 0>(tp, lp, row_s, n_row, count, P, W, sr, si, yl);
+    }
+}
+
+template <int DK, int D, int MODE, int NT, int NBUF>
+__global__ void __launch_bounds__(NT, DcRowsGeo<D, NT, NBUF, DcRowsSpc<DK>::value>::MINB)
 downconvert_rows_kernel(const DcArgs a, const __grid_constant__ DcRowsTaps<D> tp) {
-    using G = DcRowsGeo<D, NT, NBUF>;
+    constexpr int SPC = DcRowsSpc<DK>::value, BPS = 16 / SPC;
+    static_assert(MODE == 1 || DK == DK_CF32, "the table variant is cf32 little-endian only");
+    using G = DcRowsGeo<D, NT, NBUF, SPC>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const DcAnn an = a.anns[a.ann_base + blockIdx.y];
     constexpr int NB = NT - 8;
@@ -523,7 +561,7 @@ downconvert_rows_kernel(const DcArgs a, const __grid_constant__ DcRowsTaps<D> tp
     const int t = threadIdx.x;
     const uint32_t smem_s = ((uint32_t)__cvta_generic_to_shared(smem_raw) + 127u) & ~127u;
     const uint32_t raw_s = smem_s, csm_s = raw_s + NBUF * G::RAW_BYTES, g_s = csm_s + G::CSM_BYTES, t_s = g_s + G::G_BYTES;
-    const int sg = (int)((an.start_sample + an.in_off) & 1);
+    const int sg = ((an.start_sample + an.in_off) & (SPC - 1)) ? 1 : 0;       // eligible annotations: residue 0 or SPC - 1
     float h_lone;
     float2 W = make_float2(1.f, 0.f);
     if constexpr (MODE == 0) {
@@ -549,16 +587,16 @@ downconvert_rows_kernel(const DcArgs a, const __grid_constant__ DcRowsTaps<D> tp
     constexpr uint32_t kDstStep = (NT / G::CPR) * G::RS * 16;
     auto tile_n0 = [&](long long tl) { return (tl * NB - 8 - sg) * D + an.in_off + sg; };       // sample of row 0 (annotation-relative)
     auto issue = [&](long long tl, uint32_t dst0) {
-        const long long s0 = an.start_sample + tile_n0(tl);                                     // even by construction
-        const char* src = reinterpret_cast<const char*>(a.lp.base) + 8 * s0 + 16 * (long long)t;
+        const long long s0 = an.start_sample + tile_n0(tl);                                     // a chunk boundary by construction
+        const char* src = reinterpret_cast<const char*>(a.lp.base) + BPS * s0 + 16 * (long long)t;
         if (s0 >= 0 && s0 + (long long)NT * D <= a.n_samples) {
 #pragma unroll
             for (int k = 0; k < G::CPR; k++) cp_async16(dst0 + kDstStep * k, src + (size_t)NT * 16 * k);
         } else {
 #pragma unroll
             for (int k = 0; k < G::CPR; k++) {
-                const long long s = s0 + 2 * ((long long)t + NT * k);
-                const int bytes = s < 0 ? 0 : (int)max(0LL, min(2LL, a.n_samples - s)) * 8;
+                const long long s = s0 + SPC * ((long long)t + NT * k);
+                const int bytes = s < 0 ? 0 : (int)max(0LL, min((long long)SPC, a.n_samples - s)) * BPS;
                 cp_async16_partial(dst0 + kDstStep * k, bytes ? (const void*)(src + (size_t)NT * 16 * k) : a.lp.base, bytes);
             }
         }
@@ -605,12 +643,11 @@ downconvert_rows_kernel(const DcArgs a, const __grid_constant__ DcRowsTaps<D> tp
 #pragma unroll
             for (int p = 0; p < 8; p++) { sr[p] = 0.f; si[p] = 0.f; }
             float2 yl = make_float2(0.f, 0.f);
-            if (sg) {
-                if (interior) dc_rows_fir_c<D, true, 1>(tp, row_s, n_row, an.count, P, W, sr, si, yl);
-                else          dc_rows_fir_c<D, false, 1>(tp, row_s, n_row, an.count, P, W, sr, si, yl);
+            if constexpr (DK == DK_C8) {
+                dc_rows_fir_pick<DK, false, D>(tp, a.lp, sg, interior, row_s, n_row, an.count, P, W, sr, si, yl);
             } else {
-                if (interior) dc_rows_fir_c<D, true, 0>(tp, row_s, n_row, an.count, P, W, sr, si, yl);
-                else          dc_rows_fir_c<D, false, 0>(tp, row_s, n_row, an.count, P, W, sr, si, yl);
+                if (a.lp.swap) dc_rows_fir_pick<DK, true, D>(tp, a.lp, sg, interior, row_s, n_row, an.count, P, W, sr, si, yl);
+                else           dc_rows_fir_pick<DK, false, D>(tp, a.lp, sg, interior, row_s, n_row, an.count, P, W, sr, si, yl);
             }
 #pragma unroll
             for (int p = 0; p < 8; p++) sts64(csm_s + 8u * (unsigned)(p * NT + t), sr[p], si[p]);

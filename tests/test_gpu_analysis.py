@@ -240,7 +240,8 @@ def test_psd_only_batch_matches_the_batch_with_rows(engine):
     _, psd_a = engine.downconvert_psd_batch(raw, "ci16_le", 1e6, anns, psd_nfft=4096, want_iq=True)
     none, psd_b = engine.downconvert_psd_batch(raw, "ci16_le", 1e6, anns, psd_nfft=4096, want_iq=False)
     assert none is None and np.array_equal(psd_a, psd_b)
-    assert engine.last_kernel == "downconvert_kernel(pipelined)+welch_accum_mid_kernel<float,4096>"     # sa_last_kernel_name
+    assert engine.last_kernel in ("downconvert_rows_kernel+welch_accum_mid_kernel<float,4096>",           # sa_last_kernel_name
+                                  "downconvert_kernel(pipelined)+welch_accum_mid_kernel<float,4096>")
     ref = co.psd_welch(co.downconvert(raw, "ci16_le", *anns[7][:4], False), 1e6 / 4, 4096)
     strong = ref[1] > ref[1].max() - 40
     assert np.abs(psd_b[7] - ref[1])[strong].max() < 5e-3
@@ -331,21 +332,22 @@ def test_batch_of_more_annotations_than_one_launch_holds(engine):
         assert np.abs(iq[i] - ref).max() <= DC_TOL * max(np.abs(ref).max(), 0.5)
 
 
+@pytest.mark.parametrize("dt", ["cf32_le", "cf32_be", "ci16_le", "ci16_be", "cu8", "ci8"])
 @pytest.mark.parametrize("down", [8, 16, 32])
 @pytest.mark.parametrize("start,delay", [(0, "causal"), (1, "causal"), (122, "same"), (123, "same"), (4096, "valid"), (4097, "valid")])
-def test_row_kernel_alignment_edges_and_tiles(engine, down, start, delay):
-    """cf32 / power-of-two decimation takes the row-per-thread kernel (16-byte cp.async of raw rows): both parities of
+def test_row_kernel_alignment_edges_and_tiles(engine, dt, down, start, delay):
+    """Power-of-two decimation takes the row-per-thread kernel (16-byte cp.async of raw rows): both parities of
     (start + delay shift) -- the two decompositions of the tap sum --, an annotation that begins at sample 0 of the
     recording and one that ends at its last sample (chunks outside the recording are not read), zero history / zero
     tail inside a longer recording, several tiles per CTA, a count that is not a multiple of down."""
     count = 2 * 248 * down * 5 + 3 * down + 5            # a little over 10 tiles
     for tail in (0, 1, 333):                             # annotation ends at the end of the buffer / before it
-        raw = synth.recording(start + count + tail, "cf32_le", seed=21 + tail)
+        raw = synth.recording(start + count + tail, dt, seed=21 + tail)
         cfg = co.analysis_cfg(delay=delay, length="ceil")
-        ref = co.downconvert_ex(raw, "cf32_le", start, count, -0.3217, down, False, cfg)
+        ref = co.downconvert_ex(raw, dt, start, count, -0.3217, down, False, cfg)
         engine.set_analysis_config(delay=delay, length="ceil")
         try:
-            got = engine.downconvert(raw, "cf32_le", start, count, -0.3217, down, False)
+            got = engine.downconvert(raw, dt, start, count, -0.3217, down, False)
             name = engine.last_kernel
         finally:
             engine.reset_analysis_config()
@@ -373,18 +375,21 @@ def test_row_kernel_short_annotations(engine, count):
             assert np.abs(got - ref).max() <= DC_TOL * max(np.abs(ref).max(), 0.5), (start, tp is None)
 
 
-def test_row_kernel_device_path_odd_starts_and_recording_ends(engine):
+@pytest.mark.parametrize("dt,code", [("cf32_le", 0), ("ci16_le", 1), ("cu8", 2)])
+def test_row_kernel_device_path_odd_starts_and_recording_ends(engine, dt, code):
     """The device-resident batch call keeps the caller's sample offsets (the host call packs every span at an even
-    offset): odd and even starts, annotations touching sample 0 and the last sample of the recording, mixed
-    decimation factors in one call, each against the oracle."""
+    offset): odd and even starts (for the integer types: every residue of the start modulo the samples per 16-byte
+    chunk -- two of them take the row kernel, the others the staged kernel), annotations touching sample 0 and the last
+    sample of the recording, mixed decimation factors in one call, each against the oracle."""
     import ctypes as C
     import torch
     from spectral_analyzer_b200 import _capi
     n = 300001
-    raw = synth.recording(n, "cf32_le", seed=17)
+    raw = synth.recording(n, dt, seed=17)
     d_raw = torch.from_numpy(np.frombuffer(raw, np.uint8).copy()).cuda()
     specs = [(0, 100000, 16), (1, 100001, 16), (12345, 77777, 16), (200000, 100001, 16), (199999, 100002, 8),
-             (3, 299998, 32), (150001, 40000, 16), (150002, 40000, 16)]
+             (3, 299998, 32), (150001, 40000, 16), (150002, 40000, 16), (150003, 40000, 16), (150004, 40000, 16),
+             (150005, 40000, 8), (150006, 40000, 8), (150007, 40000, 32), (150008, 40000, 32)]
     anns = (_capi.Annotation * len(specs))()
     offs = (C.c_uint64 * len(specs))()
     total = 0
@@ -394,12 +399,12 @@ def test_row_kernel_device_path_odd_starts_and_recording_ends(engine):
         total += 2 * (c // d)
     d_iq = torch.empty(total, dtype=torch.float64, device="cuda")
     _capi.check(_capi.lib().sa_downconvert_psd_batch_device(
-        engine.handle, d_raw.data_ptr(), d_raw.numel(), 0, 0, 1.0e6, anns, len(specs), 0, 0, 1, d_iq.data_ptr(), offs,
+        engine.handle, d_raw.data_ptr(), d_raw.numel(), code, 0, 1.0e6, anns, len(specs), 0, 0, 1, d_iq.data_ptr(), offs,
         None, torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     got_all = d_iq.cpu().numpy()
     for i, (s, c, d) in enumerate(specs):
-        ref = co.downconvert(raw, "cf32_le", s, c, 0.05 + 0.031 * i, d, False)
+        ref = co.downconvert(raw, dt, s, c, 0.05 + 0.031 * i, d, False)
         got = got_all[offs[i]:offs[i] + 2 * (c // d)].reshape(2, c // d)
         assert rel_err(got, ref) < DC_TOL, (i, s, c, d)
 
