@@ -105,7 +105,7 @@ const void* dc_kernel(int dk, int which) {
 
 // row-per-thread kernel (cf32, little-endian, power-of-two decimation): nullptr when there is none for this factor.
 // mode 0: taps and NCO phasors as shared-memory tables, FFMA2; mode 1: taps as constant-bank immediates, NCO recurrence
-struct DcRowsShape { int mode, nt, nbuf; };
+struct DcRowsShape { int mode, nt, nbuf, swz; };
 // Shape of the row kernel, measured on B200 (C3 = 500 x 2^20 samples at D 16 incl. Welch; tools/dc_matrix.py for 8 / 32):
 //   rows per tile x raw buffers     C3          D 8        D 16       D 32
 //   256 x 1                          1.413 ms    0.827      0.621      0.479
@@ -118,27 +118,30 @@ static DcRowsShape dc_rows_shape(int down) {
     static const char* me = getenv("SA_DC_ROWS_MODE");
     static const char* ne = getenv("SA_DC_ROWS_NT");
     static const char* be = getenv("SA_DC_ROWS_NBUF");
-    DcRowsShape sh = { me ? atoi(me) : 1, ne ? atoi(ne) : 128, be ? atoi(be) : (down >= 32 ? 1 : 2) };
+    static const char* se = getenv("SA_DC_ROWS_SWZ");
+    DcRowsShape sh = { me ? atoi(me) : 1, ne ? atoi(ne) : 128, be ? atoi(be) : (down >= 32 ? 1 : 2), se ? atoi(se) : 1 };
     if (sh.nt != 256) sh.nt = 128;
     if (sh.nbuf != 1) sh.nbuf = 2;
-    if (sh.mode == 0) { sh.nt = 256; sh.nbuf = 1; }        // the table variant exists in the first shape only (ablation record)
+    if (sh.mode == 0) { sh.nt = 256; sh.nbuf = 1; sh.swz = 0; }
+    if (sh.nt == 256) sh.swz = 0;                          // swizzled rows exist in the 128-row shapes        // the table variant exists in the first shape only (ablation record)
     return sh;
 }
-template <int DK, int D, int NT, int NBUF> const void* dc_rows_fn(size_t* smem) {
-    *smem = DcRowsGeo<D, NT, NBUF, DcRowsSpc<DK>::value>::SMEM;
-    return (const void*)&downconvert_rows_kernel<DK, D, 1, NT, NBUF>;
+template <int DK, int D, int NT, int NBUF, bool SWZ = false> const void* dc_rows_fn(size_t* smem) {
+    *smem = DcRowsGeo<D, NT, NBUF, DcRowsSpc<DK>::value, SWZ>::SMEM;
+    return (const void*)&downconvert_rows_kernel<DK, D, 1, NT, NBUF, SWZ>;
 }
 // cf32: every shape (the A/B record of dc_rows_shape) and the table variant; the integer types: the default shapes only
 template <int DK, int D> const void* dc_rows_kernel_of(const DcRowsShape& sh, size_t* smem) {
     if constexpr (D % DcRowsSpc<DK>::value != 0) { *smem = 0; return nullptr; }
     else if constexpr (DK == DK_CF32) {
-        if (sh.mode == 0) { *smem = DcRowsGeo<D, 256, 1>::SMEM; return (const void*)&downconvert_rows_kernel<DK_CF32, D, 0, 256, 1>; }
+        if (sh.mode == 0) { *smem = DcRowsGeo<D, 256, 1>::SMEM; return (const void*)&downconvert_rows_kernel<DK_CF32, D, 0, 256, 1, false>; }
         if (sh.nt == 256 && sh.nbuf == 1) return dc_rows_fn<DK, D, 256, 1>(smem);
         if (sh.nt == 256 && sh.nbuf == 2) return dc_rows_fn<DK, D, 256, 2>(smem);
-        if (sh.nt == 128 && sh.nbuf == 1) return dc_rows_fn<DK, D, 128, 1>(smem);
-        return dc_rows_fn<DK, D, 128, 2>(smem);
+        if (sh.nt == 128 && sh.nbuf == 1) return sh.swz ? dc_rows_fn<DK, D, 128, 1, true>(smem) : dc_rows_fn<DK, D, 128, 1>(smem);
+        return sh.swz ? dc_rows_fn<DK, D, 128, 2, true>(smem) : dc_rows_fn<DK, D, 128, 2>(smem);
     } else {
-        return sh.nbuf == 1 ? dc_rows_fn<DK, D, 128, 1>(smem) : dc_rows_fn<DK, D, 128, 2>(smem);
+        if (sh.nbuf == 1) return sh.swz ? dc_rows_fn<DK, D, 128, 1, true>(smem) : dc_rows_fn<DK, D, 128, 1>(smem);
+        return sh.swz ? dc_rows_fn<DK, D, 128, 2, true>(smem) : dc_rows_fn<DK, D, 128, 2>(smem);
     }
 }
 template <int DK> const void* dc_rows_kernel_dk(int down, const DcRowsShape& sh, size_t* smem) {

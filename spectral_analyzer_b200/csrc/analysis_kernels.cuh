@@ -421,16 +421,28 @@ downconvert_wide_kernel(const DcArgs a) {
 // samples per chunk) and start on a chunk boundary of the recording: (start_sample + in_off) mod SPC must be 0 (sg = 0)
 // or SPC - 1 (sg = 1); every other alignment takes the staged kernel above.
 template <int DK> struct DcRowsSpc { static constexpr int value = DK == DK_CF32 ? 2 : (DK == DK_CI16 ? 4 : 8); };
-template <int D, int NT = 256, int NBUF = 1, int SPC = 2> struct DcRowsGeo {
+// SWZ: rows are packed (CPR chunks apart) and chunk c of row r sits at position c ^ swz(r) instead of rows being padded to
+// an odd stride: the same conflict-free 128-bit row reads (8 consecutive rows hit 8 different 16-byte bank groups) in
+// 8/9 of the shared memory, which is one more CTA per SM for the 128-row double-buffered shape.
+#ifndef SA_DC_ROWS_ALIAS
+#define SA_DC_ROWS_ALIAS 1
+#endif
+template <int CPR> __host__ __device__ constexpr int dc_rows_swz(int row) {
+    return CPR >= 8 ? (row & 7) : (CPR == 4 ? ((row >> 1) & 3) : (CPR == 2 ? ((row >> 2) & 1) : 0));
+}
+template <int D, int NT = 256, int NBUF = 1, int SPC = 2, bool SWZ = false> struct DcRowsGeo {
     static_assert(D >= 4 && D <= 32 && (D & (D - 1)) == 0, "row kernel: power-of-two decimation, 4..32");
     static_assert(D % SPC == 0 && NT % (D / SPC) == 0 && (NBUF == 1 || NBUF == 2), "row kernel geometry");
     static constexpr int CPR = D / SPC;                  // 16-byte chunks per row
-    static constexpr int RS = CPR | 1;                   // row stride in chunks (odd)
+    static constexpr int RS = SWZ ? CPR : (CPR | 1);     // row stride in chunks (odd unless swizzled)
     static constexpr int RAW_BYTES = NT * RS * 16;       // one raw tile: NT rows
     static constexpr int CSM_BYTES = 9 * NT * 8;
     static constexpr int G_BYTES = D * 32;               // G[i][p]
     static constexpr int T_BYTES = D * 16;               // (T.x, T.y, -T.y, T.x)
-    static constexpr int SMEM = 128 + NBUF * RAW_BYTES + CSM_BYTES + G_BYTES + T_BYTES;
+    // ALIAS: with two raw buffers the partial sums are written over the raw tile that has just been consumed (one more
+    // barrier per tile, no shared memory of their own)
+    static constexpr bool ALIAS = SA_DC_ROWS_ALIAS && NBUF == 2 && SWZ && RAW_BYTES >= CSM_BYTES;
+    static constexpr int SMEM = 128 + NBUF * RAW_BYTES + (ALIAS ? 0 : CSM_BYTES) + G_BYTES + T_BYTES;
     static constexpr int BY_SMEM = (227 * 1024) / (SMEM + 1024);
     static constexpr int BY_WARPS = 2048 / NT;
     static constexpr int BY_REGS = 65536 / (NT * 64);    // aim: 64 registers per thread at most when that raises occupancy
@@ -503,13 +515,13 @@ template <int DK, bool SWAP> __device__ __forceinline__ void dc_rows_decode(cons
 }
 
 template <int DK, bool SWAP, int D, bool INTERIOR, int SG>
-__device__ __forceinline__ void dc_rows_fir_c(const DcRowsTaps<D>& tp, const LoadParams& lp, const uint32_t row_s, const long long n_row,
+__device__ __forceinline__ void dc_rows_fir_c(const DcRowsTaps<D>& tp, const LoadParams& lp, const uint32_t row_s, const uint32_t swz16, const long long n_row,
                                               const long long count, float2 P, const float2 W, float (&sr)[8], float (&si)[8], float2& y_lone) {
     constexpr int SPC = DcRowsSpc<DK>::value;
 #pragma unroll
     for (int c = 0; c < D / SPC; c++) {
         uint4 raw;
-        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w) : "r"(row_s + 16u * (unsigned)c) : "memory");
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w) : "r"(row_s + ((16u * (unsigned)c) ^ swz16)) : "memory");
         float2 x[SPC];
         dc_rows_decode<DK, SWAP>(lp, raw, x);
 #pragma unroll
@@ -534,23 +546,23 @@ __device__ __forceinline__ void dc_rows_fir_c(const DcRowsTaps<D>& tp, const Loa
 
 template <int DK, bool SWAP, int D>
 __device__ __forceinline__ void dc_rows_fir_pick(const DcRowsTaps<D>& tp, const LoadParams& lp, const int sg, const bool interior, const uint32_t row_s,
-                                                 const long long n_row, const long long count, const float2 P, const float2 W,
+                                                 const uint32_t swz16, const long long n_row, const long long count, const float2 P, const float2 W,
                                                  float (&sr)[8], float (&si)[8], float2& yl) {
     if (sg) {
-        if (interior) dc_rows_fir_c<DK, SWAP, D, true, 1>(tp, lp, row_s, n_row, count, P, W, sr, si, yl);
-        else          dc_rows_fir_c<DK, SWAP, D, false, 1>(tp, lp, row_s, n_row, count, P, W, sr, si, yl);
+        if (interior) dc_rows_fir_c<DK, SWAP, D, true, 1>(tp, lp, row_s, swz16, n_row, count, P, W, sr, si, yl);
+        else          dc_rows_fir_c<DK, SWAP, D, false, 1>(tp, lp, row_s, swz16, n_row, count, P, W, sr, si, yl);
     } else {
-        if (interior) dc_rows_fir_c<DK, SWAP, D, true, 0>(tp, lp, row_s, n_row, count, P, W, sr, si, yl);
-        else          dc_rows_fir_c<DK, SWAP, D, false, 0>(tp, lp, row_s, n_row, count, P, W, sr, si, yl);
+        if (interior) dc_rows_fir_c<DK, SWAP, D, true, 0>(tp, lp, row_s, swz16, n_row, count, P, W, sr, si, yl);
+        else          dc_rows_fir_c<DK, SWAP, D, false, 0>(tp, lp, row_s, swz16, n_row, count, P, W, sr, si, yl);
     }
 }
 
-template <int DK, int D, int MODE, int NT, int NBUF>
-__global__ void __launch_bounds__(NT, DcRowsGeo<D, NT, NBUF, DcRowsSpc<DK>::value>::MINB)
+template <int DK, int D, int MODE, int NT, int NBUF, bool SWZ>
+__global__ void __launch_bounds__(NT, DcRowsGeo<D, NT, NBUF, DcRowsSpc<DK>::value, SWZ>::MINB)
 downconvert_rows_kernel(const DcArgs a, const __grid_constant__ DcRowsTaps<D> tp) {
     constexpr int SPC = DcRowsSpc<DK>::value, BPS = 16 / SPC;
-    static_assert(MODE == 1 || DK == DK_CF32, "the table variant is cf32 little-endian only");
-    using G = DcRowsGeo<D, NT, NBUF, SPC>;
+    static_assert(MODE == 1 || (DK == DK_CF32 && !SWZ), "the table variant is cf32 little-endian, padded rows only");
+    using G = DcRowsGeo<D, NT, NBUF, SPC, SWZ>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const DcAnn an = a.anns[a.ann_base + blockIdx.y];
     constexpr int NB = NT - 8;
@@ -560,7 +572,7 @@ downconvert_rows_kernel(const DcArgs a, const __grid_constant__ DcRowsTaps<D> tp
     if (tile >= tile_end) return;
     const int t = threadIdx.x;
     const uint32_t smem_s = ((uint32_t)__cvta_generic_to_shared(smem_raw) + 127u) & ~127u;
-    const uint32_t raw_s = smem_s, csm_s = raw_s + NBUF * G::RAW_BYTES, g_s = csm_s + G::CSM_BYTES, t_s = g_s + G::G_BYTES;
+    const uint32_t raw_s = smem_s, csm_own = raw_s + NBUF * G::RAW_BYTES, g_s = csm_own + (G::ALIAS ? 0 : G::CSM_BYTES), t_s = g_s + G::G_BYTES;
     const int sg = ((an.start_sample + an.in_off) & (SPC - 1)) ? 1 : 0;       // eligible annotations: residue 0 or SPC - 1
     float h_lone;
     float2 W = make_float2(1.f, 0.f);
@@ -583,7 +595,8 @@ downconvert_rows_kernel(const DcArgs a, const __grid_constant__ DcRowsTaps<D> tp
     const int lone_row = sg ? 0 : 8;                          // row (relative to j) that holds the lone sample
 
     // this thread's chunks of a tile: chunk g = t + NT k, row g / CPR, position g % CPR
-    const uint32_t dst_t = raw_s + 16u * (unsigned)((t / G::CPR) * G::RS + (t % G::CPR));
+    const uint32_t dst_t = raw_s + 16u * (unsigned)((t / G::CPR) * G::RS + ((t % G::CPR) ^ (SWZ ? dc_rows_swz<G::CPR>(t / G::CPR) : 0)));
+    const uint32_t swz16 = SWZ ? 16u * (unsigned)dc_rows_swz<G::CPR>(t) : 0u;
     constexpr uint32_t kDstStep = (NT / G::CPR) * G::RS * 16;
     auto tile_n0 = [&](long long tl) { return (tl * NB - 8 - sg) * D + an.in_off + sg; };       // sample of row 0 (annotation-relative)
     auto issue = [&](long long tl, uint32_t dst0) {
@@ -614,6 +627,7 @@ downconvert_rows_kernel(const DcArgs a, const __grid_constant__ DcRowsTaps<D> tp
         const float2 P = nco_phasor(an.phase_step * (unsigned long long)n_row);     // phasor of the row's first sample
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();                                    // the tile has landed; C_p of the previous tile has been consumed
+        const uint32_t csm_s = G::ALIAS ? raw_s + buf : csm_own;   // ALIAS: over the tile this iteration consumes
         if constexpr (NBUF == 2) {                          // the next tile flies under this tile's tap loop
             buf ^= (uint32_t)G::RAW_BYTES;
             if (tile + 1 < tile_end) issue(tile + 1, dst_t + buf);
@@ -644,11 +658,12 @@ downconvert_rows_kernel(const DcArgs a, const __grid_constant__ DcRowsTaps<D> tp
             for (int p = 0; p < 8; p++) { sr[p] = 0.f; si[p] = 0.f; }
             float2 yl = make_float2(0.f, 0.f);
             if constexpr (DK == DK_C8) {
-                dc_rows_fir_pick<DK, false, D>(tp, a.lp, sg, interior, row_s, n_row, an.count, P, W, sr, si, yl);
+                dc_rows_fir_pick<DK, false, D>(tp, a.lp, sg, interior, row_s, swz16, n_row, an.count, P, W, sr, si, yl);
             } else {
-                if (a.lp.swap) dc_rows_fir_pick<DK, true, D>(tp, a.lp, sg, interior, row_s, n_row, an.count, P, W, sr, si, yl);
-                else           dc_rows_fir_pick<DK, false, D>(tp, a.lp, sg, interior, row_s, n_row, an.count, P, W, sr, si, yl);
+                if (a.lp.swap) dc_rows_fir_pick<DK, true, D>(tp, a.lp, sg, interior, row_s, swz16, n_row, an.count, P, W, sr, si, yl);
+                else           dc_rows_fir_pick<DK, false, D>(tp, a.lp, sg, interior, row_s, swz16, n_row, an.count, P, W, sr, si, yl);
             }
+            if constexpr (G::ALIAS) __syncthreads();        // every row of the tile has been read
 #pragma unroll
             for (int p = 0; p < 8; p++) sts64(csm_s + 8u * (unsigned)(p * NT + t), sr[p], si[p]);
             sts64(csm_s + 8u * (unsigned)(8 * NT + t), h_lone * yl.x, h_lone * yl.y);
