@@ -34,7 +34,7 @@ void lowpass_taps(int down, std::vector<double>& h) {
     for (int k = 0; k < nt; k++) h[k] /= sum;
 }
 
-struct WelchKernel { const void* fn; const void* fin; int prec, n, cta, fpc; size_t smem; int p, np, radix[4]; int mid; };
+struct WelchKernel { const void* fn; const void* fin; int prec, n, cta, fpc; size_t smem; int p, np, radix[4]; int mid; int slots; };   // slots: partial spectra a CTA writes
 
 template <typename T, int N> WelchKernel make_welch(int prec) {
     using G = Geo<T, N>;
@@ -46,6 +46,7 @@ template <typename T, int N> WelchKernel make_welch(int prec) {
     k.n = N; k.cta = G::CTA; k.fpc = G::FPC; k.smem = G::SMEM_BYTES + G::TW_BYTES; k.p = G::P; k.np = PL::NP;
     for (int i = 0; i < 4; i++) k.radix[i] = PL::radix(i);
     k.mid = 0;
+    k.slots = k.fpc;
     return k;
 }
 // FP32 2048 .. 16384: the small-radix-first plan (welch_accum_mid_kernel)
@@ -59,6 +60,7 @@ template <int N, int CTA_ = MidGeo<N>::CTA> WelchKernel make_welch_mid() {
     k.smem = (size_t)k.fpc * G::SM_ELEMS * sizeof(float2) + G::T1_BYTES + G::WIN_BYTES; k.p = 32; k.np = 3;
     k.radix[0] = G::R0; k.radix[1] = 32; k.radix[2] = 32; k.radix[3] = 1;
     k.mid = 1;
+    k.slots = 1;                 // the CTA adds up its segment slots itself
     return k;
 }
 
@@ -114,7 +116,7 @@ struct DcRowsShape { int mode, nt, nbuf, swz; };
 //   128 x 2                          1.325       0.784      0.581      0.507
 // (small tiles double-buffered: every CTA always has a tile in flight and the load / tap-loop phases of the resident
 // CTAs no longer line up; at D 32 two buffers cost too many CTAs).  SA_DC_ROWS_NT / SA_DC_ROWS_NBUF / SA_DC_ROWS_MODE override.
-static DcRowsShape dc_rows_shape(int down) {
+static DcRowsShape dc_rows_shape(int dk, int down) {
     static const char* me = getenv("SA_DC_ROWS_MODE");
     static const char* ne = getenv("SA_DC_ROWS_NT");
     static const char* be = getenv("SA_DC_ROWS_NBUF");
@@ -123,7 +125,8 @@ static DcRowsShape dc_rows_shape(int down) {
     if (sh.nt != 256) sh.nt = 128;
     if (sh.nbuf != 1) sh.nbuf = 2;
     if (sh.mode == 0) { sh.nt = 256; sh.nbuf = 1; sh.swz = 0; }
-    if (sh.nt == 256) sh.swz = 0;                          // swizzled rows exist in the 128-row shapes        // the table variant exists in the first shape only (ablation record)
+    if (dk != DK_CF32) { sh.mode = 1; sh.nt = 128; }       // the integer types exist in the 128-row shapes only
+    if (sh.nt == 256) sh.swz = 0;                          // swizzled rows exist in the 128-row shapes (256 x 2 swizzled: C3 1.268 ms against 1.231)        // the table variant exists in the first shape only (ablation record)
     return sh;
 }
 template <int DK, int D, int NT, int NBUF, bool SWZ = false> const void* dc_rows_fn(size_t* smem) {
@@ -153,8 +156,7 @@ template <int DK> const void* dc_rows_kernel_dk(int down, const DcRowsShape& sh,
         default: *smem = 0; return nullptr;
     }
 }
-const void* dc_rows_kernel(int dk, int down, DcRowsShape sh, size_t* smem) {
-    if (dk != DK_CF32) { sh.mode = 1; sh.nt = 128; }
+const void* dc_rows_kernel(int dk, int down, const DcRowsShape& sh, size_t* smem) {
     switch (dk) {
         case DK_CF32: return dc_rows_kernel_dk<DK_CF32>(down, sh, smem);
         case DK_CI16: return dc_rows_kernel_dk<DK_CI16>(down, sh, smem);
@@ -276,7 +278,7 @@ static int welch_launch(Engine* eng, const WelchLaunch& wl, const WelchSig* d_si
     bool contiguous = wl.d_out[0] != nullptr;
     for (uint32_t i = 1; i < n_sig && contiguous; i++) contiguous = wl.d_out[i] == wl.d_out[i - 1] + nfft;
     const size_t out_bytes = contiguous ? 0 : (((size_t)n_sig * nfft * sizeof(double) + 255) & ~(size_t)255);
-    const size_t part_bytes = wk ? (size_t)n_sig * wl.nsplit * wk->fpc * nfft * elem : 0;
+    const size_t part_bytes = wk ? (size_t)n_sig * wl.nsplit * wk->slots * nfft * elem : 0;
     const int slot = wsi ? 13 : 1;
     int rc = eng->ensure_scratch(slot, std::max<size_t>(sig_bytes + out_bytes + part_bytes, 256));
     if (rc) return rc;
@@ -320,7 +322,7 @@ static int welch_launch(Engine* eng, const WelchLaunch& wl, const WelchSig* d_si
         e = cudaLaunchKernel(wk->fn, dim3(wl.nsplit, n_sig), dim3(wk->cta), wargs, wk->smem, stream);
         if (e != cudaSuccess) return cuda_fail(e, "launch welch_accum_kernel");
         eng->launches++;
-        int n = (int)nfft, slots = wl.nsplit * wk->fpc;
+        int n = (int)nfft, slots = wl.nsplit * wk->slots;
         void* fargs[] = { &wa, &n, &slots };
         e = cudaLaunchKernel(wk->fin, dim3((n + 255) / 256, n_sig), dim3(256), fargs, 0, stream);
         if (e != cudaSuccess) return cuda_fail(e, "launch welch_finalize_kernel");
@@ -410,9 +412,9 @@ static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, i
         size_t rows_smem = 0;
         if (wide) {
             a.nb = 0;                       // marks the warp-per-output kernel
-        } else if (rows_ok && !a.fast && dc_rows_aligned(a.start_sample + a.in_off, rows_spc) && !(big_endian && dc_rows_shape(D).mode == 0) &&
-                   dc_rows_kernel(dk, D, dc_rows_shape(D), &rows_smem)) {
-            a.nb = dc_rows_shape(D).nt - 8;
+        } else if (rows_ok && !a.fast && dc_rows_aligned(a.start_sample + a.in_off, rows_spc) && !(big_endian && dc_rows_shape(dk, D).mode == 0) &&
+                   dc_rows_kernel(dk, D, dc_rows_shape(dk, D), &rows_smem)) {
+            a.nb = dc_rows_shape(dk, D).nt - 8;
             rowsk[i] = 1;
         } else if (pipe_ok && !a.fast && D <= 32) {
             // pipelined variant: the whole tile is one register batch (<= 17 x 256 staged samples)
@@ -604,7 +606,7 @@ static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, i
                 long long tiles = 0;
                 for (uint32_t i = g0; i < g1; i++) tiles = std::max<long long>(tiles, (sorted[i].m_out + first.nb - 1) / first.nb);
                 size_t smem = 0;
-                const DcRowsShape rows_shape = dc_rows_shape(first.down);
+                const DcRowsShape rows_shape = dc_rows_shape(dk, first.down);
                 const void* fn = dc_rows_kernel(dk, first.down, rows_shape, &smem);
                 std::vector<float> rt;
                 dc_rows_taps(taps.data() + first.taps_off, first.down, rt);

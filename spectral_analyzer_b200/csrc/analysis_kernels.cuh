@@ -862,9 +862,30 @@ welch_accum_mid_kernel(const WelchArgs a) {
             for (int q = 0; q < P; q++) acc[q] += __fmaf_rn(v[q].x, v[q].x, v[q].y * v[q].y);
         }
     }
-    float* part = reinterpret_cast<float*>(a.partial) + (((size_t)blockIdx.y * a.nsplit + blockIdx.x) * FPC + fl) * N;
+    // one partial spectrum per CTA: the segment slots of the CTA are added up here in a fixed order (through the exchange
+    // buffers, which are free now), so the finalize step reads nsplit rows per signal instead of nsplit x FPC
+    if constexpr (FPC > 1) {
+        __syncthreads();                                     // every slot has read back its last exchange
+        float* mine = reinterpret_cast<float*>(sm);
+        if (fl > 0) {
 #pragma unroll
-    for (int q = 0; q < P; q++) part[t + TPF * q] = acc[q];
+            for (int q = 0; q < P; q++) mine[t + TPF * q] = acc[q];
+        }
+        __syncthreads();
+        if (fl == 0) {
+#pragma unroll
+            for (int f = 1; f < FPC; f++) {
+                const float* other = reinterpret_cast<const float*>(reinterpret_cast<const float2*>(smem_raw) + (size_t)f * G::SM_ELEMS);
+#pragma unroll
+                for (int q = 0; q < P; q++) acc[q] += other[t + TPF * q];
+            }
+        }
+    }
+    if (fl == 0) {
+        float* part = reinterpret_cast<float*>(a.partial) + ((size_t)blockIdx.y * a.nsplit + blockIdx.x) * N;
+#pragma unroll
+        for (int q = 0; q < P; q++) part[t + TPF * q] = acc[q];
+    }
 }
 
 // sums the partial spectra in a fixed order (deterministic), scales, dB, fft-shift
