@@ -434,8 +434,11 @@ static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, i
     }
     // ---- batches: annotations in caller order, cut where the FP32 rows of a batch reach the batch size
     const bool want_psd = d_out_psd != nullptr;
+    // FP32 rows per batch.  Round 2 cut the rows at 128 MB (about the L2) and alternated the batches between two streams;
+    // with the row-per-thread downconverter at the HBM rate one batch for the whole call is faster (C3, 262 MB of rows:
+    // 1.198 ms as one batch, 1.215 ms as two, 1.25 ms at 64-112 MB), so the cut is 512 MB now.  SA_DC_BATCH_MB overrides.
     static const char* batch_env = getenv("SA_DC_BATCH_MB");
-    const uint64_t batch_mb = batch_env && atoi(batch_env) > 0 ? (uint64_t)atoi(batch_env) : 128;
+    const uint64_t batch_mb = batch_env && atoi(batch_env) > 0 ? (uint64_t)atoi(batch_env) : 512;
     const uint64_t scr_cap_elems = (batch_mb << 20) / sizeof(float2);
     std::vector<std::pair<uint32_t, uint32_t>> batches;
     {
@@ -455,7 +458,7 @@ static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, i
     const bool dual = want_psd && batches.size() > 1;
     int rc = SA_OK;
     if (want_psd) {
-        rc = eng->ensure_scratch(12, 2 * std::max<uint64_t>(scr_total, 1) * sizeof(float2));
+        rc = eng->ensure_scratch(12, (dual ? 2 : 1) * std::max<uint64_t>(scr_total, 1) * sizeof(float2));
         if (rc) return rc;
     }
     // annotation plan (device): batch by batch, inside a batch sorted by (kernel, fast, down) so that launches group

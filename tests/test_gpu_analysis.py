@@ -427,3 +427,38 @@ def test_row_kernel_odd_delay_shift(engine, ntaps, delay):
         engine.reset_analysis_config()
     assert got.shape == ref.shape
     assert np.abs(got - ref).max() <= DC_TOL * max(np.abs(ref).max(), 0.5)
+
+
+@pytest.mark.parametrize("sched", ["0", "1"])
+def test_several_batches_on_two_streams(sched):
+    """The batch cut (SA_DC_BATCH_MB, read once per process) is far above these sizes by default, so the multi-batch
+    path -- rows in two halves of one scratch buffer, batches alternating between two streams (SA_DC_SCHED=0) or
+    pipelined behind a high-priority Welch stream (=1) -- runs here in a child process with a 1 MB cut: PSD-only and
+    rows + PSD results must be identical to each other and agree with the oracle."""
+    import subprocess
+    import sys
+    code = r'''
+import numpy as np
+from oracle import c_oracle as co
+from spectral_analyzer_b200 import synth, Engine
+eng = Engine()
+raw = synth.recording(1 << 21, "cf32_le", seed=21)
+rng = np.random.default_rng(8)
+anns = [(int(rng.integers(0, (1 << 21) - 400000)), int(rng.integers(150000, 400000)), float(rng.uniform(-0.4, 0.4)), [4, 16, 5][i % 3], False)
+        for i in range(24)]
+iqs, psd_a = eng.downconvert_psd_batch(raw, "cf32_le", 1e6, anns, psd_nfft=4096, want_iq=True)
+none, psd_b = eng.downconvert_psd_batch(raw, "cf32_le", 1e6, anns, psd_nfft=4096, want_iq=False)
+assert none is None and np.array_equal(psd_a, psd_b)
+for i in (0, 7, 13, 23):
+    s, c, f, d, fast = anns[i]
+    ref = co.downconvert(raw, "cf32_le", s, c, f, d, fast)
+    assert np.abs(iqs[i] - ref).max() / np.abs(ref).max() < 1e-5
+    rp = co.psd_welch(ref, 1e6 / d, 4096)
+    strong = rp[1] > rp[1].max() - 40
+    assert np.abs(psd_b[i] - rp[1])[strong].max() < 5e-3
+print("ok")
+'''
+    env = dict(os.environ, SA_DC_BATCH_MB="1", SA_DC_SCHED=sched)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
