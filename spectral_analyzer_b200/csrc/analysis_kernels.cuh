@@ -792,6 +792,9 @@ welch_accum_kernel(const WelchArgs a) {
 // each of the R0 slices of a segment -- 128-bit loads from the downconverter's FP32 rows when they are 16-byte aligned.
 // CTA_: threads per CTA, a multiple of the TPF threads of one segment (the spectrogram kernel's geometry, or one segment
 // per CTA so that the CTAs are small enough to share an SM with the downconverter's, see run_batch_device).
+#ifndef SA_WELCH_L2_PREFETCH
+#define SA_WELCH_L2_PREFETCH 0      // L2 prefetch of a slot's next segment: measured no faster (C3 1.226 against 1.212 ms)
+#endif
 template <int N, int CTA_>
 __global__ void __launch_bounds__(CTA_, 512 / CTA_)
 welch_accum_mid_kernel(const WelchArgs a) {
@@ -831,6 +834,15 @@ welch_accum_mid_kernel(const WelchArgs a) {
         // barriers (one slot per CTA: the test is CTA-uniform), only the mean removal uses CTA-wide barriers.  29
         // segments over 4 CTAs x 2 slots: 15 instead of 16 CTA steps per signal.
         if (!valid && !a.detrend) continue;
+#if SA_WELCH_L2_PREFETCH
+        // the slot's NEXT segment (stride segments ahead: no sample in common with this one) is pulled into L2 while this
+        // one is transformed: N * 8 bytes = N / 16 lines of 128 bytes, N / 16 / TPF = 2 prefetches per thread
+        if (sg.f32 && seg + stride < sg.nseg) {
+            const char* nx = reinterpret_cast<const char*>(sg.f32 + (seg + stride) * a.hop);
+#pragma unroll
+            for (int i = 0; i < N / 16 / TPF; i++) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 128 * (t + TPF * i)));
+        }
+#endif
         float2 v[P];
         if (valid) {
             const long long s0 = seg * a.hop + (long long)S * t;
