@@ -107,13 +107,13 @@ def test_row_downconverter_stages_by_cp_async_and_reads_taps_from_the_constant_b
     assert len(rows) >= 16                                   # D in {4, 8, 16, 32} x (table variant + four shapes)
     for k, v in rows.items():
         assert v["REG"] <= 128 and v["STACK"] <= 64, (k, v)
-    name = "_ZN2sa23downconvert_rows_kernelILi0ELi16ELi1ELi128ELi2EEEvNS_6DcArgsENS_10DcRowsTapsIXT0_EEE"     # C3: D 16, 128 rows, 2 buffers
-    assert name in rows and rows[name]["STACK"] == 0, sorted(rows)
+    name = "_ZN2sa23downconvert_rows_kernelILi0ELi16ELi1ELi128ELi2ELb1EEEvNS_6DcArgsENS_10DcRowsTapsIXT0_EEE"     # C3: cf32, D 16, 128 rows, 2 buffers, swizzled
+    assert name in rows and rows[name]["STACK"] == 0 and rows[name]["REG"] <= 80, sorted(rows)      # 6 CTAs of 128 threads per SM
     s = sass(name)
     assert count(s, r"\bLDGSTS\.E\.BYPASS\.128") >= 8          # 8 chunks per thread and tile
     assert count(s, r"\bFFMA R\d+, R\d+(\.reuse)?, UR\d+, R\d+") >= 1800                # ~16 taps x 16 samples x (2 parities x 2 edge variants x 2 byte orders); a few taps ride in vector registers
     assert count(s, r"\bLDS\.128") == 8 * 8                   # the raw row only: 8 chunks x 8 variants of the tap loop (parity, edge, byte order)
-    table = sass("_ZN2sa23downconvert_rows_kernelILi0ELi16ELi0ELi256ELi1EEEvNS_6DcArgsENS_10DcRowsTapsIXT0_EEE")
+    table = sass("_ZN2sa23downconvert_rows_kernelILi0ELi16ELi0ELi256ELi1ELb0EEEvNS_6DcArgsENS_10DcRowsTapsIXT0_EEE")
     assert count(table, r"\bLDS\.128") >= 2 * (8 + 3 * 16)     # the ablation variant reads taps and NCO phasors as tables
 
 
