@@ -235,7 +235,11 @@ SA_API int32_t sa_downconvert_psd_batch(sa_engine* engine, const void* iq, uint6
                                         uint32_t psd_nfft, uint64_t psd_hop, int32_t psd_window,
                                         double* out_iq, const uint64_t* iq_offsets,
                                         double* out_psd_db);
-/* device-resident variant used for roofline timing: d_iq device capture, outputs device. */
+/* device-resident variant used for roofline timing: d_iq device capture, outputs device.
+ * (Fast path: decimation 4 / 8 / 16 / 32 with a 16-byte aligned d_iq and (start_sample + delay shift) congruent to 0 or -1
+ * modulo the samples per 16 bytes -- every start for cf32 -- takes the row-per-thread kernel; everything else the staged
+ * kernels.  The host variant above packs each span on a 16-byte boundary itself.  Results do not depend on the path
+ * beyond the FP32 tolerance.) */
 SA_API int32_t sa_downconvert_psd_batch_device(sa_engine* engine, const void* d_iq, uint64_t iq_bytes,
                                                int32_t dtype, int32_t big_endian, double sample_rate,
                                                const sa_annotation* anns, uint32_t n_ann,
