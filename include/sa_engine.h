@@ -236,7 +236,7 @@ SA_API int32_t sa_downconvert_psd_batch(sa_engine* engine, const void* iq, uint6
                                         double* out_iq, const uint64_t* iq_offsets,
                                         double* out_psd_db);
 /* device-resident variant used for roofline timing: d_iq device capture, outputs device.
- * (Fast path: decimation 4 / 8 / 16 / 32 with a 16-byte aligned d_iq and (start_sample + delay shift) congruent to 0 or -1
+ * (Fast path: an even decimation 4 .. 32 whose rows are whole 16-byte chunks, with a 16-byte aligned d_iq and (start_sample + delay shift) congruent to 0 or -1
  * modulo the samples per 16 bytes -- every start for cf32 -- takes the row-per-thread kernel; everything else the staged
  * kernels.  The host variant above packs each span on a 16-byte boundary itself.  Results do not depend on the path
  * beyond the FP32 tolerance.) */

@@ -126,6 +126,10 @@ static DcRowsShape dc_rows_shape(int dk, int down) {
     if (sh.nbuf != 1) sh.nbuf = 2;
     if (sh.mode == 0) { sh.nt = 256; sh.nbuf = 1; sh.swz = 0; }
     if (dk != DK_CF32) { sh.mode = 1; sh.nt = 128; }       // the integer types exist in the 128-row shapes only
+    {
+        const int cpr = down / (dk == DK_CF32 ? 2 : (dk == DK_CI16 ? 4 : 8));
+        if (cpr & (cpr - 1)) { sh.mode = 1; sh.nt = 128; sh.swz = 0; }     // 3, 5, 6, 7 ... chunks per row: 128-row shapes, no swizzle
+    }
     if (sh.nt == 256) sh.swz = 0;                          // swizzled rows exist in the 128-row shapes (256 x 2 swizzled: C3 1.268 ms against 1.231)        // the table variant exists in the first shape only (ablation record)
     return sh;
 }
@@ -147,12 +151,29 @@ template <int DK, int D> const void* dc_rows_kernel_of(const DcRowsShape& sh, si
         return sh.swz ? dc_rows_fn<DK, D, 128, 2, true>(smem) : dc_rows_fn<DK, D, 128, 2>(smem);
     }
 }
+// decimations whose rows are a power-of-two number of chunks come in every shape; the other even ones (cf32: 6, 10, 12 ... 30;
+// ci16: 12, 20, 24, 28; cu8 / ci8: 24) in the 128-row shapes with packed (odd chunk count) or padded rows
+template <int DK, int D> const void* dc_rows_kernel_np2(const DcRowsShape& sh, size_t* smem) {
+    if constexpr (D % DcRowsSpc<DK>::value != 0) { *smem = 0; return nullptr; }
+    else return sh.nbuf == 1 ? dc_rows_fn<DK, D, 128, 1>(smem) : dc_rows_fn<DK, D, 128, 2>(smem);
+}
 template <int DK> const void* dc_rows_kernel_dk(int down, const DcRowsShape& sh, size_t* smem) {
     switch (down) {
         case 4:  return dc_rows_kernel_of<DK, 4>(sh, smem);
         case 8:  return dc_rows_kernel_of<DK, 8>(sh, smem);
         case 16: return dc_rows_kernel_of<DK, 16>(sh, smem);
         case 32: return dc_rows_kernel_of<DK, 32>(sh, smem);
+        case 6:  return dc_rows_kernel_np2<DK, 6>(sh, smem);
+        case 10: return dc_rows_kernel_np2<DK, 10>(sh, smem);
+        case 12: return dc_rows_kernel_np2<DK, 12>(sh, smem);
+        case 14: return dc_rows_kernel_np2<DK, 14>(sh, smem);
+        case 18: return dc_rows_kernel_np2<DK, 18>(sh, smem);
+        case 20: return dc_rows_kernel_np2<DK, 20>(sh, smem);
+        case 22: return dc_rows_kernel_np2<DK, 22>(sh, smem);
+        case 24: return dc_rows_kernel_np2<DK, 24>(sh, smem);
+        case 26: return dc_rows_kernel_np2<DK, 26>(sh, smem);
+        case 28: return dc_rows_kernel_np2<DK, 28>(sh, smem);
+        case 30: return dc_rows_kernel_np2<DK, 30>(sh, smem);
         default: *smem = 0; return nullptr;
     }
 }

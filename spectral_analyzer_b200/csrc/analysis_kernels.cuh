@@ -431,8 +431,9 @@ template <int CPR> __host__ __device__ constexpr int dc_rows_swz(int row) {
     return CPR >= 8 ? (row & 7) : (CPR == 4 ? ((row >> 1) & 3) : (CPR == 2 ? ((row >> 2) & 1) : 0));
 }
 template <int D, int NT = 256, int NBUF = 1, int SPC = 2, bool SWZ = false> struct DcRowsGeo {
-    static_assert(D >= 4 && D <= 32 && (D & (D - 1)) == 0, "row kernel: power-of-two decimation, 4..32");
-    static_assert(D % SPC == 0 && NT % (D / SPC) == 0 && (NBUF == 1 || NBUF == 2), "row kernel geometry");
+    static_assert(D >= 2 && D <= 32, "row kernel: decimation 2..32");
+    static_assert(D % SPC == 0 && (NBUF == 1 || NBUF == 2), "row kernel geometry: rows are whole 16-byte chunks");
+    static_assert(!SWZ || ((D / SPC) & (D / SPC - 1)) == 0, "swizzled rows: a power-of-two number of chunks per row");
     static constexpr int CPR = D / SPC;                  // 16-byte chunks per row
     static constexpr int RS = SWZ ? CPR : (CPR | 1);     // row stride in chunks (odd unless swizzled)
     static constexpr int RAW_BYTES = NT * RS * 16;       // one raw tile: NT rows
@@ -595,7 +596,11 @@ downconvert_rows_kernel(const DcArgs a, const __grid_constant__ DcRowsTaps<D> tp
     const int lone_row = sg ? 0 : 8;                          // row (relative to j) that holds the lone sample
 
     // this thread's chunks of a tile: chunk g = t + NT k, row g / CPR, position g % CPR
-    const uint32_t dst_t = raw_s + 16u * (unsigned)((t / G::CPR) * G::RS + ((t % G::CPR) ^ (SWZ ? dc_rows_swz<G::CPR>(t / G::CPR) : 0)));
+    // (NT a multiple of CPR: the chunks of a thread are kDstStep apart; otherwise -- 3, 5, 6, 7 ... chunks per row -- the row and
+    // position of every chunk are computed, divisions by a compile-time constant)
+    constexpr bool kRegular = NT % G::CPR == 0;
+    auto chunk_dst = [&](int g) { const int row = g / G::CPR, c = g % G::CPR; return 16u * (unsigned)(row * G::RS + (c ^ (SWZ ? dc_rows_swz<G::CPR>(row) : 0))); };
+    const uint32_t dst_t = raw_s + chunk_dst(t);
     const uint32_t swz16 = SWZ ? 16u * (unsigned)dc_rows_swz<G::CPR>(t) : 0u;
     constexpr uint32_t kDstStep = (NT / G::CPR) * G::RS * 16;
     auto tile_n0 = [&](long long tl) { return (tl * NB - 8 - sg) * D + an.in_off + sg; };       // sample of row 0 (annotation-relative)
@@ -604,13 +609,15 @@ downconvert_rows_kernel(const DcArgs a, const __grid_constant__ DcRowsTaps<D> tp
         const char* src = reinterpret_cast<const char*>(a.lp.base) + BPS * s0 + 16 * (long long)t;
         if (s0 >= 0 && s0 + (long long)NT * D <= a.n_samples) {
 #pragma unroll
-            for (int k = 0; k < G::CPR; k++) cp_async16(dst0 + kDstStep * k, src + (size_t)NT * 16 * k);
+            for (int k = 0; k < G::CPR; k++)
+                cp_async16(kRegular ? dst0 + kDstStep * k : dst0 - chunk_dst(t) + chunk_dst(t + NT * k), src + (size_t)NT * 16 * k);
         } else {
 #pragma unroll
             for (int k = 0; k < G::CPR; k++) {
                 const long long s = s0 + SPC * ((long long)t + NT * k);
                 const int bytes = s < 0 ? 0 : (int)max(0LL, min((long long)SPC, a.n_samples - s)) * BPS;
-                cp_async16_partial(dst0 + kDstStep * k, bytes ? (const void*)(src + (size_t)NT * 16 * k) : a.lp.base, bytes);
+                cp_async16_partial(kRegular ? dst0 + kDstStep * k : dst0 - chunk_dst(t) + chunk_dst(t + NT * k),
+                                   bytes ? (const void*)(src + (size_t)NT * 16 * k) : a.lp.base, bytes);
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");

@@ -333,7 +333,7 @@ def test_batch_of_more_annotations_than_one_launch_holds(engine):
 
 
 @pytest.mark.parametrize("dt", ["cf32_le", "cf32_be", "ci16_le", "ci16_be", "cu8", "ci8"])
-@pytest.mark.parametrize("down", [8, 16, 32])
+@pytest.mark.parametrize("down", [8, 16, 32, 6, 10, 12, 24, 30])
 @pytest.mark.parametrize("start,delay", [(0, "causal"), (1, "causal"), (122, "same"), (123, "same"), (4096, "valid"), (4097, "valid")])
 def test_row_kernel_alignment_edges_and_tiles(engine, dt, down, start, delay):
     """Power-of-two decimation takes the row-per-thread kernel (16-byte cp.async of raw rows): both parities of
@@ -353,8 +353,11 @@ def test_row_kernel_alignment_edges_and_tiles(engine, dt, down, start, delay):
             engine.reset_analysis_config()
         assert got.shape == ref.shape
         assert np.abs(got - ref).max() <= DC_TOL * max(np.abs(ref).max(), 0.5), (tail, name)
+        spc = 2 if dt.startswith("cf32") else 4 if dt.startswith("ci16") else 8       # samples per 16-byte chunk
         if os.environ.get("SA_DC_ROWS", "1") != "0":
-            assert "downconvert_rows_kernel" in name
+            # rows of whole chunks take the row kernel (the host call packs spans on chunk boundaries and the delay shifts
+            # of the built-in taps, 0 / 4 down / 8 down, are multiples of every chunk size here); the rest the staged one
+            assert ("downconvert_rows_kernel" in name) == (down % spc == 0), (name, down, spc)
 
 
 @pytest.mark.parametrize("count", [1, 15, 16, 17, 100, 248 * 16, 248 * 16 + 1, 5000])
@@ -389,7 +392,8 @@ def test_row_kernel_device_path_odd_starts_and_recording_ends(engine, dt, code):
     d_raw = torch.from_numpy(np.frombuffer(raw, np.uint8).copy()).cuda()
     specs = [(0, 100000, 16), (1, 100001, 16), (12345, 77777, 16), (200000, 100001, 16), (199999, 100002, 8),
              (3, 299998, 32), (150001, 40000, 16), (150002, 40000, 16), (150003, 40000, 16), (150004, 40000, 16),
-             (150005, 40000, 8), (150006, 40000, 8), (150007, 40000, 32), (150008, 40000, 32)]
+             (150005, 40000, 8), (150006, 40000, 8), (150007, 40000, 32), (150008, 40000, 32),
+             (5, 60000, 10), (6, 60001, 12), (7, 60002, 24), (8, 60003, 30), (11, 60000, 6), (12, 60000, 20)]
     anns = (_capi.Annotation * len(specs))()
     offs = (C.c_uint64 * len(specs))()
     total = 0
