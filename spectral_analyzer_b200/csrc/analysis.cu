@@ -185,6 +185,14 @@ const void* dc_rows_kernel(int dk, int down, const DcRowsShape& sh, size_t* smem
         default: *smem = 0; return nullptr;
     }
 }
+const void* dc_rows_fast_kernel(int dk) {
+    switch (dk) {
+        case DK_CF32: return (const void*)&downconvert_rows_fast_kernel<DK_CF32>;
+        case DK_CI16: return (const void*)&downconvert_rows_fast_kernel<DK_CI16>;
+        case DK_C8:   return (const void*)&downconvert_rows_fast_kernel<DK_C8>;
+        default: return nullptr;
+    }
+}
 static bool dc_rows_aligned(long long first, long long spc) { const long long r = first & (spc - 1); return r == 0 || r == spc - 1; }
 // kernel-parameter tap block of the row kernel (the layout of DcRowsTaps<D>): g[sg][i][p] = h[(p+1)D - i - sg], h[0], h[8D]
 static void dc_rows_taps(const float* h, int D, std::vector<float>& out) {
@@ -433,6 +441,10 @@ static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, i
         size_t rows_smem = 0;
         if (wide) {
             a.nb = 0;                       // marks the warp-per-output kernel
+        } else if (rows_ok && a.fast && D % rows_spc == 0 && (a.start_sample & (rows_spc - 1)) == 0 &&
+                   dc_fast_smem_bytes((int)(D / rows_spc)) <= kDcFastSmemMax) {
+            a.nb = kDcFastRows;              // box-car mode of the row-per-thread kernel: one output per row, no halo
+            rowsk[i] = 1;
         } else if (rows_ok && !a.fast && dc_rows_aligned(a.start_sample + a.in_off, rows_spc) && !(big_endian && dc_rows_shape(dk, D).mode == 0) &&
                    dc_rows_kernel(dk, D, dc_rows_shape(dk, D), &rows_smem)) {
             a.nb = dc_rows_shape(dk, D).nt - 8;
@@ -625,6 +637,26 @@ static int run_batch_device(Engine* eng, const void* d_iq, uint64_t n_samples, i
                     if (e != cudaSuccess) return cuda_fail(e, "launch downconvert_wide_kernel");
                     eng->launches++;
                     dc_name = "downconvert_wide_kernel";
+                }
+            } else if (rowsk[order[g0]] && first.fast) {     // row-per-thread kernel, box-car mode
+                long long tiles = 0;
+                for (uint32_t i = g0; i < g1; i++) tiles = std::max<long long>(tiles, (sorted[i].m_out + first.nb - 1) / first.nb);
+                const size_t smem = (size_t)dc_fast_smem_bytes(first.down / (int)rows_spc);
+                const void* fn = dc_rows_fast_kernel(dk);
+                const long long group_tiles = tiles * (long long)(g1 - g0);
+                da.tiles_per_cta = group_tiles >= 16LL * 16 * eng->num_sms ? 16 : 4;
+                const long long ctas = (tiles + da.tiles_per_cta - 1) / da.tiles_per_cta;
+                if (ctas > 0) {
+                    size_t& have = eng->dc_smem_set[fn];
+                    if (have < smem) {
+                        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                        if (e != cudaSuccess) return cuda_fail(e, "downconvert smem attribute");
+                        have = smem;
+                    }
+                    e = cudaLaunchKernel(fn, dim3((unsigned)ctas, g1 - g0), dim3(kDcFastRows), args, smem, s);
+                    if (e != cudaSuccess) return cuda_fail(e, "launch downconvert_rows_fast_kernel");
+                    eng->launches++;
+                    dc_name = "downconvert_rows_fast_kernel";
                 }
             } else if (rowsk[order[g0]]) {     // row-per-thread kernel
                 long long tiles = 0;

@@ -687,6 +687,104 @@ downconvert_rows_kernel(const DcArgs a, const __grid_constant__ DcRowsTaps<D> tp
     }
 }
 
+// Box-car ("fast") mode of the same idea: z[m] = (1/D) sum_{k<D} y[mD + k] is the mean of ONE row, so there are no partial
+// sums, no halo and no taps -- thread b mixes and adds its own row and writes output m0 + b.  The decimation factor is a
+// run-time value here (any multiple of the samples per 16-byte chunk whose double-buffered 128-row tile fits the shared
+// memory budget); rows are padded to an odd number of chunks.  Needs start_sample on a chunk boundary (in_off is 0).
+constexpr int kDcFastRows = 128;
+__host__ __device__ constexpr int dc_fast_smem_bytes(int cpr) { return 128 + 2 * kDcFastRows * (cpr | 1) * 16; }
+constexpr int kDcFastSmemMax = 72 * 1024;          // three CTAs per SM
+
+template <int DK, bool SWAP, bool INTERIOR>
+__device__ __forceinline__ float2 dc_rows_boxcar(const LoadParams& lp, const uint32_t row_s, const int cpr, const long long n_row,
+                                                 const long long count, float2 P, const float2 W) {
+    constexpr int SPC = DcRowsSpc<DK>::value;
+    float sr = 0.f, si = 0.f;
+    for (int c = 0; c < cpr; c++) {
+        uint4 raw;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w) : "r"(row_s + 16u * (unsigned)c) : "memory");
+        float2 x[SPC];
+        dc_rows_decode<DK, SWAP>(lp, raw, x);
+#pragma unroll
+        for (int hh = 0; hh < SPC; hh++) {
+            if constexpr (!INTERIOR) {
+                const long long n = n_row + SPC * c + hh;
+                if (n < 0 || n >= count) x[hh] = make_float2(0.f, 0.f);
+            }
+            sr += __fmaf_rn(x[hh].x, P.x, -x[hh].y * P.y);
+            si += __fmaf_rn(x[hh].x, P.y, x[hh].y * P.x);
+            P = make_float2(__fmaf_rn(P.x, W.x, -P.y * W.y), __fmaf_rn(P.x, W.y, P.y * W.x));
+        }
+    }
+    return make_float2(sr, si);
+}
+
+template <int DK>
+__global__ void __launch_bounds__(kDcFastRows, 3)
+downconvert_rows_fast_kernel(const DcArgs a) {
+    constexpr int SPC = DcRowsSpc<DK>::value, BPS = 16 / SPC, NT = kDcFastRows;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const DcAnn an = a.anns[a.ann_base + blockIdx.y];
+    const long long n_tiles = (an.m_out + NT - 1) / NT;
+    long long tile = (long long)blockIdx.x * a.tiles_per_cta;
+    const long long tile_end = min(n_tiles, tile + a.tiles_per_cta);
+    if (tile >= tile_end) return;
+    const int t = threadIdx.x, D = an.down, cpr = D / SPC, rs = cpr | 1;
+    const uint32_t raw_s = ((uint32_t)__cvta_generic_to_shared(smem_raw) + 127u) & ~127u;
+    const uint32_t raw_bytes = (uint32_t)(NT * rs * 16);
+    const unsigned magic = cpr > 1 ? (unsigned)(0xFFFFFFFFu / (unsigned)cpr + 1u) : 0u;       // g / cpr = umulhi(g, magic), g < NT cpr
+    const float2 W = nco_phasor_acc(an.phase_step);
+    const float inv = 1.0f / (float)D;
+    auto issue = [&](long long tl, uint32_t dst_base) {
+        const long long s0 = an.start_sample + tl * NT * D;                                   // a chunk boundary (host-checked)
+        const char* src = reinterpret_cast<const char*>(a.lp.base) + BPS * s0 + 16 * (long long)t;
+        const bool inside = s0 >= 0 && s0 + (long long)NT * D <= a.n_samples;
+        for (int k = 0; k < cpr; k++) {
+            const int g = t + NT * k;
+            const int row = cpr > 1 ? (int)__umulhi((unsigned)g, magic) : g;
+            const uint32_t dst = dst_base + 16u * (unsigned)(row * rs + (g - row * cpr));
+            if (inside) {
+                cp_async16(dst, src + (size_t)NT * 16 * k);
+            } else {
+                const long long s = s0 + (long long)SPC * g;
+                const int bytes = s < 0 ? 0 : (int)max(0LL, min((long long)SPC, a.n_samples - s)) * BPS;
+                cp_async16_partial(dst, bytes ? (const void*)(src + (size_t)NT * 16 * k) : a.lp.base, bytes);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue(tile, raw_s);
+    uint32_t buf = 0;
+    for (; tile < tile_end; tile++) {
+        const long long m0 = tile * NT;
+        const int nbt = (int)min((long long)NT, an.m_out - m0);
+        const uint32_t row_s = raw_s + buf + (unsigned)(t * rs * 16);
+        const long long n_row = (m0 + t) * D;
+        const float2 P = nco_phasor(an.phase_step * (unsigned long long)n_row);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                    // the tile has landed; the other buffer has been read by every thread
+        buf ^= raw_bytes;
+        if (tile + 1 < tile_end) issue(tile + 1, raw_s + buf);
+        const bool interior = (m0 + NT) * D <= an.count;
+        float2 z;
+        if constexpr (DK == DK_C8) {
+            z = interior ? dc_rows_boxcar<DK, false, true>(a.lp, row_s, cpr, n_row, an.count, P, W)
+                         : dc_rows_boxcar<DK, false, false>(a.lp, row_s, cpr, n_row, an.count, P, W);
+        } else if (a.lp.swap) {
+            z = interior ? dc_rows_boxcar<DK, true, true>(a.lp, row_s, cpr, n_row, an.count, P, W)
+                         : dc_rows_boxcar<DK, true, false>(a.lp, row_s, cpr, n_row, an.count, P, W);
+        } else {
+            z = interior ? dc_rows_boxcar<DK, false, true>(a.lp, row_s, cpr, n_row, an.count, P, W)
+                         : dc_rows_boxcar<DK, false, false>(a.lp, row_s, cpr, n_row, an.count, P, W);
+        }
+        if (t < nbt) {
+            z.x *= inv; z.y *= inv;
+            if (a.out) { double* o = a.out + an.out_off + m0 + t; o[0] = (double)z.x; o[an.m_out] = (double)z.y; }
+            if (a.scratch) a.scratch[an.scr_off + m0 + t] = z;
+        }
+    }
+}
+
 // ---------------- Welch ----------------
 struct WelchSig {
     const double* re;      // planar FP64 input (the downconverter's output rows), or

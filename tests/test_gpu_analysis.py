@@ -394,11 +394,13 @@ def test_row_kernel_device_path_odd_starts_and_recording_ends(engine, dt, code):
              (3, 299998, 32), (150001, 40000, 16), (150002, 40000, 16), (150003, 40000, 16), (150004, 40000, 16),
              (150005, 40000, 8), (150006, 40000, 8), (150007, 40000, 32), (150008, 40000, 32),
              (5, 60000, 10), (6, 60001, 12), (7, 60002, 24), (8, 60003, 30), (11, 60000, 6), (12, 60000, 20)]
+    fast_from = len(specs)                                   # box-car mode: chunk-aligned starts take the row kernel, the others the staged one
+    specs += [(16, 50000, 16), (17, 50000, 16), (24, 50001, 6), (3, 50001, 8), (299000, 1001, 4)]
     anns = (_capi.Annotation * len(specs))()
     offs = (C.c_uint64 * len(specs))()
     total = 0
     for i, (s, c, d) in enumerate(specs):
-        anns[i] = _capi.Annotation(s, c, 0.05 + 0.031 * i, d, 0)
+        anns[i] = _capi.Annotation(s, c, 0.05 + 0.031 * i, d, 1 if i >= fast_from else 0)
         offs[i] = total
         total += 2 * (c // d)
     d_iq = torch.empty(total, dtype=torch.float64, device="cuda")
@@ -408,7 +410,7 @@ def test_row_kernel_device_path_odd_starts_and_recording_ends(engine, dt, code):
     torch.cuda.synchronize()
     got_all = d_iq.cpu().numpy()
     for i, (s, c, d) in enumerate(specs):
-        ref = co.downconvert(raw, dt, s, c, 0.05 + 0.031 * i, d, False)
+        ref = co.downconvert(raw, dt, s, c, 0.05 + 0.031 * i, d, i >= fast_from)
         got = got_all[offs[i]:offs[i] + 2 * (c // d)].reshape(2, c // d)
         assert rel_err(got, ref) < DC_TOL, (i, s, c, d)
 
@@ -466,3 +468,30 @@ print("ok")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("dt", ["cf32_le", "cf32_be", "ci16_le", "cu8", "ci8"])
+@pytest.mark.parametrize("down", [2, 4, 6, 8, 16, 30, 40, 44, 64, 7])
+def test_row_kernel_boxcar_mode(engine, dt, down):
+    """fast = moving average then decimate: the mean of one row.  Decimation factors that fill whole 16-byte chunks (and a
+    tile that fits shared memory) take downconvert_rows_fast_kernel, the others the staged kernel; several tiles, a count
+    that is not a multiple of down with the ceil rule (the last row is cut by the annotation end), the annotation at the
+    start and at the end of the recording."""
+    count = 128 * down * 5 + 3 * down + 1
+    for start, tail in ((0, 0), (64, 5), (24, 0)):
+        raw = synth.recording(start + count + tail, dt, seed=50 + tail)
+        for length in ("floor", "ceil"):
+            cfg = co.analysis_cfg(length=length)
+            ref = co.downconvert_ex(raw, dt, start, count, 0.2317, down, True, cfg)
+            engine.set_analysis_config(length=length)
+            try:
+                got = engine.downconvert(raw, dt, start, count, 0.2317, down, True)
+                name = engine.last_kernel
+            finally:
+                engine.reset_analysis_config()
+            assert got.shape == ref.shape
+            assert np.abs(got - ref).max() <= DC_TOL * max(np.abs(ref).max(), 0.5), (start, length, name)
+            spc = 2 if dt.startswith("cf32") else 4 if dt.startswith("ci16") else 8
+            fits = 128 + 2 * 128 * ((down // spc) | 1) * 16 <= 72 * 1024
+            if os.environ.get("SA_DC_ROWS", "1") != "0":
+                assert (name == "downconvert_rows_fast_kernel") == (down % spc == 0 and fits), (name, down)

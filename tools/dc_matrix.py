@@ -21,6 +21,9 @@ def main():
     ap.add_argument("--count", type=int, default=1 << 20)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--downs", default="2,4,10,16,32")
+    ap.add_argument("--fast", action="store_true", help="box-car mode (moving average, then decimate)")
+    ap.add_argument("--align", type=int, default=1, help="annotation starts are multiples of this many samples (8: every "
+                    "input type starts on a 16-byte boundary, as the spans packed by the host call do)")
     args = ap.parse_args()
     eng = sa.Engine(0)
     dev = torch.device("cuda", 0)
@@ -38,7 +41,8 @@ def main():
             anns = (_capi.Annotation * n_ann)()
             offs = (C.c_uint64 * n_ann)()
             for i in range(n_ann):
-                anns[i] = _capi.Annotation(int(rng.integers(0, n_samples - count)), count, float(rng.uniform(-0.4, 0.4)), down, 0)
+                start = int(rng.integers(0, n_samples - count)) // args.align * args.align
+                anns[i] = _capi.Annotation(start, count, float(rng.uniform(-0.4, 0.4)), down, 1 if args.fast else 0)
                 offs[i] = i * 2 * m
             out_iq = torch.empty(n_ann * 2 * m, device=dev, dtype=torch.float64)
             out_psd = torch.empty(n_ann * 8192, device=dev, dtype=torch.float64)
@@ -47,7 +51,7 @@ def main():
                 _capi.check(L.sa_downconvert_psd_batch_device(eng.handle, raw.data_ptr(), n_samples * bpp, code, 0, 1.0e6, anns,
                                                               n_ann, 8192, 2048, 1, out_iq.data_ptr(), offs, out_psd.data_ptr(), stream))
             ms = timed(run, args.steps)
-            print(json.dumps({"dtype": name, "down": down, "ms": round(ms, 4), "Gsamples_per_s": round(n_ann * count / ms / 1e6, 1),
+            print(json.dumps({"dtype": name, "down": down, "fast": bool(args.fast), "align": args.align, "ms": round(ms, 4), "Gsamples_per_s": round(n_ann * count / ms / 1e6, 1),
                               "kernel": eng.last_kernel}))
             del out_iq, out_psd
     eng.close()
