@@ -113,6 +113,8 @@ def test_row_downconverter_stages_by_cp_async_and_reads_taps_from_the_constant_b
     assert count(s, r"\bLDGSTS\.E\.BYPASS\.128") >= 8          # 8 chunks per thread and tile
     assert count(s, r"\bFFMA R\d+, R\d+(\.reuse)?, UR\d+, R\d+") >= 1800                # ~16 taps x 16 samples x (2 parities x 2 edge variants x 2 byte orders); a few taps ride in vector registers
     assert count(s, r"\bLDS\.128") == 8 * 8                   # the raw row only: 8 chunks x 8 variants of the tap loop (parity, edge, byte order)
+    fast = {k: v for k, v in res.items() if "downconvert_rows_fast_kernel" in k}      # box-car mode: 3 CTAs of 128 threads, no spills
+    assert len(fast) == 3 and all(v["REG"] <= 128 and v["STACK"] == 0 for v in fast.values()), fast
     table = sass("_ZN2sa23downconvert_rows_kernelILi0ELi16ELi0ELi256ELi1ELb0EEEvNS_6DcArgsENS_10DcRowsTapsIXT0_EEE")
     assert count(table, r"\bLDS\.128") >= 2 * (8 + 3 * 16)     # the ablation variant reads taps and NCO phasors as tables
 
