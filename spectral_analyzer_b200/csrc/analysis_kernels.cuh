@@ -400,22 +400,25 @@ downconvert_wide_kernel(const DcArgs a) {
     }
 }
 
-// ---------------- row-per-thread downconverter (cf32, even power-of-two decimation) ----------------
+// ---------------- row-per-thread downconverter (even decimation 4..32, rows on the 16-byte grid) ----------------
 // The staged kernel above spends two thirds of its instructions moving samples (register batch -> decode -> NCO
-// recurrence -> padded shared-memory store -> LDS.64 per tap row).  Here the RAW tile goes global -> shared memory
-// with 16-byte cp.async (no registers, no per-sample address arithmetic: a thread's D/2 chunks differ by immediates),
-// and thread b owns ROW b = D consecutive raw samples, which it reads back as 128-bit loads (rows are D/2 | 1 chunks
-// apart: an odd stride, so the 8 lanes of a quarter-warp hit 8 different 16-byte bank groups).  The NCO is split
-//     e^{-i th (n_b + i)} = P_b T[i],   T[i] = e^{-i th i} (shared-memory table, D entries, exact 64-bit phase),
-// so there is no recurrence: the row is mixed with the lane-uniform T[i], filtered into the 8 polyphase partial sums
-//     S_p[b] = sum_i h[(p+1)D - i - sg] x[b][i] T[i]      (taps G[i][p], lane-uniform 128-bit broadcasts)
-// and the row's own phasor P_b (one sincos per row from the exact phase) multiplies the 8 sums once.
-// cp.async needs 16-byte aligned sources, i.e. rows that start on an even sample of the recording.  sg = parity of
-// (start_sample + in_off) picks one of two equivalent decompositions of z[m] = sum_k h[k] y[q - k], q = mD + in_off:
+// recurrence -> padded shared-memory store -> LDS.64 per tap row).  Here the RAW tile (NT rows of D samples) goes
+// global -> shared memory with 16-byte cp.async (no registers in flight, no per-sample address arithmetic: a thread's
+// chunks differ by immediates), and thread b owns ROW b = D consecutive raw samples, which it reads back as 128-bit loads
+// (rows an odd number of chunks apart, or packed and XOR-swizzled: the 8 lanes of a quarter-warp hit 8 different 16-byte
+// bank groups).  Row b is mixed with the NCO and filtered into the 8 polyphase partial sums
+//     S_p[b] = sum_i h[(p+1)D - i - sg] y[b][i],      z[m] = sum_p S_p[row(m) - p] + lone tap,
+// which go through shared memory once (DESIGN.md K5 has the history of the two variants below and their ncu records):
+//   MODE 0 (ablation record): NCO split e^{-i th (n_b + i)} = P_b T[i] with T[] and the taps G[i][p] as shared-memory tables
+//           read by lane-uniform LDS.128, FFMA2 arithmetic, P_b applied to the 8 sums -- half the staged kernel's
+//           instructions and the same time: bound by the shared-memory pipe;
+//   MODE 1 (shipped): taps as immediates of the kernel-parameter constant bank, NCO as a per-row recurrence.
+// cp.async needs 16-byte aligned sources, i.e. rows that start on a chunk boundary of the recording.  sg (the residue of
+// start_sample + in_off) picks one of two equivalent decompositions of z[m] = sum_k h[k] y[q - k], q = mD + in_off:
 //   sg = 0: rows START at q - (p+1)D: taps k = 1..8D from rows j..j+7, lone tap h[0] on the first sample of row j+8
 //   sg = 1: rows END   at q - pD    : taps k = 0..8D-1 from rows j+1..j+8, lone tap h[8D] on the last sample of row j
-// (j = output index within the tile, 248 outputs per 256 rows).  Samples outside the annotation are zeroed in the
-// tiles that touch its ends; chunks outside the recording are not read (cp.async src-size 0 / 8).
+// (j = output index within the tile, NT - 8 outputs per NT rows).  Samples outside the annotation are zeroed in the
+// tiles that touch its ends; chunks outside the recording are not read (cp.async src-size).
 // Input types: cf32 (2 samples per 16-byte chunk), ci16 (4), cu8 / ci8 (8), either byte order; the integer types are decoded
 // in the tap loop (the same exact one-FMA decodes as everywhere else).  A row must be whole chunks (D a multiple of the
 // samples per chunk) and start on a chunk boundary of the recording: (start_sample + in_off) mod SPC must be 0 (sg = 0)
