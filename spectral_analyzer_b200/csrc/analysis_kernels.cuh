@@ -809,6 +809,8 @@ struct WelchArgs {
     int detrend;           // 1: subtract the segment's mean before the window
     int window_id;         // direct kernel: window evaluated in the kernel
     double* out_db;        // [sig][N], fft-shifted
+    int* ticket;           // welch_accum_mid_kernel: task counter (zeroed before the launch); a task = (signal, split)
+    int n_tasks;           // signals x nsplit
 };
 
 template <typename T> __device__ __forceinline__ cpx<T> welch_load(const WelchSig& sg, long long i) {
@@ -927,7 +929,18 @@ welch_accum_mid_kernel(const WelchArgs a) {
         seed.q_lo = seed.om; seed.q_hi = seed.om;
     }
     const TwPair<float>* t1_row = t1 + (t % R0);
-    const WelchSig sg = a.sigs[blockIdx.y];
+    // Persistent CTAs: the tables above are set up once per CTA, then the CTA draws (signal, split) tasks from a ticket
+    // counter until none is left (C3: 1000 tasks on 148 CTAs; with one CTA per task the table setup, the CTA launch and
+    // the tail of every CTA were ~4 % of the step).  A task's partial spectrum does not depend on which CTA computes it.
+    __shared__ int s_task;
+  for (;;) {
+    __syncthreads();                                         // the previous task is done with the exchange buffers and s_task
+    if (threadIdx.x == 0) s_task = atomicAdd(a.ticket, 1);
+    __syncthreads();
+    const int task = s_task;
+    if (task >= a.n_tasks) break;
+    const int task_sig = task / a.nsplit, task_split = task - task_sig * a.nsplit;
+    const WelchSig sg = a.sigs[task_sig];
     // 128-bit loads: FP32 rows whose every slice start is 16-byte aligned (S t is even for every plan; hop and row start must be)
     const bool vec = sg.f32 && ((reinterpret_cast<uintptr_t>(sg.f32) & 15) == 0) && ((a.hop & 1) == 0);
     float acc[P];
@@ -936,7 +949,7 @@ welch_accum_mid_kernel(const WelchArgs a) {
     const long long stride = (long long)a.nsplit * FPC;
     const long long iters = (sg.nseg + stride - 1) / stride;
     for (long long it = 0; it < iters; it++) {
-        const long long seg = it * stride + (long long)blockIdx.x * FPC + fl;
+        const long long seg = it * stride + (long long)task_split * FPC + fl;
         const bool valid = seg < sg.nseg;
         // a slot whose segment does not exist skips the transform: the slots of a CTA synchronise on their own named
         // barriers (one slot per CTA: the test is CTA-uniform), only the mean removal uses CTA-wide barriers.  29
@@ -1006,10 +1019,11 @@ welch_accum_mid_kernel(const WelchArgs a) {
         }
     }
     if (fl == 0) {
-        float* part = reinterpret_cast<float*>(a.partial) + ((size_t)blockIdx.y * a.nsplit + blockIdx.x) * N;
+        float* part = reinterpret_cast<float*>(a.partial) + (size_t)task * N;
 #pragma unroll
         for (int q = 0; q < P; q++) part[t + TPF * q] = acc[q];
     }
+  }
 }
 
 // sums the partial spectra in a fixed order (deterministic), scales, dB, fft-shift
