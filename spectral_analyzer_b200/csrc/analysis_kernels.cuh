@@ -929,6 +929,14 @@ welch_accum_mid_kernel(const WelchArgs a) {
         seed.q_lo = seed.om; seed.q_hi = seed.om;
     }
     const TwPair<float>* t1_row = t1 + (t % R0);
+#ifndef SA_WELCH_REC1
+#define SA_WELCH_REC1 1
+#endif
+    TwSeed<float> seed1;                                     // pass-1 twiddle recurrence: om = W^(t mod R0), oh = om^16
+    {
+        const TwPair<float> m0 = ldg_tw<true>(t1_row), m1 = ldg_tw<true>(t1_row + R0);
+        seed1.om = m1.lo; seed1.oh = m0.hi; seed1.q_lo = seed1.om; seed1.q_hi = seed1.om;
+    }
     // Persistent CTAs: the tables above are set up once per CTA, then the CTA draws (signal, split) tasks from a ticket
     // counter until none is left (C3: 1000 tasks on 148 CTAs; with one CTA per task the table setup, the CTA launch and
     // the tail of every CTA were ~4 % of the step).  A task's partial spectrum does not depend on which CTA computes it.
@@ -993,7 +1001,7 @@ welch_accum_mid_kernel(const WelchArgs a) {
 #pragma unroll
             for (int q = 0; q < P; q++) { v[q].x -= m.x; v[q].y -= m.y; }
         }
-        mid_fft<N, true>(v, t, fl, sm, win, t1_row, seed);
+        mid_fft<N, true, SA_WELCH_REC1 != 0>(v, t, fl, sm, win, t1_row, seed, &seed1);
         if (valid) {
 #pragma unroll
             for (int q = 0; q < P; q++) acc[q] += __fmaf_rn(v[q].x, v[q].x, v[q].y * v[q].y);

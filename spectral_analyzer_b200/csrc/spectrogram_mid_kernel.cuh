@@ -179,10 +179,13 @@ __device__ __forceinline__ void mid_decode_staged(const LoadParams& lp, const un
 // The three passes of the small-radix-first plan on the registers of one frame.  In: v[i + S*m] = sample
 // m*(N/R0) + S*t + i (already decoded); out: v[q] = X[t + TPF*q].  `sm` is the frame's exchange buffer, `win` the
 // thread's window row (pair order), `t1_row` = pass-1 twiddle pairs + (t mod R0), seed = (W_N^t, W_N^(16 t)).
-template <int N, bool WIN>
+// REC1: the pass-1 twiddles W_{32 R0}^{(t mod R0) m} come from a packed register recurrence seeded by `seed1`
+// (om = the m = 1 entry of the thread's table column, oh = om^16) instead of 16 LDS.128 per frame -- for callers bound by
+// the shared-memory pipe (the Welch kernel: LSU wavefronts 68 %, FMA pipe 47 %).
+template <int N, bool WIN, bool REC1 = false>
 __device__ __forceinline__ void mid_fft_front(float2 (&v)[32], const int t, const int fl, float2* __restrict__ sm,
                                               const float* __restrict__ win, const TwPair<float>* __restrict__ t1_row,
-                                              const TwSeed<float>& seed) {
+                                              const TwSeed<float>& seed, const TwSeed<float>* seed1 = nullptr) {
     using G = MidGeo<N>;
     constexpr int P = 32, R0 = G::R0, S = G::S, TPF = G::TPF, FPC = G::FPC;
     // pass 0: S radix-R0 butterflies on v[i + S*m]
@@ -200,7 +203,8 @@ __device__ __forceinline__ void mid_fft_front(float2 (&v)[32], const int t, cons
     for (int q = 0; q < P; q++) v[q] = sm[mid_pad(t) + q * (TPF + TPF / 32)];
 
     // pass 1: radix 32, Ns = R0
-    radix_fft<float, 32, 1, 0, P, MUL_CPX, true>(v, nullptr, t1_row, R0, seed);
+    if constexpr (REC1) radix_fft<float, 32, 1, 0, P, MUL_REC, false>(v, nullptr, nullptr, 0, *seed1);
+    else radix_fft<float, 32, 1, 0, P, MUL_CPX, true>(v, nullptr, t1_row, R0, seed);
     mid_sync<TPF, FPC>(fl);
     {
         float2* dst = sm + (t / R0) * (33 * R0) + (t % R0);
@@ -217,11 +221,11 @@ __device__ __forceinline__ void mid_fft_back(float2 (&v)[32], const TwSeed<float
     radix_fft<float, 32, 1, 0, 32, MUL_REC, false>(v, nullptr, nullptr, 0, seed);
 }
 
-template <int N, bool WIN>
+template <int N, bool WIN, bool REC1 = false>
 __device__ __forceinline__ void mid_fft(float2 (&v)[32], const int t, const int fl, float2* __restrict__ sm,
                                         const float* __restrict__ win, const TwPair<float>* __restrict__ t1_row,
-                                        const TwSeed<float>& seed) {
-    mid_fft_front<N, WIN>(v, t, fl, sm, win, t1_row, seed);
+                                        const TwSeed<float>& seed, const TwSeed<float>* seed1 = nullptr) {
+    mid_fft_front<N, WIN, REC1>(v, t, fl, sm, win, t1_row, seed, seed1);
     mid_fft_back(v, seed);
 }
 
