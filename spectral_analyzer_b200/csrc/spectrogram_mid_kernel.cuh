@@ -31,6 +31,9 @@
 
 namespace sa {
 
+#ifndef SA_MID_REC1_MIN_N
+#define SA_MID_REC1_MIN_N 8192
+#endif
 template <int N> struct MidGeo {
     static constexpr int P = 32, R0 = N / 1024, S = P / R0, TPF = N / P;
     // FPC consecutive frames per CTA step (16 warps; measured per size: 2048 -> 512 threads (C4 4.85 -> 4.76 ms); 4096 -> 512 threads together with the
@@ -281,6 +284,13 @@ spectrogram_mid_kernel(const SpecArgs a) {
         seed.oh = __ldg(&root[(16 * t) & (N - 1)]);
     }
     const TwPair<float>* t1_row = t1 + (t % R0);
+    // pass-1 twiddles by register recurrence (mid_fft_front REC1) for the sizes listed in SA_MID_REC1_MIN_N and up
+    constexpr bool kRec1 = N >= SA_MID_REC1_MIN_N;
+    TwSeed<float> seed1;
+    {
+        const TwPair<float> m0 = ldg_tw<true>(t1_row), m1 = ldg_tw<true>(t1_row + R0);
+        seed1.om = m1.lo; seed1.oh = m0.hi; seed1.q_lo = seed1.om; seed1.q_hi = seed1.om;
+    }
 
     const long long n_blocks = (a.n_frames + FPC - 1) / FPC;
     const int new_bytes = (int)(a.hop < N ? a.hop : N) * bps;
@@ -323,7 +333,7 @@ spectrogram_mid_kernel(const SpecArgs a) {
             else           mid_load_frame<DK, N, false>(a.lp, base + s0 * bps, t, v);
         }
 
-        mid_fft_front<N, WIN>(v, t, fl, sm, win, t1_row, seed);
+        mid_fft_front<N, WIN, kRec1>(v, t, fl, sm, win, t1_row, seed, &seed1);
         if constexpr (PF) {
             mid_sync<TPF, FPC>(fl);                                        // the exchange buffer has been read back by everyone
             if (readable_f(nf)) mid_stage_frame<DK, N>(base + (a.start_sample + nf * a.hop) * bps, t, sm_addr);
